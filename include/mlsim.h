@@ -1,0 +1,113 @@
+/*
+ * mlsim.h -- C ABI of the B200-native rollout hot path (solver step + learned correction).
+ *
+ * The reference (BigBalloon8/ml-accelerated-simulation) is pure Python and has no FFI; the boundary it
+ * exposes for this path is the Python call surface of torch_cfd plus src/models.  Each entry point
+ * below names the reference call it stands in for.  Conventions:
+ *   - return 0 on success, a negative MLSIM_E* code otherwise; no exceptions cross the ABI;
+ *     mlsim_last_error() returns a thread-local message for the last failure;
+ *   - field pointers are DEVICE pointers to contiguous fp32 arrays [batch][nx][ny] (axis 0 = x,
+ *     axis 1 = y contiguous: the reference's GridVariable.data layout, src/data_generation.py:219-220),
+ *     16-byte aligned, owned by the caller; everything else is owned by the plan;
+ *   - all device work is enqueued on the cudaStream_t passed as `stream` (void*), stream-ordered, with
+ *     no hidden synchronisation, except the *_host entry points which synchronise before returning;
+ *   - a plan is not thread-safe; distinct plans are independent.  One plan == one device.
+ */
+#ifndef MLSIM_H
+#define MLSIM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLSIM_OK            0
+#define MLSIM_EINVAL       -1   /* bad argument / unsupported configuration */
+#define MLSIM_ECUDA        -2   /* CUDA runtime error (message has the detail) */
+#define MLSIM_ENOMEM       -3
+#define MLSIM_ESTATE       -4   /* call out of order (e.g. cnn not finalised) */
+
+#define MLSIM_ADV_VAN_LEER      0
+#define MLSIM_ADV_UPWIND        1
+#define MLSIM_ADV_LAX_WENDROFF  2
+
+typedef struct mlsim_plan mlsim_plan;
+
+/* Geometry + physics of one rollout.  Stands in for the objects built at src/inference.py:54-93:
+ * grids.Grid((nx,ny), domain=((0,lx),(0,ly))), stable_time_step(...) -> dt,
+ * NavierStokes2DFVMProjection(viscosity, density, drag, forcing=KolmogorovForcing(wave_number, scale)). */
+typedef struct {
+  int32_t nx, ny, batch;          /* powers of two, 64 <= n <= 2048 (batch >= 1) */
+  double  lx, ly;                 /* domain lengths (reference: 2*pi) */
+  double  dt;                     /* full RK4 step */
+  double  viscosity, density, drag;
+  int32_t forcing_wavenumber;     /* KolmogorovForcing wave_number (src/inference.py:81) */
+  double  forcing_scale;          /* 1.0 in the reference; 0 disables forcing */
+  int32_t advection;              /* MLSIM_ADV_* (reference: van Leer) */
+  double  lw_dt_scale;            /* 1.0: Lax-Wendroff Courant number uses the full dt */
+  int32_t device;                 /* CUDA device ordinal */
+} mlsim_config;
+
+int  mlsim_plan_create (const mlsim_config* cfg, mlsim_plan** out);
+int  mlsim_plan_destroy(mlsim_plan* plan);
+
+/* ---- learned correction network: buildModel([CNN block]) of src/models/modelbuilder.py:5-31,
+ * src/models/CNN.py:24-40 (3x3, stride 1, zero padding 1, groups 1, ReLU between layers). ----
+ * mlsim_cnn_begin declares the layer count; mlsim_cnn_set_layer uploads one layer from HOST memory:
+ * w_oihw = Conv2d.weight [cout][cin][3][3], bias [cout], both fp64 (src_dtype 1, the reference's
+ * checkpoint dtype, src/train.py:50,56) or fp32 (src_dtype 0).  BatchNorm (bn:true configs) must be
+ * folded by the caller.  mlsim_cnn_finalize packs the weights to bf16 operand images on the device. */
+int  mlsim_cnn_begin    (mlsim_plan* plan, int32_t nlayers);
+int  mlsim_cnn_set_layer(mlsim_plan* plan, int32_t layer, int32_t cin, int32_t cout, int32_t ksize,
+                         const void* w_oihw, const void* bias, int32_t src_dtype, int32_t relu_after);
+int  mlsim_cnn_finalize (mlsim_plan* plan);
+
+/* Host-only helper (no CUDA call): pack one layer into the bf16 shared-memory operand image the kernels
+ * consume.  kind 0 = first layer, 1 = hidden layer, 2 = last layer.  out == NULL returns the byte size. */
+int64_t mlsim_cnn_pack_host(int32_t kind, int32_t cin, int32_t cout, const double* w_oihw, const double* bias,
+                            void* out, int64_t out_bytes);
+
+/* ---- the hot loop, src/inference.py:100-102:
+ *        v, p = step_fn.forward(v, dt, equation=ns2d);  v += model(v)
+ * nsteps iterations in place on (u, v).  p_or_null receives the pseudo-pressure of the last
+ * projection of the last step.  apply_cnn=0 gives the bare solver step used by
+ * src/data_generation.py:206,211,212 and test/sim_test.py:81. */
+int  mlsim_step(mlsim_plan* plan, float* u, float* v, float* p_or_null, int32_t nsteps,
+                int32_t apply_cnn, double cnn_input_scale, void* stream);
+
+/* Same loop through HOST buffers (pinned or pageable): H2D of (u, v), nsteps, D2H of (u, v) and
+ * optionally p, synchronised on return.  This is the end-to-end call bench.py times as `e2e`. */
+int  mlsim_rollout_host(mlsim_plan* plan, float* host_u, float* host_v, float* host_p_or_null,
+                        int32_t nsteps, int32_t apply_cnn, double cnn_input_scale);
+
+/* ---- pieces of the step, exposed for parity tests ---- */
+/* F(u,v;dt): NavierStokes2DFVMProjection.explicit_terms */
+int  mlsim_explicit_terms(mlsim_plan* plan, const float* u, const float* v, float* du, float* dv, void* stream);
+/* P(u,v): ...pressure_projection (App. A.4), in place; p_or_null optional */
+int  mlsim_project(mlsim_plan* plan, float* u, float* v, float* p_or_null, void* stream);
+/* fdm.divergence(v) (test/sim_test.py:42) */
+int  mlsim_divergence(mlsim_plan* plan, const float* u, const float* v, float* div, void* stream);
+/* y = model(stack((u,v),1) * input_scale): y is [batch][cout_last][nx][ny] fp32 (NCHW) */
+int  mlsim_cnn_forward(mlsim_plan* plan, const float* u, const float* v, float* y_nchw,
+                       double cnn_input_scale, void* stream);
+/* u += y[:,0]; v += y[:,1] with y = model(...) -- the fused correction-add of src/inference.py:102 */
+int  mlsim_cnn_correct(mlsim_plan* plan, float* u, float* v, double cnn_input_scale, void* stream);
+
+/* ---- introspection ---- */
+/* number of kernel launches one mlsim_step(nsteps=1) issues (solver only, or solver + cnn) */
+int  mlsim_launches_per_step(mlsim_plan* plan, int32_t apply_cnn);
+/* bytes of device workspace owned by the plan */
+int64_t mlsim_workspace_bytes(mlsim_plan* plan);
+/* time one kernel class in isolation with CUDA events on `stream`: which = 0 explicit terms (stage 2
+ * form), 1 div+row FFT, 2 column solve, 3 row iFFT+gradient, 4 first conv, 5 one mid conv layer,
+ * 6 last conv + correction add.  Runs `iters` launches after `warmup`, returns mean ms in *ms_out. */
+int  mlsim_time_kernel(mlsim_plan* plan, int32_t which, int32_t warmup, int32_t iters, float* ms_out, void* stream);
+
+const char* mlsim_last_error(void);
+const char* mlsim_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLSIM_H */

@@ -1,0 +1,62 @@
+// Shared host/device helpers for the mlsim sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/mlsim.h"
+
+namespace mlsim {
+
+void set_error(const std::string& msg);
+
+#define MLSIM_CUDA_CHECK(expr)                                                          \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      ::mlsim::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));           \
+      return MLSIM_ECUDA;                                                               \
+    }                                                                                   \
+  } while (0)
+
+#define MLSIM_REQUIRE(cond, msg)                                                        \
+  do {                                                                                  \
+    if (!(cond)) {                                                                      \
+      ::mlsim::set_error(std::string(msg) + " [" #cond "]");                            \
+      return MLSIM_EINVAL;                                                              \
+    }                                                                                   \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Solver parameters handed to the kernels by value.
+struct SolverParams {
+  int nx, ny, batch;
+  int nyc;        // ny/2 + 1 spectral columns
+  int nycp;       // padded pitch of the spectral buffer (float2 units)
+  float inv_hx, inv_hy;       // 1/h
+  float nu_hx2, nu_hy2;       // (viscosity/density)/h^2
+  float dt_hx, dt_hy;         // lw_dt_scale*dt/h  (Courant factor)
+  float drag;
+  int advection;
+};
+
+// Stage coefficients of the RK4-with-projection scheme.
+//   mode 0: du,dv = F                       (test hook)
+//   mode 1: acc = u0 + ca*k ; ustar = u0 + cs*k            (stage 1: u_s == u0)
+//   mode 2: acc = acc + ca*k ; ustar = u0 + cs*k           (stages 2,3)
+//   mode 3: ustar = acc + cs*k                              (stage 4)
+struct StageArgs {
+  const float* us; const float* vs;   // state the explicit terms are evaluated on
+  const float* u0; const float* v0;   // state at the start of the step
+  float* accu; float* accv;           // running sum u0 + dt*sum(b_j k_j)
+  float* outu; float* outv;           // ustar (or du,dv in mode 0)
+  float ca, cs;
+  int mode;
+};
+
+static inline int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+static inline bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
+}  // namespace mlsim

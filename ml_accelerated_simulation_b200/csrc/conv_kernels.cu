@@ -1,0 +1,440 @@
+// Learned-correction CNN (reference src/models/CNN.py:36-40 as built by buildModel, MLACFD.json):
+// 3x3 / stride 1 / zero-padding 1 convolutions as implicit GEMMs on the 5th-gen tensor cores
+// (tcgen05.mma, bf16 operands, fp32 accumulators in TMEM).
+//
+// Activation layout in HBM (plan-owned, bf16):  act[b][x][c8][yp][8]
+//   c8 = channel/8 (8 planes), yp = y+1 in [0, ny+2) with zero halo columns yp=0 and yp=ny+1,
+//   innermost 8 channels = one 16-byte granule.  A row-plane (fixed b,x,c8) is contiguous along y, so
+//   * an input row tile [130 pixels][64 ch] is 8 bulk copies (UBLKCP) of 2080 contiguous bytes, and it
+//     lands in shared memory directly in the UMMA "no-swizzle K-major" canonical layout
+//     (pixel stride 16 B, 8-pixel group stride SBO = 128 B, channel-chunk stride LBO = 2080 B);
+//   * the +-1 pixel shifts of the 3x3 stencil along y are just +-16 B on the descriptor start address;
+//   * epilogue stores are 16 B per thread, 512 contiguous bytes per warp.
+//
+// Mid layers are "input stationary": one staged input row X feeds the three output rows X-1, X, X+1 in
+// ONE MMA of N = 3*64 (B operand = [W(dx=+1); W(dx=0); W(dx=-1)] stacked along N) whose accumulator
+// columns are three adjacent 64-column TMEM slots of an 8-slot ring.  Per input row: 3 (dy) x 4 (K16)
+// MMAs of M=128 x N=192 x K=16; shared-memory operand traffic 10 KB per 96 tensor-clocks.
+#include "common.cuh"
+#include "tc05.cuh"
+#include "conv_kernels.h"
+
+namespace mlsim {
+
+using namespace tc;
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// =============================================================================================
+// First layer: 2 -> 64 channels.  K = 9 taps * 2 ch = 18, zero padded to 32 (two K16 MMAs).
+// The im2col A tile is built by the threads from the fp32 state (fusing stack((u,v),1), the input
+// scale and the fp32 -> bf16 conversion), so this kernel is HBM-bound on its 128 B/pixel output.
+// =============================================================================================
+constexpr int CF_THREADS = 128;
+constexpr int CF_LBO_A = 128 * 16;     // chunk plane stride of the A tile
+constexpr int CF_LBO_B = 64 * 16;      // chunk plane stride of the weight image
+constexpr int CF_WBYTES = 4 * CF_LBO_B;
+
+__global__ void __launch_bounds__(CF_THREADS)
+k_conv_first(ConvFirstArgs a) {
+  __shared__ __align__(128) uint8_t sA[4 * CF_LBO_A];
+  __shared__ __align__(128) uint8_t sW[CF_WBYTES];
+  __shared__ float sBias[64];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < CF_WBYTES / 16; i += CF_THREADS)
+    reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(a.wimg) + i);
+  if (tid < 64) sBias[tid] = __ldg(reinterpret_cast<const float*>(a.wimg + CF_WBYTES) + tid);
+  if (tid == 0) {
+    mbar_init(&mbar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_slot, 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t idesc = umma_idesc_bf16(64);
+
+  const int nyt = (a.ny + 127) >> 7;
+  const int ntiles = a.batch * a.nx * nyt;
+  const size_t plane = (size_t)(a.ny + 2);
+  uint32_t parity = 0;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int yt = tile % nyt;
+    const int x = (tile / nyt) % a.nx;
+    const int b = tile / (nyt * a.nx);
+    const int y = yt * 128 + tid;
+
+    // ---- im2col row of this pixel: k = (i*3 + j)*2 + ch, i <-> dx+1, j <-> dy+1 ----
+    float val[18];
+    const float* __restrict__ gu = a.u + (size_t)b * a.nx * a.ny;
+    const float* __restrict__ gv = a.v + (size_t)b * a.nx * a.ny;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int xx = x + i - 1;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int yy = y + j - 1;
+        const bool in = (xx >= 0) && (xx < a.nx) && (yy >= 0) && (yy < a.ny);
+        const size_t off = (size_t)xx * a.ny + yy;
+        val[(i * 3 + j) * 2 + 0] = in ? __ldg(gu + off) * a.scale : 0.0f;
+        val[(i * 3 + j) * 2 + 1] = in ? __ldg(gv + off) * a.scale : 0.0f;
+      }
+    }
+    uint4 c0, c1, c2;
+    c0.x = pack_bf16(val[0], val[1]);   c0.y = pack_bf16(val[2], val[3]);
+    c0.z = pack_bf16(val[4], val[5]);   c0.w = pack_bf16(val[6], val[7]);
+    c1.x = pack_bf16(val[8], val[9]);   c1.y = pack_bf16(val[10], val[11]);
+    c1.z = pack_bf16(val[12], val[13]); c1.w = pack_bf16(val[14], val[15]);
+    c2.x = pack_bf16(val[16], val[17]); c2.y = 0u; c2.z = 0u; c2.w = 0u;
+    *reinterpret_cast<uint4*>(sA + 0 * CF_LBO_A + tid * 16) = c0;
+    *reinterpret_cast<uint4*>(sA + 1 * CF_LBO_A + tid * 16) = c1;
+    *reinterpret_cast<uint4*>(sA + 2 * CF_LBO_A + tid * 16) = c2;
+    *reinterpret_cast<uint4*>(sA + 3 * CF_LBO_A + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();           // generic-proxy writes -> visible to the tensor core (async proxy)
+    __syncthreads();
+
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k16 = 0; k16 < 2; ++k16) {
+        const uint64_t da = umma_desc(smem_u32(sA) + k16 * 2 * CF_LBO_A, CF_LBO_A, 128);
+        const uint64_t db = umma_desc(smem_u32(sW) + k16 * 2 * CF_LBO_B, CF_LBO_B, 128);
+        umma_bf16(tmem, da, db, idesc, k16 > 0);
+      }
+      umma_commit(&mbar);
+    }
+    mbar_wait(&mbar, parity);
+    parity ^= 1;
+    tc_fence_after();
+
+    uint32_t r0[32], r1[32];
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    tmem_ld32(taddr, r0);
+    tmem_ld32(taddr + 32, r1);
+    tmem_ld_wait();
+
+    if (y < a.ny) {
+      uint8_t* orow = reinterpret_cast<uint8_t*>(a.out) +
+                      ((((size_t)b * a.nx + x) * 8) * plane + (size_t)(y + 1)) * 16;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int ch = c * 8 + e;
+          const float acc = __uint_as_float(ch < 32 ? r0[ch & 31] : r1[ch & 31]);
+          f[e] = fmaxf(acc + sBias[ch], 0.0f);
+        }
+        uint4 o;
+        o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+        o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+        *reinterpret_cast<uint4*>(orow + (size_t)c * plane * 16) = o;
+      }
+    }
+    tc_fence_before();
+    __syncthreads();                    // TMEM reads + smem A reuse ordered before the next tile's MMA
+  }
+
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc(tmem, 64);
+  }
+}
+
+// =============================================================================================
+// Mid / last layers: 64 -> NB channels per dx block (NB = 64 mid, 16 last).
+// Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer, warps 2..5 = epilogue.
+// =============================================================================================
+constexpr int CM_THREADS = 192;
+constexpr int CM_STAGES = 6;
+constexpr int CM_NPX = 130;
+constexpr int CM_PLANE = CM_NPX * 16;            // 2080 B: LBO of the A operand
+constexpr int CM_STAGE_BYTES = 8 * CM_PLANE;     // 16640 B
+constexpr int CM_SLOTS = 8;
+
+template <int NB> struct ConvMidSmem {
+  static constexpr int LBO_B = 3 * NB * 16;
+  static constexpr int WDY = 8 * LBO_B;
+  static constexpr int WBYTES = 3 * WDY;
+  static constexpr int BIAS_OFF = WBYTES;
+  static constexpr int STAGE_OFF = ((WBYTES + NB * 4 + 127) / 128) * 128;
+  static constexpr int BAR_OFF = STAGE_OFF + CM_STAGES * CM_STAGE_BYTES;
+  static constexpr int NBARS = 2 * CM_STAGES + 2 * CM_SLOTS + 1;
+  static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
+};
+
+template <int NB, bool LAST>
+__global__ void __launch_bounds__(CM_THREADS, 1)
+k_conv_mid(ConvMidArgs a) {
+  using L = ConvMidSmem<NB>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sW = smem;
+  const float* sBias = reinterpret_cast<const float*>(smem + L::BIAS_OFF);
+  uint8_t* sStage = smem + L::STAGE_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + CM_STAGES;
+  uint64_t* tfull = bars + 2 * CM_STAGES;
+  uint64_t* tempty = tfull + CM_SLOTS;
+  uint64_t* wbar = tempty + CM_SLOTS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + L::NBARS);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t TMEM_COLS = (NB * CM_SLOTS < 32) ? 32 : NB * CM_SLOTS;
+
+  if (tid == 0) {
+    for (int s = 0; s < CM_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < CM_SLOTS; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    mbar_init(wbar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int nyt = (a.ny + 127) >> 7;
+  const int nstrips = (a.nx + a.rs - 1) / a.rs;
+  const int nitems = a.batch * nstrips * nyt;
+  const size_t plane = (size_t)(a.ny + 2);
+
+  if (warp == 0) {
+    // ------------------------------ producer ------------------------------
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wbar, (uint32_t)(L::WBYTES + NB * 4));
+      {
+        // weight image + bias, in pieces of at most 32 KB
+        uint32_t off = 0;
+        const uint32_t total = L::WBYTES + NB * 4;
+        while (off < total) {
+          const uint32_t n = (total - off) > 32768u ? 32768u : (total - off);
+          bulk_g2s(sW + off, a.wimg + off, n, wbar);
+          off += n;
+        }
+      }
+      uint32_t m = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int yt = item % nyt;
+        const int strip = (item / nyt) % nstrips;
+        const int b = item / (nyt * nstrips);
+        const int x0 = strip * a.rs;
+        const int x1 = min(x0 + a.rs, a.nx);
+        const int xlo = max(x0 - 1, 0), xhi = min(x1, a.nx - 1);
+        const int y0 = yt * 128;
+        const int npx = min(CM_NPX, a.ny + 2 - y0);
+        const uint32_t bytes = (uint32_t)npx * 16u;
+        for (int X = xlo; X <= xhi; ++X, ++m) {
+          const uint32_t stage = m % CM_STAGES, use = m / CM_STAGES;
+          mbar_wait(&empty[stage], (use & 1) ^ 1);
+          mbar_arrive_expect_tx(&full[stage], 8 * bytes);
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.in) +
+                               ((((size_t)b * a.nx + X) * 8) * plane + (size_t)y0) * 16;
+          uint8_t* dst = sStage + stage * CM_STAGE_BYTES;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) bulk_g2s(dst + c * CM_PLANE, src + (size_t)c * plane * 16, bytes, &full[stage]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      mbar_wait(wbar, 0);
+      tc_fence_after();
+      const uint32_t wbase = smem_u32(sW);
+      uint32_t m = 0, nb = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int strip = (item / nyt) % nstrips;
+        const int x0 = strip * a.rs;
+        const int x1 = min(x0 + a.rs, a.nx);
+        const int xlo = max(x0 - 1, 0), xhi = min(x1, a.nx - 1);
+        for (int X = xlo; X <= xhi; ++X, ++m) {
+          const uint32_t stage = m % CM_STAGES, use = m / CM_STAGES;
+          const int lo = max(X - 1, x0), hi = min(X + 1, x1 - 1);
+          // rows whose accumulation starts with this input row need their TMEM slot drained
+          for (int x = lo; x <= hi; ++x) {
+            const bool is_new = (x == X + 1) || (x == X && X == 0);
+            if (is_new) {
+              const uint32_t n = nb + (uint32_t)(x - x0);
+              mbar_wait(&tempty[n % CM_SLOTS], ((n / CM_SLOTS) & 1) ^ 1);
+            }
+          }
+          mbar_wait(&full[stage], use & 1);
+          tc_fence_after();
+          const uint32_t abase = smem_u32(sStage + stage * CM_STAGE_BYTES);
+#pragma unroll 1
+          for (int dyi = 0; dyi < 3; ++dyi) {
+#pragma unroll 1
+            for (int k16 = 0; k16 < 4; ++k16) {
+              const bool first = (dyi == 0 && k16 == 0);
+              const uint64_t da = umma_desc(abase + dyi * 16 + k16 * 2 * CM_PLANE, CM_PLANE, 128);
+              int s0 = lo;
+              while (s0 <= hi) {
+                const uint32_t n0 = nb + (uint32_t)(s0 - x0);
+                const uint32_t slot0 = n0 % CM_SLOTS;
+                const bool new0 = (s0 == X + 1) || (s0 == X && X == 0);
+                int s1 = s0;
+                while (s1 + 1 <= hi) {
+                  const uint32_t slotn = (nb + (uint32_t)(s1 + 1 - x0)) % CM_SLOTS;
+                  if (slotn == 0) break;                               // ring wrap: columns not adjacent
+                  const bool newn = (s1 + 1 == X + 1) || (s1 + 1 == X && X == 0);
+                  if (first && newn != new0) break;                    // different accumulate flag
+                  ++s1;
+                }
+                const int nrows = s1 - s0 + 1;
+                const int bi = s0 - (X - 1);                           // dx block: 0 <-> dx=+1, 1 <-> 0, 2 <-> -1
+                const uint64_t db = umma_desc(wbase + dyi * L::WDY + k16 * 2 * L::LBO_B + bi * NB * 16, L::LBO_B, 128);
+                const uint32_t acc = first ? (new0 ? 0u : 1u) : 1u;
+                umma_bf16(tmem + slot0 * NB, da, db, umma_idesc_bf16(nrows * NB), acc);
+                s0 = s1 + 1;
+              }
+            }
+          }
+          umma_commit(&empty[stage]);                                  // smem stage free once the MMAs retire
+          if (X - 1 >= x0) umma_commit(&tfull[(nb + (uint32_t)(X - 1 - x0)) % CM_SLOTS]);
+          if (X == xhi && xhi == x1 - 1) umma_commit(&tfull[(nb + (uint32_t)(X - x0)) % CM_SLOTS]);
+        }
+        nb += (uint32_t)(x1 - x0);
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (4 warps = 128 TMEM lanes) ------------------------------
+    const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
+    mbar_wait(wbar, 0);                               // bias lives behind the weight image
+    uint32_t nb = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int yt = item % nyt;
+      const int strip = (item / nyt) % nstrips;
+      const int b = item / (nyt * nstrips);
+      const int x0 = strip * a.rs;
+      const int x1 = min(x0 + a.rs, a.nx);
+      const int y = yt * 128 + quarter * 32 + lane;
+      for (int x = x0; x < x1; ++x) {
+        const uint32_t n = nb + (uint32_t)(x - x0);
+        const uint32_t slot = n % CM_SLOTS;
+        mbar_wait(&tfull[slot], (n / CM_SLOTS) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + slot * NB;
+        if constexpr (!LAST) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(taddr, r0);
+          tmem_ld32(taddr + 32, r1);
+          tmem_ld_wait();
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&tempty[slot]);
+          if (y < a.ny) {
+            uint8_t* orow = reinterpret_cast<uint8_t*>(a.out) +
+                            ((((size_t)b * a.nx + x) * 8) * plane + (size_t)(y + 1)) * 16;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int ch = c * 8 + e;
+                const float acc = __uint_as_float(ch < 32 ? r0[ch & 31] : r1[ch & 31]);
+                f[e] = acc + sBias[ch];
+                if (a.relu) f[e] = fmaxf(f[e], 0.0f);
+              }
+              uint4 o;
+              o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+              o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+              *reinterpret_cast<uint4*>(orow + (size_t)c * plane * 16) = o;
+            }
+          }
+        } else {
+          uint32_t r[16];
+          tmem_ld16(taddr, r);
+          tmem_ld_wait();
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&tempty[slot]);
+          if (y < a.ny) {
+            const size_t off = ((size_t)b * a.nx + x) * a.ny + y;
+            if (a.y_nchw != nullptr) {
+              const size_t img = (size_t)a.nx * a.ny;
+#pragma unroll
+              for (int co = 0; co < 16; ++co)
+                if (co < a.cout)
+                  a.y_nchw[((size_t)b * a.cout + co) * img + (size_t)x * a.ny + y] = __uint_as_float(r[co]) + sBias[co];
+            } else {
+              // fused correction add (reference src/inference.py:102): v += model(v)
+              a.u[off] += __uint_as_float(r[0]) + sBias[0];
+              a.v[off] += __uint_as_float(r[1]) + sBias[1];
+            }
+          }
+        }
+      }
+      nb += (uint32_t)(x1 - x0);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+// =============================================================================================
+// launchers
+// =============================================================================================
+int launch_conv_first(const ConvFirstArgs& a, int sm_count, cudaStream_t st) {
+  const int nyt = (a.ny + 127) / 128;
+  const long ntiles = (long)a.batch * a.nx * nyt;
+  int grid = (int)(ntiles < (long)sm_count * 6 ? ntiles : (long)sm_count * 6);
+  k_conv_first<<<grid, CF_THREADS, 0, st>>>(a);
+  MLSIM_CUDA_CHECK(cudaGetLastError());
+  return MLSIM_OK;
+}
+
+int conv_pick_strip(int nx, int ny, int batch, int sm_count) {
+  const int nyt = (ny + 127) / 128;
+  int rs = nx < 32 ? nx : 32;
+  while (rs > 4 && (long)batch * ((nx + rs - 1) / rs) * nyt < 2L * sm_count) rs >>= 1;
+  return rs;
+}
+
+template <int NB, bool LAST>
+static int launch_conv_mid_t(const ConvMidArgs& a, int sm_count, cudaStream_t st) {
+  using L = ConvMidSmem<NB>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MLSIM_CUDA_CHECK(cudaFuncSetAttribute(k_conv_mid<NB, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_done = true;
+  }
+  const int nyt = (a.ny + 127) / 128;
+  const int nstrips = (a.nx + a.rs - 1) / a.rs;
+  const long nitems = (long)a.batch * nstrips * nyt;
+  const int grid = (int)(nitems < sm_count ? nitems : sm_count);
+  k_conv_mid<NB, LAST><<<grid, CM_THREADS, L::TOTAL, st>>>(a);
+  MLSIM_CUDA_CHECK(cudaGetLastError());
+  return MLSIM_OK;
+}
+
+int launch_conv_mid(const ConvMidArgs& a, int sm_count, cudaStream_t st) {
+  return launch_conv_mid_t<64, false>(a, sm_count, st);
+}
+int launch_conv_last(const ConvMidArgs& a, int sm_count, cudaStream_t st) {
+  return launch_conv_mid_t<16, true>(a, sm_count, st);
+}
+
+int conv_first_wimg_bytes() { return CF_WBYTES + 64 * 4; }
+int conv_mid_wimg_bytes() { return ConvMidSmem<64>::WBYTES + 64 * 4; }
+int conv_last_wimg_bytes() { return ConvMidSmem<16>::WBYTES + 16 * 4; }
+
+}  // namespace mlsim

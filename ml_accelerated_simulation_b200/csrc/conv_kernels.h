@@ -1,0 +1,35 @@
+// Launchers of the correction-CNN kernels (definitions in conv_kernels.cu).
+#pragma once
+#include "common.cuh"
+
+namespace mlsim {
+
+struct ConvFirstArgs {
+  const float* u; const float* v;     // fp32 state [batch][nx][ny]
+  __nv_bfloat16* out;                 // activation buffer act[b][x][8][ny+2][8]
+  const uint8_t* wimg;                // packed weights (conv_first_wimg_bytes)
+  float scale;                        // cnn_input_scale
+  int nx, ny, batch;
+};
+
+struct ConvMidArgs {
+  const __nv_bfloat16* in;            // activation buffer
+  __nv_bfloat16* out;                 // mid layers: activation buffer
+  float* u; float* v;                 // last layer, fused correction add (when y_nchw == nullptr)
+  float* y_nchw;                      // last layer, test hook output [batch][cout][nx][ny]
+  const uint8_t* wimg;                // packed weights + bias
+  int nx, ny, batch;
+  int rs;                             // output rows per work item (strip length)
+  int cout;                           // real output channels of this layer
+  int relu;
+};
+
+int launch_conv_first(const ConvFirstArgs& a, int sm_count, cudaStream_t st);
+int launch_conv_mid(const ConvMidArgs& a, int sm_count, cudaStream_t st);
+int launch_conv_last(const ConvMidArgs& a, int sm_count, cudaStream_t st);
+int conv_pick_strip(int nx, int ny, int batch, int sm_count);
+int conv_first_wimg_bytes();
+int conv_mid_wimg_bytes();
+int conv_last_wimg_bytes();
+
+}  // namespace mlsim

@@ -1,0 +1,139 @@
+// In-register power-of-two DFTs and Stockham autosort stage helpers used by the pressure-projection
+// kernels.  The index formulas are the ones validated in tests/test_fft_indexing.py (numpy model).
+//
+// One Stockham stage of radix R over a line of N complex points, Ns = product of the previous radices:
+//   thread j in [0, N/R):  k = j mod Ns
+//     v[r]  = in[j + r*N/R]                      r = 0..R-1
+//     v[r] *= exp(SIGN*2*pi*i * r*k / (Ns*R))
+//     V     = DFT_R(v)
+//     out[(j/Ns)*Ns*R + k + q*Ns] = V[q]         q = 0..R-1
+// After the last stage (Ns*R == N) the output is in natural order.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace mlsim {
+
+__host__ __device__ constexpr float cos16(int i) {
+  constexpr float t[16] = {1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
+                           0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f,
+                           -1.0f, -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f,
+                           0.0f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f};
+  return t[i & 15];
+}
+__host__ __device__ constexpr float sin16(int i) { return cos16(i - 4); }
+
+__host__ __device__ constexpr int bitrev(int i, int bits) {
+  int r = 0;
+  for (int b = 0; b < bits; ++b) r |= ((i >> b) & 1) << (bits - 1 - b);
+  return r;
+}
+__host__ __device__ constexpr int clog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+
+// One radix-2 butterfly level (sub-transform length LEN) of the in-register DIT network.
+template <int R, int SIGN, int LEN>
+__device__ __forceinline__ void dft_level(float2 (&a)[R]) {
+#pragma unroll
+  for (int b = 0; b < R; b += LEN) {
+#pragma unroll
+    for (int k = 0; k < LEN / 2; ++k) {
+      const int ti = k * (16 / LEN);            // twiddle angle 2*pi*ti/16
+      const float2 x = a[b + k + LEN / 2];
+      float2 t;
+      if (ti == 0) {
+        t = x;
+      } else if (ti == 4) {                      // w = SIGN * i
+        t = (SIGN > 0) ? make_float2(-x.y, x.x) : make_float2(x.y, -x.x);
+      } else {
+        const float c = (ti == 1) ? 0.92387953251128674f : (ti == 2) ? 0.70710678118654752f
+                      : (ti == 3) ? 0.38268343236508977f : (ti == 5) ? -0.38268343236508977f
+                      : (ti == 6) ? -0.70710678118654752f : -0.92387953251128674f;
+        const float sa = (ti == 1) ? 0.38268343236508977f : (ti == 2) ? 0.70710678118654752f
+                       : (ti == 3) ? 0.92387953251128674f : (ti == 5) ? 0.92387953251128674f
+                       : (ti == 6) ? 0.70710678118654752f : 0.38268343236508977f;
+        const float s = (SIGN > 0) ? sa : -sa;
+        t = make_float2(x.x * c - x.y * s, x.x * s + x.y * c);
+      }
+      const float2 y = a[b + k];
+      a[b + k + LEN / 2] = make_float2(y.x - t.x, y.y - t.y);
+      a[b + k] = make_float2(y.x + t.x, y.y + t.y);
+    }
+  }
+}
+
+// Natural-order in, natural-order out DFT of R in {2,4,8,16} points held in registers.
+// SIGN = -1 forward, +1 inverse (unnormalised).
+template <int R, int SIGN>
+__device__ __forceinline__ void dft_regs(float2 (&v)[R]) {
+  static_assert(R == 2 || R == 4 || R == 8 || R == 16, "radix");
+  constexpr int BITS = clog2(R);
+  float2 a[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) a[bitrev(i, BITS)] = v[i];
+  dft_level<R, SIGN, 2>(a);
+  if constexpr (R >= 4) dft_level<R, SIGN, 4>(a);
+  if constexpr (R >= 8) dft_level<R, SIGN, 8>(a);
+  if constexpr (R >= 16) dft_level<R, SIGN, 16>(a);
+#pragma unroll
+  for (int i = 0; i < R; ++i) v[i] = a[i];
+}
+
+// Multiply v[r] by the inter-stage twiddles.  tw[m] = exp(-2*pi*i*m/N), m in [0, N).
+template <int N, int R, int NS, int SIGN>
+__device__ __forceinline__ void stage_twiddle(float2 (&v)[R], int j, const float2* __restrict__ tw) {
+  if (NS == 1) return;
+  const int k = j & (NS - 1);
+  constexpr int STEP = N / (NS * R);
+#pragma unroll
+  for (int r = 1; r < R; ++r) {
+    float2 w = __ldg(&tw[r * k * STEP]);
+    if (SIGN > 0) w.y = -w.y;
+    const float2 x = v[r];
+    v[r] = make_float2(x.x * w.x - x.y * w.y, x.x * w.y + x.y * w.x);
+  }
+}
+
+// Output index base for thread j in a stage with sub-transform size NS and radix R.
+template <int R, int NS>
+__device__ __forceinline__ int stage_out_base(int j) {
+  return (j / NS) * NS * R + (j & (NS - 1));
+}
+
+// One complete shared-memory -> shared-memory stage for the thread's butterfly j (if j < N/R) on the
+// line at column offset `c` of a line-fastest buffer with line stride LS (float2 units).  Contains the
+// two __syncthreads() that make the in-place update safe; every thread of the block must call it.
+template <int N, int R, int NS, int SIGN>
+__device__ __forceinline__ void stage_smem(float2* buf, int LS, int c, int j, bool active,
+                                           const float2* __restrict__ tw) {
+  float2 v[R];
+  const bool on = active && (j < N / R);
+  if (on) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = buf[(j + r * (N / R)) * LS + c];
+  }
+  __syncthreads();
+  if (on) {
+    stage_twiddle<N, R, NS, SIGN>(v, j, tw);
+    dft_regs<R, SIGN>(v);
+    const int j0 = stage_out_base<R, NS>(j);
+#pragma unroll
+    for (int q = 0; q < R; ++q) buf[(j0 + q * NS) * LS + c] = v[q];
+  }
+  __syncthreads();
+}
+
+// Radix plans per transform length (R3 == 1 means two stages).  R1*R2*R3 == N.
+template <int N> struct FftPlan;
+template <> struct FftPlan<64>   { static constexpr int R1 = 8,  R2 = 8,  R3 = 1; };
+template <> struct FftPlan<128>  { static constexpr int R1 = 8,  R2 = 16, R3 = 1; };
+template <> struct FftPlan<256>  { static constexpr int R1 = 16, R2 = 16, R3 = 1; };
+template <> struct FftPlan<512>  { static constexpr int R1 = 8,  R2 = 8,  R3 = 8; };
+template <> struct FftPlan<1024> { static constexpr int R1 = 8,  R2 = 8,  R3 = 16; };
+template <> struct FftPlan<2048> { static constexpr int R1 = 8,  R2 = 16, R3 = 16; };
+
+template <int N> struct FftMinRadix {
+  using P = FftPlan<N>;
+  static constexpr int a = P::R1 < P::R2 ? P::R1 : P::R2;
+  static constexpr int value = (P::R3 > 1 && P::R3 < a) ? P::R3 : a;
+};
+
+}  // namespace mlsim

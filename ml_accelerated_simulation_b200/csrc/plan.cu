@@ -1,0 +1,538 @@
+// Plan management and the C ABI of include/mlsim.h.
+#include <math.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_kernels.h"
+#include "solver_kernels.h"
+
+namespace mlsim {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+struct CnnLayer {
+  int cin = 0, cout = 0, relu = 0;
+  std::vector<double> w, b;   // OIHW, bias
+  bool set = false;
+  uint8_t* d_wimg = nullptr;
+};
+
+}  // namespace mlsim
+
+using namespace mlsim;
+
+struct mlsim_plan {
+  mlsim_config cfg;
+  SolverParams sp;
+  int sm_count = 148;
+  size_t field_elems = 0;
+  int64_t ws_bytes = 0;
+  // solver tables / workspace
+  float* d_forcing = nullptr;
+  float* d_inv_eig = nullptr;
+  float2* d_twx = nullptr;
+  float2* d_twy = nullptr;
+  float* d_w1u = nullptr; float* d_w1v = nullptr;
+  float* d_w2u = nullptr; float* d_w2v = nullptr;
+  float* d_accu = nullptr; float* d_accv = nullptr;
+  float2* d_spec = nullptr;
+  // cnn
+  std::vector<CnnLayer> layers;
+  bool cnn_ready = false;
+  __nv_bfloat16* d_act[2] = {nullptr, nullptr};
+  size_t act_bytes = 0;
+  int rs = 32;
+  // host-rollout staging
+  float* d_hu = nullptr; float* d_hv = nullptr; float* d_hp = nullptr;
+  cudaStream_t own_stream = nullptr;
+  // timing scratch
+  float* d_tu = nullptr; float* d_tv = nullptr;
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(mlsim_plan* pl, T** p, size_t n) {
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+    return MLSIM_ENOMEM;
+  }
+  pl->ws_bytes += (int64_t)(n * sizeof(T));
+  return MLSIM_OK;
+}
+
+uint16_t f32_to_bf16_rne(float f) {
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  if ((x & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((x >> 16) | 0x40);   // NaN
+  const uint32_t lsb = (x >> 16) & 1u;
+  x += 0x7fffu + lsb;
+  return (uint16_t)(x >> 16);
+}
+
+int build_tables(mlsim_plan* pl) {
+  const mlsim_config& c = pl->cfg;
+  const int nx = c.nx, ny = c.ny, nyc = ny / 2 + 1;
+  const double hx = c.lx / nx, hy = c.ly / ny;
+  const double PI = 3.14159265358979323846;
+  std::vector<float> forcing(ny);
+  for (int j = 0; j < ny; ++j)
+    forcing[j] = (float)(c.forcing_scale * sin(c.forcing_wavenumber * (j + 0.5) * hy) / c.density);
+  // inverse spectrum of the periodic 5-point Laplacian, 1/(nx*ny) folded in.
+  // cutoff 10*eps(float64): the reference solves in fp64, so only the (0,0) mode is removed.
+  std::vector<float> inv((size_t)nx * nyc);
+  const double cutoff = 10.0 * 2.220446049250313e-16;
+  for (int kx = 0; kx < nx; ++kx) {
+    const double lx = (2.0 * cos(2.0 * PI * kx / nx) - 2.0) / (hx * hx);
+    for (int ky = 0; ky < nyc; ++ky) {
+      const double ly = (2.0 * cos(2.0 * PI * ky / ny) - 2.0) / (hy * hy);
+      const double lam = lx + ly;
+      inv[(size_t)kx * nyc + ky] = (fabs(lam) > cutoff) ? (float)(1.0 / lam / ((double)nx * ny)) : 0.0f;
+    }
+  }
+  std::vector<float2> twx(nx), twy(ny);
+  for (int m = 0; m < nx; ++m) twx[m] = make_float2((float)cos(2.0 * PI * m / nx), (float)(-sin(2.0 * PI * m / nx)));
+  for (int m = 0; m < ny; ++m) twy[m] = make_float2((float)cos(2.0 * PI * m / ny), (float)(-sin(2.0 * PI * m / ny)));
+
+  int rc;
+  if ((rc = dev_alloc(pl, &pl->d_forcing, ny))) return rc;
+  if ((rc = dev_alloc(pl, &pl->d_inv_eig, inv.size()))) return rc;
+  if ((rc = dev_alloc(pl, &pl->d_twx, nx))) return rc;
+  if ((rc = dev_alloc(pl, &pl->d_twy, ny))) return rc;
+  MLSIM_CUDA_CHECK(cudaMemcpy(pl->d_forcing, forcing.data(), ny * sizeof(float), cudaMemcpyHostToDevice));
+  MLSIM_CUDA_CHECK(cudaMemcpy(pl->d_inv_eig, inv.data(), inv.size() * sizeof(float), cudaMemcpyHostToDevice));
+  MLSIM_CUDA_CHECK(cudaMemcpy(pl->d_twx, twx.data(), nx * sizeof(float2), cudaMemcpyHostToDevice));
+  MLSIM_CUDA_CHECK(cudaMemcpy(pl->d_twy, twy.data(), ny * sizeof(float2), cudaMemcpyHostToDevice));
+  return MLSIM_OK;
+}
+
+int check_field(const void* p, const char* name) {
+  if (p == nullptr) {
+    set_error(std::string(name) + " is null");
+    return MLSIM_EINVAL;
+  }
+  if ((reinterpret_cast<uintptr_t>(p) & 15u) != 0) {
+    set_error(std::string(name) + " is not 16-byte aligned");
+    return MLSIM_EINVAL;
+  }
+  return MLSIM_OK;
+}
+
+// P(u,v) in place on (u,v): K2 -> K3 -> K4
+int project(mlsim_plan* pl, float* u, float* v, float* p_or_null, cudaStream_t st) {
+  int rc;
+  if ((rc = launch_div_rfft(u, v, pl->d_spec, pl->d_twy, pl->sp, st))) return rc;
+  if ((rc = launch_col_solve(pl->d_spec, pl->d_inv_eig, pl->d_twx, pl->sp, st))) return rc;
+  return launch_irfft_grad(pl->d_spec, u, v, u, v, p_or_null, pl->d_twy, pl->sp, st);
+}
+
+// One classic-RK4 step with a projection after every stage, in place on (u,v).
+int solver_step(mlsim_plan* pl, float* u, float* v, float* p_or_null, cudaStream_t st) {
+  const float dt = (float)pl->cfg.dt;
+  int rc;
+  StageArgs a;
+  a.u0 = u; a.v0 = v; a.accu = pl->d_accu; a.accv = pl->d_accv;
+  // stage 1: k1 = F(u0); acc = u0 + dt/6 k1; u* = u0 + dt/2 k1
+  a.us = u; a.vs = v; a.outu = pl->d_w1u; a.outv = pl->d_w1v;
+  a.ca = dt / 6.0f; a.cs = 0.5f * dt; a.mode = 1;
+  if ((rc = launch_explicit(a, pl->sp, pl->d_forcing, st))) return rc;
+  if ((rc = project(pl, pl->d_w1u, pl->d_w1v, nullptr, st))) return rc;
+  // stage 2: k2 = F(u1); acc += dt/3 k2; u* = u0 + dt/2 k2
+  a.us = pl->d_w1u; a.vs = pl->d_w1v; a.outu = pl->d_w2u; a.outv = pl->d_w2v;
+  a.ca = dt / 3.0f; a.cs = 0.5f * dt; a.mode = 2;
+  if ((rc = launch_explicit(a, pl->sp, pl->d_forcing, st))) return rc;
+  if ((rc = project(pl, pl->d_w2u, pl->d_w2v, nullptr, st))) return rc;
+  // stage 3: k3 = F(u2); acc += dt/3 k3; u* = u0 + dt k3
+  a.us = pl->d_w2u; a.vs = pl->d_w2v; a.outu = pl->d_w1u; a.outv = pl->d_w1v;
+  a.ca = dt / 3.0f; a.cs = dt; a.mode = 2;
+  if ((rc = launch_explicit(a, pl->sp, pl->d_forcing, st))) return rc;
+  if ((rc = project(pl, pl->d_w1u, pl->d_w1v, nullptr, st))) return rc;
+  // stage 4: k4 = F(u3); u* = acc + dt/6 k4  -> written over the caller's state, then projected
+  a.us = pl->d_w1u; a.vs = pl->d_w1v; a.outu = u; a.outv = v;
+  a.ca = 0.0f; a.cs = dt / 6.0f; a.mode = 3;
+  if ((rc = launch_explicit(a, pl->sp, pl->d_forcing, st))) return rc;
+  return project(pl, u, v, p_or_null, st);
+}
+
+// y = model(stack((u,v),1)*scale); either y_nchw (test hook) or fused u += y0, v += y1.
+int cnn_apply(mlsim_plan* pl, const float* u_in, const float* v_in, float* u, float* v, float* y_nchw, double scale,
+              cudaStream_t st) {
+  if (!pl->cnn_ready) {
+    set_error("correction network not finalised (mlsim_cnn_begin / set_layer / finalize)");
+    return MLSIM_ESTATE;
+  }
+  const mlsim_config& c = pl->cfg;
+  const int L = (int)pl->layers.size();
+  int rc;
+  ConvFirstArgs f;
+  f.u = u_in; f.v = v_in; f.out = pl->d_act[0]; f.wimg = pl->layers[0].d_wimg; f.scale = (float)scale;
+  f.nx = c.nx; f.ny = c.ny; f.batch = c.batch;
+  if ((rc = launch_conv_first(f, pl->sm_count, st))) return rc;
+  int cur = 0;
+  for (int l = 1; l < L; ++l) {
+    ConvMidArgs m;
+    m.in = pl->d_act[cur]; m.out = pl->d_act[cur ^ 1];
+    m.u = u; m.v = v; m.y_nchw = y_nchw;
+    m.wimg = pl->layers[l].d_wimg;
+    m.nx = c.nx; m.ny = c.ny; m.batch = c.batch; m.rs = pl->rs;
+    m.cout = pl->layers[l].cout; m.relu = pl->layers[l].relu;
+    if (l < L - 1) {
+      if ((rc = launch_conv_mid(m, pl->sm_count, st))) return rc;
+    } else {
+      if ((rc = launch_conv_last(m, pl->sm_count, st))) return rc;
+    }
+    cur ^= 1;
+  }
+  return MLSIM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mlsim_last_error(void) { return g_last_error.c_str(); }
+const char* mlsim_version(void) { return "mlsim-b200 0.1 (sm_100a)"; }
+
+int mlsim_plan_create(const mlsim_config* cfg, mlsim_plan** out) {
+  if (!cfg || !out) { set_error("null argument"); return MLSIM_EINVAL; }
+  *out = nullptr;
+  MLSIM_REQUIRE(is_pow2(cfg->nx) && cfg->nx >= 64 && cfg->nx <= 2048, "nx must be a power of two in [64, 2048]");
+  MLSIM_REQUIRE(is_pow2(cfg->ny) && cfg->ny >= 64 && cfg->ny <= 2048, "ny must be a power of two in [64, 2048]");
+  MLSIM_REQUIRE(cfg->batch >= 1 && cfg->batch <= 65535, "batch must be in [1, 65535]");
+  MLSIM_REQUIRE(cfg->lx > 0 && cfg->ly > 0 && cfg->dt > 0 && cfg->density > 0, "lx, ly, dt, density must be positive");
+  MLSIM_REQUIRE(cfg->advection >= 0 && cfg->advection <= 2, "unknown advection scheme");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error(std::string("no CUDA device: ") + cudaGetErrorString(e));
+    return MLSIM_ECUDA;
+  }
+  MLSIM_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "bad device ordinal");
+  MLSIM_CUDA_CHECK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  MLSIM_CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) {
+    set_error("this library contains sm_100a code only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+    return MLSIM_ECUDA;
+  }
+  mlsim_plan* pl = new mlsim_plan();
+  pl->cfg = *cfg;
+  pl->sm_count = prop.multiProcessorCount;
+  const double hx = cfg->lx / cfg->nx, hy = cfg->ly / cfg->ny;
+  SolverParams& sp = pl->sp;
+  sp.nx = cfg->nx; sp.ny = cfg->ny; sp.batch = cfg->batch;
+  sp.nyc = cfg->ny / 2 + 1;
+  sp.nycp = (sp.nyc + 3) & ~3;
+  sp.inv_hx = (float)(1.0 / hx); sp.inv_hy = (float)(1.0 / hy);
+  sp.nu_hx2 = (float)(cfg->viscosity / cfg->density / (hx * hx));
+  sp.nu_hy2 = (float)(cfg->viscosity / cfg->density / (hy * hy));
+  sp.dt_hx = (float)(cfg->lw_dt_scale * cfg->dt / hx);
+  sp.dt_hy = (float)(cfg->lw_dt_scale * cfg->dt / hy);
+  sp.drag = (float)cfg->drag;
+  sp.advection = cfg->advection;
+  pl->field_elems = (size_t)cfg->batch * cfg->nx * cfg->ny;
+
+  int rc = build_tables(pl);
+  const size_t n = pl->field_elems;
+  if (!rc) rc = dev_alloc(pl, &pl->d_w1u, n);
+  if (!rc) rc = dev_alloc(pl, &pl->d_w1v, n);
+  if (!rc) rc = dev_alloc(pl, &pl->d_w2u, n);
+  if (!rc) rc = dev_alloc(pl, &pl->d_w2v, n);
+  if (!rc) rc = dev_alloc(pl, &pl->d_accu, n);
+  if (!rc) rc = dev_alloc(pl, &pl->d_accv, n);
+  if (!rc) rc = dev_alloc(pl, &pl->d_spec, (size_t)cfg->batch * cfg->nx * sp.nycp);
+  if (!rc) {
+    cudaError_t e2 = cudaMemset(pl->d_spec, 0, (size_t)cfg->batch * cfg->nx * sp.nycp * sizeof(float2));
+    if (e2 != cudaSuccess) { set_error(cudaGetErrorString(e2)); rc = MLSIM_ECUDA; }
+  }
+  if (!rc) {
+    cudaError_t e2 = cudaStreamCreateWithFlags(&pl->own_stream, cudaStreamNonBlocking);
+    if (e2 != cudaSuccess) { set_error(cudaGetErrorString(e2)); rc = MLSIM_ECUDA; }
+  }
+  if (rc) { mlsim_plan_destroy(pl); return rc; }
+  *out = pl;
+  return MLSIM_OK;
+}
+
+int mlsim_plan_destroy(mlsim_plan* pl) {
+  if (!pl) return MLSIM_OK;
+  cudaSetDevice(pl->cfg.device);
+  cudaDeviceSynchronize();
+  void* ptrs[] = {pl->d_forcing, pl->d_inv_eig, pl->d_twx, pl->d_twy, pl->d_w1u, pl->d_w1v, pl->d_w2u, pl->d_w2v,
+                  pl->d_accu, pl->d_accv, pl->d_spec, pl->d_act[0], pl->d_act[1], pl->d_hu, pl->d_hv, pl->d_hp,
+                  pl->d_tu, pl->d_tv};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& l : pl->layers) if (l.d_wimg) cudaFree(l.d_wimg);
+  if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
+  delete pl;
+  return MLSIM_OK;
+}
+
+
+// Host-only: pack one conv layer (OIHW fp64 weights + bias) into the bf16 operand image the kernels
+// bulk-copy into shared memory.  kind 0 = first layer (K = 18 padded to 32, N = 64), 1 = mid layer
+// (NB = 64), 2 = last layer (NB = 16).  With out == nullptr returns the image size in bytes.
+int64_t mlsim_cnn_pack_host(int32_t kind, int32_t cin, int32_t cout, const double* w, const double* bias, void* out,
+                            int64_t out_bytes) {
+  const int64_t need = kind == 0 ? conv_first_wimg_bytes() : (kind == 1 ? conv_mid_wimg_bytes() : conv_last_wimg_bytes());
+  if (out == nullptr) return need;
+  if (out_bytes < need || !w || !bias || kind < 0 || kind > 2) { set_error("mlsim_cnn_pack_host: bad arguments"); return MLSIM_EINVAL; }
+  uint8_t* img = static_cast<uint8_t*>(out);
+  memset(img, 0, (size_t)need);
+  auto W = [&](int co, int ci, int i, int j) -> float {
+    if (co >= cout || ci >= cin) return 0.0f;
+    return (float)w[(((size_t)co * cin + ci) * 3 + i) * 3 + j];
+  };
+  uint16_t* q = reinterpret_cast<uint16_t*>(img);
+  int nbias;
+  if (kind == 0) {
+    // [chunk c (4)][n (64)][8] with k = c*8+e = (i*3+j)*2 + ch   (i <-> dx+1, j <-> dy+1)
+    for (int c = 0; c < 4; ++c)
+      for (int n = 0; n < 64; ++n)
+        for (int e = 0; e < 8; ++e) {
+          const int k = c * 8 + e;
+          float val = 0.0f;
+          if (k < 18) { const int tap = k / 2, ch = k % 2; val = W(n, ch, tap / 3, tap % 3); }
+          q[((size_t)c * 64 + n) * 8 + e] = f32_to_bf16_rne(val);
+        }
+    nbias = 64;
+  } else {
+    const int NB = (kind == 2) ? 16 : 64;
+    // [dy (3)][chunk c8 (8)][n = blk*NB + co (3*NB)][8]; blk 0,1,2 <-> dx = +1,0,-1 <-> kernel row i = 2,1,0
+    for (int dyi = 0; dyi < 3; ++dyi)
+      for (int c8 = 0; c8 < 8; ++c8)
+        for (int n = 0; n < 3 * NB; ++n)
+          for (int e = 0; e < 8; ++e) {
+            const int co = n % NB, blk = n / NB;
+            q[(((size_t)dyi * 8 + c8) * (3 * NB) + n) * 8 + e] = f32_to_bf16_rne(W(co, c8 * 8 + e, 2 - blk, dyi));
+          }
+    nbias = NB;
+  }
+  float* bq = reinterpret_cast<float*>(img + need - (int64_t)nbias * 4);
+  for (int i = 0; i < nbias; ++i) bq[i] = (i < cout) ? (float)bias[i] : 0.0f;
+  return need;
+}
+
+int mlsim_cnn_begin(mlsim_plan* pl, int32_t nlayers) {
+  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_REQUIRE(nlayers >= 2 && nlayers <= 64, "the tensor-core path needs 2..64 conv layers");
+  for (auto& l : pl->layers) if (l.d_wimg) { cudaFree(l.d_wimg); l.d_wimg = nullptr; }
+  pl->layers.assign(nlayers, CnnLayer());
+  pl->cnn_ready = false;
+  return MLSIM_OK;
+}
+
+int mlsim_cnn_set_layer(mlsim_plan* pl, int32_t layer, int32_t cin, int32_t cout, int32_t ksize, const void* w,
+                        const void* bias, int32_t src_dtype, int32_t relu_after) {
+  if (!pl || !w || !bias) { set_error("null argument"); return MLSIM_EINVAL; }
+  const int L = (int)pl->layers.size();
+  MLSIM_REQUIRE(layer >= 0 && layer < L, "layer index out of range (call mlsim_cnn_begin first)");
+  MLSIM_REQUIRE(ksize == 3, "only 3x3 / stride 1 / padding 1 convolutions are on the hot path");
+  MLSIM_REQUIRE(src_dtype == 0 || src_dtype == 1, "src_dtype: 0 = f32, 1 = f64");
+  if (layer == 0) MLSIM_REQUIRE(cin == 2 && cout >= 1 && cout <= 64, "first layer must be 2 -> (1..64) channels");
+  else if (layer == L - 1) MLSIM_REQUIRE(cin >= 1 && cin <= 64 && cout >= 1 && cout <= 16, "last layer must be (1..64) -> (1..16) channels");
+  else MLSIM_REQUIRE(cin >= 1 && cin <= 64 && cout >= 1 && cout <= 64, "hidden layers must be (1..64) -> (1..64) channels");
+  MLSIM_REQUIRE((relu_after != 0) == (layer != L - 1), "ReLU after every layer but the last (reference CNN.forward)");
+  CnnLayer& l = pl->layers[layer];
+  l.cin = cin; l.cout = cout; l.relu = relu_after ? 1 : 0;
+  const size_t nw = (size_t)cout * cin * 9;
+  l.w.resize(nw); l.b.resize(cout);
+  if (src_dtype == 1) {
+    memcpy(l.w.data(), w, nw * sizeof(double));
+    memcpy(l.b.data(), bias, cout * sizeof(double));
+  } else {
+    for (size_t i = 0; i < nw; ++i) l.w[i] = ((const float*)w)[i];
+    for (int i = 0; i < cout; ++i) l.b[i] = ((const float*)bias)[i];
+  }
+  l.set = true;
+  pl->cnn_ready = false;
+  return MLSIM_OK;
+}
+
+int mlsim_cnn_finalize(mlsim_plan* pl) {
+  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  const int L = (int)pl->layers.size();
+  MLSIM_REQUIRE(L >= 2, "no layers declared");
+  for (int i = 0; i < L; ++i) {
+    MLSIM_REQUIRE(pl->layers[i].set, "a layer was not set");
+    if (i > 0) MLSIM_REQUIRE(pl->layers[i].cin == pl->layers[i - 1].cout, "channel mismatch between layers");
+  }
+  MLSIM_CUDA_CHECK(cudaSetDevice(pl->cfg.device));
+  for (int li = 0; li < L; ++li) {
+    CnnLayer& l = pl->layers[li];
+    const int kind = (li == 0) ? 0 : (li == L - 1 ? 2 : 1);
+    std::vector<uint8_t> img((size_t)mlsim_cnn_pack_host(kind, l.cin, l.cout, nullptr, nullptr, nullptr, 0));
+    if (mlsim_cnn_pack_host(kind, l.cin, l.cout, l.w.data(), l.b.data(), img.data(), (int64_t)img.size()) < 0) return MLSIM_EINVAL;
+    if (l.d_wimg) { cudaFree(l.d_wimg); l.d_wimg = nullptr; }
+    int rc = dev_alloc(pl, &l.d_wimg, img.size());
+    if (rc) return rc;
+    MLSIM_CUDA_CHECK(cudaMemcpy(l.d_wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
+  }
+  if (!pl->d_act[0]) {
+    const mlsim_config& c = pl->cfg;
+    pl->act_bytes = (size_t)c.batch * c.nx * 8 * (size_t)(c.ny + 2) * 16;
+    for (int i = 0; i < 2; ++i) {
+      uint8_t* p = nullptr;
+      int rc = dev_alloc(pl, &p, pl->act_bytes);
+      if (rc) return rc;
+      pl->d_act[i] = reinterpret_cast<__nv_bfloat16*>(p);
+      MLSIM_CUDA_CHECK(cudaMemset(p, 0, pl->act_bytes));     // zero halo columns yp = 0 and yp = ny+1
+    }
+    pl->rs = conv_pick_strip(c.nx, c.ny, c.batch, pl->sm_count);
+  }
+  MLSIM_CUDA_CHECK(cudaDeviceSynchronize());
+  pl->cnn_ready = true;
+  return MLSIM_OK;
+}
+
+int mlsim_step(mlsim_plan* pl, float* u, float* v, float* p_or_null, int32_t nsteps, int32_t apply_cnn,
+               double cnn_input_scale, void* stream) {
+  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  int rc;
+  if ((rc = check_field(u, "u")) || (rc = check_field(v, "v"))) return rc;
+  if (p_or_null && (rc = check_field(p_or_null, "p"))) return rc;
+  MLSIM_REQUIRE(nsteps >= 0, "nsteps must be >= 0");
+  if (apply_cnn && !pl->cnn_ready) { set_error("apply_cnn set but the correction network is not finalised"); return MLSIM_ESTATE; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int s = 0; s < nsteps; ++s) {
+    float* pp = (s == nsteps - 1) ? p_or_null : nullptr;
+    if ((rc = solver_step(pl, u, v, pp, st))) return rc;
+    if (apply_cnn && (rc = cnn_apply(pl, u, v, u, v, nullptr, cnn_input_scale, st))) return rc;
+  }
+  return MLSIM_OK;
+}
+
+int mlsim_rollout_host(mlsim_plan* pl, float* hu, float* hv, float* hp, int32_t nsteps, int32_t apply_cnn,
+                       double cnn_input_scale) {
+  if (!pl || !hu || !hv) { set_error("null argument"); return MLSIM_EINVAL; }
+  MLSIM_CUDA_CHECK(cudaSetDevice(pl->cfg.device));
+  const size_t n = pl->field_elems;
+  int rc;
+  if (!pl->d_hu) {
+    if ((rc = dev_alloc(pl, &pl->d_hu, n)) || (rc = dev_alloc(pl, &pl->d_hv, n)) || (rc = dev_alloc(pl, &pl->d_hp, n))) return rc;
+  }
+  cudaStream_t st = pl->own_stream;
+  MLSIM_CUDA_CHECK(cudaMemcpyAsync(pl->d_hu, hu, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  MLSIM_CUDA_CHECK(cudaMemcpyAsync(pl->d_hv, hv, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  if ((rc = mlsim_step(pl, pl->d_hu, pl->d_hv, hp ? pl->d_hp : nullptr, nsteps, apply_cnn, cnn_input_scale, st))) return rc;
+  MLSIM_CUDA_CHECK(cudaMemcpyAsync(hu, pl->d_hu, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  MLSIM_CUDA_CHECK(cudaMemcpyAsync(hv, pl->d_hv, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (hp) MLSIM_CUDA_CHECK(cudaMemcpyAsync(hp, pl->d_hp, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  MLSIM_CUDA_CHECK(cudaStreamSynchronize(st));
+  return MLSIM_OK;
+}
+
+int mlsim_explicit_terms(mlsim_plan* pl, const float* u, const float* v, float* du, float* dv, void* stream) {
+  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  int rc;
+  if ((rc = check_field(u, "u")) || (rc = check_field(v, "v")) || (rc = check_field(du, "du")) || (rc = check_field(dv, "dv"))) return rc;
+  StageArgs a;
+  a.us = u; a.vs = v; a.u0 = u; a.v0 = v; a.accu = nullptr; a.accv = nullptr; a.outu = du; a.outv = dv;
+  a.ca = 0.f; a.cs = 0.f; a.mode = 0;
+  return launch_explicit(a, pl->sp, pl->d_forcing, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mlsim_project(mlsim_plan* pl, float* u, float* v, float* p_or_null, void* stream) {
+  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  int rc;
+  if ((rc = check_field(u, "u")) || (rc = check_field(v, "v"))) return rc;
+  return project(pl, u, v, p_or_null, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mlsim_divergence(mlsim_plan* pl, const float* u, const float* v, float* d, void* stream) {
+  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  int rc;
+  if ((rc = check_field(u, "u")) || (rc = check_field(v, "v")) || (rc = check_field(d, "div"))) return rc;
+  return launch_divergence(u, v, d, pl->sp, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mlsim_cnn_forward(mlsim_plan* pl, const float* u, const float* v, float* y, double scale, void* stream) {
+  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  int rc;
+  if ((rc = check_field(u, "u")) || (rc = check_field(v, "v")) || (rc = check_field(y, "y"))) return rc;
+  return cnn_apply(pl, u, v, nullptr, nullptr, y, scale, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mlsim_cnn_correct(mlsim_plan* pl, float* u, float* v, double scale, void* stream) {
+  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  int rc;
+  if ((rc = check_field(u, "u")) || (rc = check_field(v, "v"))) return rc;
+  if (!pl->cnn_ready) { set_error("correction network not finalised"); return MLSIM_ESTATE; }
+  MLSIM_REQUIRE(pl->layers.back().cout == 2, "the fused correction add needs a 2-channel output (u, v)");
+  return cnn_apply(pl, u, v, u, v, nullptr, scale, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mlsim_launches_per_step(mlsim_plan* pl, int32_t apply_cnn) {
+  if (!pl) return MLSIM_EINVAL;
+  int n = 16;   // 4 stages x (explicit, div+rfft, column solve, irfft+grad)
+  if (apply_cnn && pl->cnn_ready) n += (int)pl->layers.size();
+  return n;
+}
+
+int64_t mlsim_workspace_bytes(mlsim_plan* pl) { return pl ? pl->ws_bytes : 0; }
+
+int mlsim_time_kernel(mlsim_plan* pl, int32_t which, int32_t warmup, int32_t iters, float* ms_out, void* stream) {
+  if (!pl || !ms_out) { set_error("null argument"); return MLSIM_EINVAL; }
+  MLSIM_REQUIRE(which >= 0 && which <= 6 && iters >= 1 && warmup >= 0, "bad arguments");
+  if (which >= 4 && !pl->cnn_ready) { set_error("correction network not finalised"); return MLSIM_ESTATE; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t n = pl->field_elems;
+  int rc;
+  if (!pl->d_tu) {
+    if ((rc = dev_alloc(pl, &pl->d_tu, n)) || (rc = dev_alloc(pl, &pl->d_tv, n))) return rc;
+    MLSIM_CUDA_CHECK(cudaMemsetAsync(pl->d_tu, 0, n * sizeof(float), st));
+    MLSIM_CUDA_CHECK(cudaMemsetAsync(pl->d_tv, 0, n * sizeof(float), st));
+  }
+  const mlsim_config& c = pl->cfg;
+  const float dt = (float)c.dt;
+  auto run = [&]() -> int {
+    switch (which) {
+      case 0: {
+        StageArgs a;
+        a.us = pl->d_tu; a.vs = pl->d_tv; a.u0 = pl->d_w2u; a.v0 = pl->d_w2v; a.accu = pl->d_accu; a.accv = pl->d_accv;
+        a.outu = pl->d_w1u; a.outv = pl->d_w1v; a.ca = 0.f * dt; a.cs = 0.f * dt; a.mode = 2;
+        return launch_explicit(a, pl->sp, pl->d_forcing, st);
+      }
+      case 1: return launch_div_rfft(pl->d_tu, pl->d_tv, pl->d_spec, pl->d_twy, pl->sp, st);
+      case 2: return launch_col_solve(pl->d_spec, pl->d_inv_eig, pl->d_twx, pl->sp, st);
+      case 3: return launch_irfft_grad(pl->d_spec, pl->d_tu, pl->d_tv, pl->d_w1u, pl->d_w1v, nullptr, pl->d_twy, pl->sp, st);
+      case 4: {
+        ConvFirstArgs f;
+        f.u = pl->d_tu; f.v = pl->d_tv; f.out = pl->d_act[0]; f.wimg = pl->layers[0].d_wimg; f.scale = 1.0f;
+        f.nx = c.nx; f.ny = c.ny; f.batch = c.batch;
+        return launch_conv_first(f, pl->sm_count, st);
+      }
+      default: {
+        const int L = (int)pl->layers.size();
+        const int l = (which == 5) ? 1 : L - 1;
+        if (which == 5 && L < 3) { set_error("no mid layer in this network"); return MLSIM_EINVAL; }
+        ConvMidArgs m;
+        m.in = pl->d_act[0]; m.out = pl->d_act[1]; m.u = pl->d_w1u; m.v = pl->d_w1v; m.y_nchw = nullptr;
+        m.wimg = pl->layers[l].d_wimg; m.nx = c.nx; m.ny = c.ny; m.batch = c.batch; m.rs = pl->rs;
+        m.cout = pl->layers[l].cout; m.relu = pl->layers[l].relu;
+        return (which == 5) ? launch_conv_mid(m, pl->sm_count, st) : launch_conv_last(m, pl->sm_count, st);
+      }
+    }
+  };
+  for (int i = 0; i < warmup; ++i) if ((rc = run())) return rc;
+  cudaEvent_t e0, e1;
+  MLSIM_CUDA_CHECK(cudaEventCreate(&e0));
+  MLSIM_CUDA_CHECK(cudaEventCreate(&e1));
+  MLSIM_CUDA_CHECK(cudaEventRecord(e0, st));
+  for (int i = 0; i < iters; ++i) if ((rc = run())) return rc;
+  MLSIM_CUDA_CHECK(cudaEventRecord(e1, st));
+  MLSIM_CUDA_CHECK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  MLSIM_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_out = ms / iters;
+  return MLSIM_OK;
+}
+
+}  // extern "C"

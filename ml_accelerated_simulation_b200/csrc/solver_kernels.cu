@@ -1,0 +1,498 @@
+// Solver half of the rollout step: explicit terms + RK combine (K1), divergence + row FFT (K2),
+// column FFT * inverse Laplacian spectrum * column iFFT (K3), row iFFT + gradient subtraction (K4).
+//
+// Stands in for torch_cfd.fvm.RKStepper.forward / NavierStokes2DFVMProjection as called at
+// reference src/inference.py:101 (algorithm: SURVEY.md App. A.2-A.4).  All kernels are HBM-bound:
+// state fields are fp32 [batch][nx][ny] (y contiguous); the spectral buffer is float2
+// [batch][nx][nycp] with nyc = ny/2+1 valid columns.
+#include "common.cuh"
+#include "fft.cuh"
+#include "solver_kernels.h"
+
+namespace mlsim {
+
+// ---------------------------------------------------------------------------------------------
+// K1: explicit terms F(u,v) and Runge-Kutta stage combine.
+// Tile: TX=32 rows (x) by TY columns (y); each thread owns 4 consecutive columns and marches over
+// RPG rows so the x-face flux is reused from the previous row; y-face fluxes are shared between
+// the thread's four columns (5 evaluations for 4 cells).
+// ---------------------------------------------------------------------------------------------
+constexpr int K1_TX = 32;
+constexpr int K1_HALO = 2;
+constexpr int K1_THREADS = 256;
+
+__device__ __forceinline__ float face_flux(float cl, float c, float cr, float crr, float w, float cfl,
+                                           int adv) {
+  // TVD face value times face velocity (App. A.3.2).  phi(r) = 2r/(1+r) is evaluated as
+  // 2*num/(d+num): identical for r = num/d > 0 and free of the inf/inf hazard when d is tiny.
+  const bool pos = w > 0.0f;
+  const float low = pos ? c : cr;
+  if (adv == MLSIM_ADV_UPWIND) return low * w;
+  const float d = cr - c;
+  const float courant = cfl * w;
+  const float high = pos ? fmaf(0.5f * (1.0f - courant), d, c) : fmaf(-0.5f * (1.0f + courant), d, cr);
+  if (adv == MLSIM_ADV_LAX_WENDROFF) return high * w;
+  const float num = pos ? (c - cl) : (crr - cr);
+  const bool same = (num > 0.0f && d > 0.0f) || (num < 0.0f && d < 0.0f);
+  const float phi = same ? (2.0f * num) / (d + num) : 0.0f;
+  return (low - (low - high) * phi) * w;
+}
+
+template <int TY>
+__global__ void __launch_bounds__(K1_THREADS)
+k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
+  constexpr int NTY = TY / 4;                 // threads along y
+  constexpr int NG = K1_THREADS / NTY;        // row groups
+  constexpr int RPG = K1_TX / NG;             // rows marched per thread
+  constexpr int SW = TY + 8;                  // smem row width (4-column halo each side, float4 aligned)
+  constexpr int SH = K1_TX + 2 * K1_HALO;
+  extern __shared__ float4 smem4[];
+  float* su = reinterpret_cast<float*>(smem4);
+  float* sv = su + SH * SW;
+
+  const int b = blockIdx.z;
+  const int i0 = blockIdx.y * K1_TX;
+  const int j0 = blockIdx.x * TY;
+  const size_t img = (size_t)b * p.nx * p.ny;
+  const float* __restrict__ gu = a.us + img;
+  const float* __restrict__ gv = a.vs + img;
+
+  // ---- load the (TX+4) x (TY+8) halo tile, periodic wrap, float4 granules ----
+  constexpr int W4 = SW / 4;
+  const int ny4 = p.ny >> 2;
+  for (int idx = threadIdx.x; idx < SH * W4; idx += K1_THREADS) {
+    const int r = idx / W4, c4 = idx - r * W4;
+    const int gi = (i0 - K1_HALO + r) & (p.nx - 1);
+    const int gc = ((j0 >> 2) - 1 + c4) & (ny4 - 1);
+    const float4 vu = __ldg(reinterpret_cast<const float4*>(gu + (size_t)gi * p.ny) + gc);
+    const float4 vv = __ldg(reinterpret_cast<const float4*>(gv + (size_t)gi * p.ny) + gc);
+    reinterpret_cast<float4*>(su + r * SW)[c4] = vu;
+    reinterpret_cast<float4*>(sv + r * SW)[c4] = vv;
+  }
+  __syncthreads();
+
+  const int ty = threadIdx.x % NTY;
+  const int g = threadIdx.x / NTY;
+  const int lj = 4 + 4 * ty;                  // smem column of the thread's first cell
+  const int li0 = K1_HALO + g * RPG;          // smem row of the thread's first cell
+  const int adv = p.advection;
+
+#define SU(i, j) su[(i) * SW + (j)]
+#define SV(i, j) sv[(i) * SW + (j)]
+
+  // x-face fluxes at face (li0-1) for the 4 columns: carried along the march
+  float fxu_prev[4], fxv_prev[4];
+  {
+    const int i = li0 - 1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = lj + k;
+      const float wxu = 0.5f * (SU(i, j) + SU(i + 1, j));
+      fxu_prev[k] = face_flux(SU(i - 1, j), SU(i, j), SU(i + 1, j), SU(i + 2, j), wxu, p.dt_hx, adv);
+      const float wxv = 0.5f * (SU(i, j) + SU(i, j + 1));
+      fxv_prev[k] = face_flux(SV(i - 1, j), SV(i, j), SV(i + 1, j), SV(i + 2, j), wxv, p.dt_hx, adv);
+    }
+  }
+
+  float frc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) frc[k] = __ldg(&forcing[j0 + 4 * ty + k]);
+
+#pragma unroll 2
+  for (int rr = 0; rr < RPG; ++rr) {
+    const int i = li0 + rr;
+    float fxu[4], fxv[4], fyu[5], fyv[5];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = lj + k;
+      const float wxu = 0.5f * (SU(i, j) + SU(i + 1, j));
+      fxu[k] = face_flux(SU(i - 1, j), SU(i, j), SU(i + 1, j), SU(i + 2, j), wxu, p.dt_hx, adv);
+      const float wxv = 0.5f * (SU(i, j) + SU(i, j + 1));
+      fxv[k] = face_flux(SV(i - 1, j), SV(i, j), SV(i + 1, j), SV(i + 2, j), wxv, p.dt_hx, adv);
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int j = lj - 1 + k;               // y-face between columns j and j+1
+      const float wyu = 0.5f * (SV(i, j) + SV(i + 1, j));
+      fyu[k] = face_flux(SU(i, j - 1), SU(i, j), SU(i, j + 1), SU(i, j + 2), wyu, p.dt_hy, adv);
+      const float wyv = 0.5f * (SV(i, j) + SV(i, j + 1));
+      fyv[k] = face_flux(SV(i, j - 1), SV(i, j), SV(i, j + 1), SV(i, j + 2), wyv, p.dt_hy, adv);
+    }
+    float ku[4], kv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = lj + k;
+      const float cu = SU(i, j), cv = SV(i, j);
+      const float advu = -((fxu[k] - fxu_prev[k]) * p.inv_hx + (fyu[k + 1] - fyu[k]) * p.inv_hy);
+      const float advv = -((fxv[k] - fxv_prev[k]) * p.inv_hx + (fyv[k + 1] - fyv[k]) * p.inv_hy);
+      const float lapu = (SU(i - 1, j) + SU(i + 1, j) - 2.0f * cu) * p.nu_hx2 +
+                         (SU(i, j - 1) + SU(i, j + 1) - 2.0f * cu) * p.nu_hy2;
+      const float lapv = (SV(i - 1, j) + SV(i + 1, j) - 2.0f * cv) * p.nu_hx2 +
+                         (SV(i, j - 1) + SV(i, j + 1) - 2.0f * cv) * p.nu_hy2;
+      ku[k] = advu + lapu - p.drag * cu + frc[k];
+      kv[k] = advv + lapv - p.drag * cv;
+      fxu_prev[k] = fxu[k];
+      fxv_prev[k] = fxv[k];
+    }
+    // ---- RK combine + float4 I/O ----
+    const int gi = i0 + (i - K1_HALO);
+    const size_t off = img + (size_t)gi * p.ny + (j0 + 4 * ty);
+    float4 ou, ov;
+    if (a.mode == 0) {
+      ou = make_float4(ku[0], ku[1], ku[2], ku[3]);
+      ov = make_float4(kv[0], kv[1], kv[2], kv[3]);
+    } else if (a.mode == 3) {
+      const float4 au = *reinterpret_cast<const float4*>(a.accu + off);
+      const float4 av = *reinterpret_cast<const float4*>(a.accv + off);
+      ou = make_float4(fmaf(a.cs, ku[0], au.x), fmaf(a.cs, ku[1], au.y), fmaf(a.cs, ku[2], au.z), fmaf(a.cs, ku[3], au.w));
+      ov = make_float4(fmaf(a.cs, kv[0], av.x), fmaf(a.cs, kv[1], av.y), fmaf(a.cs, kv[2], av.z), fmaf(a.cs, kv[3], av.w));
+    } else {
+      float4 bu, bv;            // u0, v0
+      if (a.mode == 1) {        // u_s == u0: already in shared memory
+        bu = make_float4(SU(i, lj), SU(i, lj + 1), SU(i, lj + 2), SU(i, lj + 3));
+        bv = make_float4(SV(i, lj), SV(i, lj + 1), SV(i, lj + 2), SV(i, lj + 3));
+      } else {
+        bu = __ldg(reinterpret_cast<const float4*>(a.u0 + off));
+        bv = __ldg(reinterpret_cast<const float4*>(a.v0 + off));
+      }
+      float4 au = bu, av = bv;
+      if (a.mode == 2) {
+        au = *reinterpret_cast<const float4*>(a.accu + off);
+        av = *reinterpret_cast<const float4*>(a.accv + off);
+      }
+      au = make_float4(fmaf(a.ca, ku[0], au.x), fmaf(a.ca, ku[1], au.y), fmaf(a.ca, ku[2], au.z), fmaf(a.ca, ku[3], au.w));
+      av = make_float4(fmaf(a.ca, kv[0], av.x), fmaf(a.ca, kv[1], av.y), fmaf(a.ca, kv[2], av.z), fmaf(a.ca, kv[3], av.w));
+      *reinterpret_cast<float4*>(a.accu + off) = au;
+      *reinterpret_cast<float4*>(a.accv + off) = av;
+      ou = make_float4(fmaf(a.cs, ku[0], bu.x), fmaf(a.cs, ku[1], bu.y), fmaf(a.cs, ku[2], bu.z), fmaf(a.cs, ku[3], bu.w));
+      ov = make_float4(fmaf(a.cs, kv[0], bv.x), fmaf(a.cs, kv[1], bv.y), fmaf(a.cs, kv[2], bv.z), fmaf(a.cs, kv[3], bv.w));
+    }
+    *reinterpret_cast<float4*>(a.outu + off) = ou;
+    *reinterpret_cast<float4*>(a.outv + off) = ov;
+  }
+#undef SU
+#undef SV
+}
+
+template <int TY>
+static int launch_explicit_ty(const StageArgs& a, const SolverParams& p, const float* forcing, cudaStream_t st) {
+  constexpr int SW = TY + 8, SH = K1_TX + 2 * K1_HALO;
+  const size_t smem = (size_t)2 * SH * SW * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    MLSIM_CUDA_CHECK(cudaFuncSetAttribute(k_explicit_rk<TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  dim3 grid(p.ny / TY, p.nx / K1_TX, p.batch);
+  k_explicit_rk<TY><<<grid, K1_THREADS, smem, st>>>(a, p, forcing);
+  MLSIM_CUDA_CHECK(cudaGetLastError());
+  return MLSIM_OK;
+}
+
+int launch_explicit(const StageArgs& a, const SolverParams& p, const float* forcing, cudaStream_t st) {
+  if (p.ny >= 256) return launch_explicit_ty<256>(a, p, forcing, st);
+  if (p.ny == 128) return launch_explicit_ty<128>(a, p, forcing, st);
+  return launch_explicit_ty<64>(a, p, forcing, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// divergence (test hook; fdm.divergence of test/sim_test.py:42)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_divergence(const float* __restrict__ u, const float* __restrict__ v, float* __restrict__ d,
+                             SolverParams p) {
+  const size_t n = (size_t)p.batch * p.nx * p.ny;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % p.ny);
+    const size_t row = idx / p.ny;
+    const int i = (int)(row % p.nx);
+    const size_t img = (row / p.nx) * (size_t)p.nx * p.ny;
+    const int im = (i - 1) & (p.nx - 1), jm = (j - 1) & (p.ny - 1);
+    d[idx] = (u[idx] - u[img + (size_t)im * p.ny + j]) * p.inv_hx + (v[idx] - v[img + (size_t)i * p.ny + jm]) * p.inv_hy;
+  }
+}
+
+int launch_divergence(const float* u, const float* v, float* d, const SolverParams& p, cudaStream_t st) {
+  k_divergence<<<148 * 8, 256, 0, st>>>(u, v, d, p);
+  MLSIM_CUDA_CHECK(cudaGetLastError());
+  return MLSIM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: divergence of (u*, v*) for 2Q rows, packed as Q complex lines (row 2q -> re, row 2q+1 -> im),
+// forward FFT along y in shared memory, untangle to the two half spectra, store nyc columns per row.
+// ---------------------------------------------------------------------------------------------
+template <int N> struct RowCfg {
+  // lines per CTA such that Q*N/Rmin <= 1024 threads
+  static constexpr int RMIN = FftMinRadix<N>::value;
+  static constexpr int Q = (N <= 256) ? 16 : (N <= 1024 ? 8 : 4);
+  static constexpr int THREADS = Q * N / RMIN;
+  static constexpr int LS = Q + 1;
+  static constexpr size_t SMEM = (size_t)N * LS * sizeof(float2);
+};
+
+template <int N>
+__global__ void __launch_bounds__(RowCfg<N>::THREADS)
+k_div_rfft(const float* __restrict__ u, const float* __restrict__ v, float2* __restrict__ S,
+           const float2* __restrict__ tw, SolverParams p) {
+  using P = FftPlan<N>;
+  using C = RowCfg<N>;
+  constexpr int Q = C::Q, LS = C::LS, NT = C::THREADS;
+  extern __shared__ float4 smem4[];
+  float2* buf = reinterpret_cast<float2*>(smem4);
+
+  const int b = blockIdx.y;
+  const int i0 = blockIdx.x * (2 * Q);
+  const size_t img = (size_t)b * p.nx * N;
+  const float* __restrict__ gu = u + img;
+  const float* __restrict__ gv = v + img;
+
+  for (int idx = threadIdx.x; idx < 2 * Q * N; idx += NT) {
+    const int r = idx / N, j = idx - r * N;
+    const int i = i0 + r;
+    const int im = (i - 1) & (p.nx - 1), jm = (j - 1) & (N - 1);
+    const float d = (gu[(size_t)i * N + j] - gu[(size_t)im * N + j]) * p.inv_hx +
+                    (gv[(size_t)i * N + j] - gv[(size_t)i * N + jm]) * p.inv_hy;
+    reinterpret_cast<float*>(&buf[j * LS + (r >> 1)])[r & 1] = d;
+  }
+  __syncthreads();
+
+  const int c = threadIdx.x % Q, j = threadIdx.x / Q;
+  stage_smem<N, P::R1, 1, -1>(buf, LS, c, j, true, tw);
+  stage_smem<N, P::R2, P::R1, -1>(buf, LS, c, j, true, tw);
+  if constexpr (P::R3 > 1) stage_smem<N, P::R3, P::R1 * P::R2, -1>(buf, LS, c, j, true, tw);
+
+  const int nyc = N / 2 + 1;
+  for (int idx = threadIdx.x; idx < Q * nyc; idx += NT) {
+    const int q = idx / nyc, k = idx - q * nyc;
+    const float2 z = buf[k * LS + q];
+    const float2 zm = buf[((N - k) & (N - 1)) * LS + q];
+    const float2 A = make_float2(0.5f * (z.x + zm.x), 0.5f * (z.y - zm.y));
+    const float2 B = make_float2(0.5f * (z.y + zm.y), -0.5f * (z.x - zm.x));
+    const size_t row = (size_t)b * p.nx + i0 + 2 * q;
+    S[row * p.nycp + k] = A;
+    S[(row + 1) * p.nycp + k] = B;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: rebuild Q complex lines from 2Q rows of p-hat, inverse FFT along y, then
+//     u -= d+x p, v -= d+y p  for the first 2Q-1 rows (the last row is the x-halo of p).
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(RowCfg<N>::THREADS)
+k_irfft_grad(const float2* __restrict__ S, const float* __restrict__ uin, const float* __restrict__ vin,
+             float* __restrict__ uout, float* __restrict__ vout, float* __restrict__ pout,
+             const float2* __restrict__ tw, SolverParams p) {
+  using P = FftPlan<N>;
+  using C = RowCfg<N>;
+  constexpr int Q = C::Q, LS = C::LS, NT = C::THREADS;
+  extern __shared__ float4 smem4[];
+  float2* buf = reinterpret_cast<float2*>(smem4);
+
+  const int b = blockIdx.y;
+  const int i0 = blockIdx.x * (2 * Q - 1);
+  const int nyc = N / 2 + 1;
+
+  for (int idx = threadIdx.x; idx < Q * nyc; idx += NT) {
+    const int q = idx / nyc, k = idx - q * nyc;
+    const int ia = (i0 + 2 * q) & (p.nx - 1), ib = (i0 + 2 * q + 1) & (p.nx - 1);
+    const float2 A = __ldg(&S[((size_t)b * p.nx + ia) * p.nycp + k]);
+    const float2 B = __ldg(&S[((size_t)b * p.nx + ib) * p.nycp + k]);
+    if (k == 0 || k == N / 2) {
+      buf[k * LS + q] = make_float2(A.x, B.x);          // c2r ignores Im of DC / Nyquist
+    } else {
+      buf[k * LS + q] = make_float2(A.x - B.y, A.y + B.x);
+      buf[(N - k) * LS + q] = make_float2(A.x + B.y, B.x - A.y);
+    }
+  }
+  __syncthreads();
+
+  const int c = threadIdx.x % Q, j = threadIdx.x / Q;
+  // inverse radix order (R3,R2,R1) mirrors the column kernel; any order is valid
+  if constexpr (P::R3 > 1) {
+    stage_smem<N, P::R3, 1, +1>(buf, LS, c, j, true, tw);
+    stage_smem<N, P::R2, P::R3, +1>(buf, LS, c, j, true, tw);
+    stage_smem<N, P::R1, P::R3 * P::R2, +1>(buf, LS, c, j, true, tw);
+  } else {
+    stage_smem<N, P::R2, 1, +1>(buf, LS, c, j, true, tw);
+    stage_smem<N, P::R1, P::R2, +1>(buf, LS, c, j, true, tw);
+  }
+
+  const size_t img = (size_t)b * p.nx * N;
+  for (int idx = threadIdx.x; idx < (2 * Q - 1) * N; idx += NT) {
+    const int r = idx / N, y = idx - r * N;
+    const int i = i0 + r;
+    if (i >= p.nx) break;
+    const float p0 = reinterpret_cast<const float*>(&buf[y * LS + (r >> 1)])[r & 1];
+    const float pxp = reinterpret_cast<const float*>(&buf[y * LS + ((r + 1) >> 1)])[(r + 1) & 1];
+    const float pyp = reinterpret_cast<const float*>(&buf[((y + 1) & (N - 1)) * LS + (r >> 1)])[r & 1];
+    const size_t off = img + (size_t)i * N + y;
+    uout[off] = uin[off] - (pxp - p0) * p.inv_hx;
+    vout[off] = vin[off] - (pyp - p0) * p.inv_hy;
+    if (pout) pout[off] = p0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: for C adjacent ky columns: FFT along x, multiply by inv_eig (includes 1/(nx*ny)), iFFT along x.
+// First stage loads straight from global, last stage stores straight to global, and the last forward
+// stage hands its registers to the first inverse stage (same thread owns the same points).
+// ---------------------------------------------------------------------------------------------
+template <int N> struct ColCfg {
+  static constexpr int RMIN = FftMinRadix<N>::value;
+  static constexpr int C = (N <= 512) ? 16 : (N <= 1024 ? 8 : 4);
+  static constexpr int THREADS = C * N / RMIN;
+  static constexpr int LS = C + 1;
+  static constexpr size_t SMEM = (size_t)N * LS * sizeof(float2);
+};
+
+template <int N>
+__global__ void __launch_bounds__(ColCfg<N>::THREADS)
+k_col_solve(float2* __restrict__ S, const float* __restrict__ inv_eig, const float2* __restrict__ tw,
+            SolverParams p) {
+  using P = FftPlan<N>;
+  using CC = ColCfg<N>;
+  constexpr int C = CC::C, LS = CC::LS;
+  constexpr int RL = (P::R3 > 1) ? P::R3 : P::R2;        // radix of the last forward stage
+  constexpr int NSL = N / RL;                            // its Ns
+  extern __shared__ float4 smem4[];
+  float2* buf = reinterpret_cast<float2*>(smem4);
+
+  const int c = threadIdx.x % C, j = threadIdx.x / C;
+  const int ky = blockIdx.x * C + c;
+  const bool valid = ky < p.nyc;
+  float2* base = S + (size_t)blockIdx.y * N * p.nycp + ky;
+
+  // forward stage 1: global -> registers -> smem
+  {
+    constexpr int R = P::R1;
+    if (j < N / R) {
+      float2 v[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        v[r] = valid ? base[(size_t)(j + r * (N / R)) * p.nycp] : make_float2(0.f, 0.f);
+      dft_regs<R, -1>(v);
+#pragma unroll
+      for (int q = 0; q < R; ++q) buf[(j * R + q) * LS + c] = v[q];
+    }
+    __syncthreads();
+  }
+  if constexpr (P::R3 > 1) stage_smem<N, P::R2, P::R1, -1>(buf, LS, c, j, true, tw);
+
+  // last forward stage -> scale -> first inverse stage, all in registers
+  {
+    float2 v[RL];
+    const bool on = j < N / RL;
+    if (on) {
+#pragma unroll
+      for (int r = 0; r < RL; ++r) v[r] = buf[(j + r * NSL) * LS + c];
+    }
+    __syncthreads();
+    if (on) {
+      stage_twiddle<N, RL, NSL, -1>(v, j, tw);
+      dft_regs<RL, -1>(v);                                // X[kx = j + q*NSL]
+#pragma unroll
+      for (int q = 0; q < RL; ++q) {
+        const float s = valid ? __ldg(&inv_eig[(size_t)(j + q * NSL) * p.nyc + ky]) : 0.f;
+        v[q].x *= s;
+        v[q].y *= s;
+      }
+      dft_regs<RL, +1>(v);                                // inverse stage 1: Ns = 1, no twiddle
+#pragma unroll
+      for (int q = 0; q < RL; ++q) buf[(j * RL + q) * LS + c] = v[q];
+    }
+    __syncthreads();
+  }
+  if constexpr (P::R3 > 1) stage_smem<N, P::R2, P::R3, +1>(buf, LS, c, j, true, tw);
+
+  // last inverse stage: smem -> registers -> global
+  {
+    constexpr int R = P::R1;
+    constexpr int NS = N / R;
+    if (j < N / R) {
+      float2 v[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = buf[(j + r * (N / R)) * LS + c];
+      stage_twiddle<N, R, NS, +1>(v, j, tw);
+      dft_regs<R, +1>(v);
+      if (valid) {
+#pragma unroll
+        for (int q = 0; q < R; ++q) base[(size_t)(j + q * NS) * p.nycp] = v[q];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+template <int N>
+static int launch_div_rfft_n(const float* u, const float* v, float2* S, const float2* tw, const SolverParams& p,
+                             cudaStream_t st) {
+  using C = RowCfg<N>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MLSIM_CUDA_CHECK(cudaFuncSetAttribute(k_div_rfft<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    attr_done = true;
+  }
+  dim3 grid(p.nx / (2 * C::Q), p.batch);
+  k_div_rfft<N><<<grid, C::THREADS, C::SMEM, st>>>(u, v, S, tw, p);
+  MLSIM_CUDA_CHECK(cudaGetLastError());
+  return MLSIM_OK;
+}
+
+template <int N>
+static int launch_irfft_grad_n(const float2* S, const float* uin, const float* vin, float* uout, float* vout,
+                               float* pout, const float2* tw, const SolverParams& p, cudaStream_t st) {
+  using C = RowCfg<N>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MLSIM_CUDA_CHECK(cudaFuncSetAttribute(k_irfft_grad<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    attr_done = true;
+  }
+  const int rows = 2 * C::Q - 1;
+  dim3 grid((p.nx + rows - 1) / rows, p.batch);
+  k_irfft_grad<N><<<grid, C::THREADS, C::SMEM, st>>>(S, uin, vin, uout, vout, pout, tw, p);
+  MLSIM_CUDA_CHECK(cudaGetLastError());
+  return MLSIM_OK;
+}
+
+template <int N>
+static int launch_col_solve_n(float2* S, const float* inv_eig, const float2* tw, const SolverParams& p,
+                              cudaStream_t st) {
+  using C = ColCfg<N>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MLSIM_CUDA_CHECK(cudaFuncSetAttribute(k_col_solve<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    attr_done = true;
+  }
+  dim3 grid((p.nyc + C::C - 1) / C::C, p.batch);
+  k_col_solve<N><<<grid, C::THREADS, C::SMEM, st>>>(S, inv_eig, tw, p);
+  MLSIM_CUDA_CHECK(cudaGetLastError());
+  return MLSIM_OK;
+}
+
+#define MLSIM_DISPATCH_N(n, CALL)                     \
+  switch (n) {                                        \
+    case 64:   { constexpr int N_ = 64;   return CALL; }   \
+    case 128:  { constexpr int N_ = 128;  return CALL; }   \
+    case 256:  { constexpr int N_ = 256;  return CALL; }   \
+    case 512:  { constexpr int N_ = 512;  return CALL; }   \
+    case 1024: { constexpr int N_ = 1024; return CALL; }   \
+    case 2048: { constexpr int N_ = 2048; return CALL; }   \
+    default: set_error("unsupported grid size (need power of two in [64, 2048])"); return MLSIM_EINVAL; \
+  }
+
+int launch_div_rfft(const float* u, const float* v, float2* S, const float2* tw_y, const SolverParams& p,
+                    cudaStream_t st) {
+  MLSIM_DISPATCH_N(p.ny, launch_div_rfft_n<N_>(u, v, S, tw_y, p, st));
+}
+int launch_irfft_grad(const float2* S, const float* uin, const float* vin, float* uout, float* vout, float* pout,
+                      const float2* tw_y, const SolverParams& p, cudaStream_t st) {
+  MLSIM_DISPATCH_N(p.ny, launch_irfft_grad_n<N_>(S, uin, vin, uout, vout, pout, tw_y, p, st));
+}
+int launch_col_solve(float2* S, const float* inv_eig, const float2* tw_x, const SolverParams& p, cudaStream_t st) {
+  MLSIM_DISPATCH_N(p.nx, launch_col_solve_n<N_>(S, inv_eig, tw_x, p, st));
+}
+
+}  // namespace mlsim

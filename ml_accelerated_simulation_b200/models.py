@@ -1,0 +1,143 @@
+"""Correction-network front end: the reference's ``buildModel`` / ``CNN`` module API and checkpoint layout
+(reference src/models/modelbuilder.py:5-31, src/models/CNN.py:24-40, src/models/tools.py:1-34; weights
+contract src/train.py:50), with the forward pass executed by the tcgen05 convolution kernels.
+
+The module tree and parameter names are identical to the reference's (``models.{m}.layers.{i}[.0|.1].*``)
+so ``load_state_dict`` / ``safetensors.torch.save_model`` / ``load_model`` interoperate with reference
+checkpoints.  Parameters are created with the same ``nn.Conv2d`` / ``nn.BatchNorm2d`` constructors in the
+same order, so a given ``torch.manual_seed`` yields the reference's initial weights.
+
+Only the CNN block family on the hot path is implemented: 3x3 / stride 1 / padding 1 / groups 1, ReLU,
+dropout inactive (eval), optional BatchNorm (folded), in_channels = 2, hidden <= 64, out_channels <= 16.
+Anything else raises -- there is no PyTorch fallback.
+"""
+from __future__ import annotations
+
+import json
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from .plan import Plan, PlanConfig
+
+
+def _as_list(param, n: int, what: str) -> list:
+    if isinstance(param, list):
+        if len(param) != n:
+            raise ValueError(f"{what}: list length must equal the number of layers ({n})")
+        return list(param)
+    if isinstance(param, (int, float)):
+        return [param] * n
+    raise TypeError(f"{what}: expected a number or a list")
+
+
+def _channels(structure: dict) -> List[int]:
+    vals = list(structure.values())
+    if len(vals) != 3:
+        raise TypeError("structures must have in_channels, hidden_channels, out_channels")
+    return [int(vals[0])] + [int(c) for c in vals[1]] + [int(vals[2])]
+
+
+class CNN(nn.Module):
+    """Parameter container with the reference CNN block's layout; forward runs on the B200 kernels."""
+
+    def __init__(self, config: dict):
+        super().__init__()
+        chans = _channels(config["structures"])
+        n = len(chans) - 1
+        ks = _as_list(config["kernel_sizes"], n, "kernel_sizes")
+        st = _as_list(config["strides"], n, "strides")
+        pd = _as_list(config["paddings"], n, "paddings")
+        gr = _as_list(config["group"], n, "group")
+        self.dropouts = _as_list(config["dropouts"], n, "dropouts")
+        if str(config["activation_func"]).lower() != "relu":
+            raise NotImplementedError("only ReLU CNN blocks are on the B200 hot path")
+        if any(k != 3 for k in ks) or any(s != 1 for s in st) or any(p != 1 for p in pd) or any(g != 1 for g in gr):
+            raise NotImplementedError("only 3x3 / stride 1 / padding 1 / groups 1 convolutions are on the B200 hot path")
+        if n < 2 or chans[0] != 2 or max(chans[1:-1]) > 64 or chans[-1] > 16:
+            raise NotImplementedError("supported shapes: 2 -> (<=64)* -> (<=16) channels, at least two layers")
+        self.channels = chans
+        self.bn = bool(config["bn"])
+        if self.bn:
+            self.layers = nn.ModuleList([nn.Sequential(nn.Conv2d(chans[i], chans[i + 1], 3, 1, 1),
+                                                       nn.BatchNorm2d(chans[i + 1])) for i in range(n)])
+        else:
+            self.layers = nn.ModuleList([nn.Conv2d(chans[i], chans[i + 1], 3, 1, 1) for i in range(n)])
+
+    def folded_layers(self) -> List[Tuple[torch.Tensor, torch.Tensor]]:
+        """[(weight, bias)] in fp64 with eval-mode BatchNorm folded into the convolution."""
+        out = []
+        for layer in self.layers:
+            if self.bn:
+                conv, bn = layer[0], layer[1]
+                w = conv.weight.detach().double().cpu()
+                b = conv.bias.detach().double().cpu()
+                scale = bn.weight.detach().double().cpu() / torch.sqrt(bn.running_var.detach().double().cpu() + bn.eps)
+                w = w * scale[:, None, None, None]
+                b = (b - bn.running_mean.detach().double().cpu()) * scale + bn.bias.detach().double().cpu()
+            else:
+                w = layer.weight.detach().double().cpu()
+                b = layer.bias.detach().double().cpu()
+            out.append((w.contiguous(), b.contiguous()))
+        return out
+
+    def param_version(self) -> tuple:
+        return tuple(int(p._version) for p in list(self.parameters()) + list(self.buffers()))
+
+
+class buildModel(nn.Module):
+    """Drop-in for the reference's ``buildModel(configs)`` restricted to a single CNN block."""
+
+    def __init__(self, configs: Sequence[dict]):
+        super().__init__()
+        if len(configs) != 1 or str(configs[0]["name"]).upper() != "CNN":
+            raise NotImplementedError("the B200 hot path covers buildModel([CNN block]) (e.g. MLACFD.json)")
+        self.models_name = [c["name"] for c in configs]
+        self.models = nn.ModuleList([CNN(configs[0])])
+        self.input_scale = 1.0
+        self._plans: Dict[tuple, Tuple[Plan, tuple]] = {}
+        self.eval()
+
+    @property
+    def cnn(self) -> CNN:
+        return self.models[0]
+
+    def attach(self, plan: Plan) -> None:
+        """Upload (BN-folded, bf16-packed) weights into ``plan`` so plan.step(..., apply_cnn=True) can run."""
+        plan.set_cnn(self.cnn.folded_layers())
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.training:
+            raise RuntimeError("the B200 CNN path is inference-only; call .eval()")
+        if not x.is_cuda:
+            raise RuntimeError("the B200 CNN path runs on CUDA tensors only (no CPU fallback)")
+        if x.dim() != 4 or x.shape[1] != 2:
+            raise ValueError("expected input [batch, 2, nx, ny]")
+        b, _, nx, ny = x.shape
+        key = (b, nx, ny, x.device.index)
+        ver = self.cnn.param_version()
+        entry = self._plans.get(key)
+        if entry is None or entry[1] != ver:
+            plan = entry[0] if entry is not None else Plan(PlanConfig(nx=nx, ny=ny, batch=b, dt=1.0,
+                                                                     device=x.device.index or 0))
+            self.attach(plan)
+            self._plans[key] = (plan, ver)
+        plan = self._plans[key][0]
+        u = x[:, 0].to(torch.float32).contiguous()
+        v = x[:, 1].to(torch.float32).contiguous()
+        return plan.cnn_forward(u, v, 1.0).to(x.dtype)
+
+
+def load_config(path: str) -> list:
+    with open(path, "r") as f:
+        return json.load(f)
+
+
+def load_model(config_path: str, weights_path: str) -> buildModel:
+    """Build from a reference JSON config and load a reference ``.safetensors`` checkpoint (src/train.py:50)."""
+    import safetensors.torch as st
+    model = buildModel(load_config(config_path))
+    sd = st.load_file(weights_path)
+    model.load_state_dict(sd)
+    return model

@@ -1,0 +1,177 @@
+"""Python owner of an ``mlsim_plan`` (include/mlsim.h): one grid/batch/physics configuration on one B200.
+
+PyTorch is used for device memory and streams only; every numerical operation on the hot path is a
+hand-written sm_100a kernel reached through the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import math
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+ADVECTION = {"van_leer": 0, "upwind": 1, "lax_wendroff": 2}
+
+
+@dataclasses.dataclass
+class PlanConfig:
+    """Physics defaults are the reference's (src/inference.py:54-93)."""
+    nx: int = 64
+    ny: int = 64
+    batch: int = 1
+    lx: float = 2 * math.pi
+    ly: float = 2 * math.pi
+    dt: Optional[float] = None           # default: stable_time_step(min(h), max_velocity, cfl, viscosity)
+    viscosity: float = 1e-3
+    density: float = 1.0
+    drag: float = 0.1
+    forcing_wavenumber: int = 4
+    forcing_scale: float = 1.0
+    advection: str = "van_leer"
+    lw_dt_scale: float = 1.0
+    max_velocity: float = 7.0
+    cfl: float = 0.5
+    device: int = 0
+
+    def resolved_dt(self) -> float:
+        if self.dt is not None:
+            return float(self.dt)
+        from .equations import stable_time_step
+        return stable_time_step(dx=min(self.lx / self.nx, self.ly / self.ny), max_velocity=self.max_velocity,
+                                max_courant_number=self.cfl, viscosity=self.viscosity)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Plan:
+    def __init__(self, cfg: PlanConfig):
+        if not torch.cuda.is_available():
+            raise RuntimeError("mlsim needs a CUDA device (sm_100a); there is no CPU fallback")
+        self._lib = _lib.load()
+        self.cfg = cfg
+        self.dt = cfg.resolved_dt()
+        c = _lib.MlsimConfig(cfg.nx, cfg.ny, cfg.batch, cfg.lx, cfg.ly, self.dt, cfg.viscosity, cfg.density,
+                             cfg.drag, cfg.forcing_wavenumber, cfg.forcing_scale, ADVECTION[cfg.advection],
+                             cfg.lw_dt_scale, cfg.device)
+        h = C.c_void_p()
+        _lib.check(self._lib.mlsim_plan_create(C.byref(c), C.byref(h)))
+        self._h = h
+        self.device = torch.device("cuda", cfg.device)
+        self.shape = (cfg.batch, cfg.nx, cfg.ny)
+        self.cnn_out_channels = 0
+        self.has_cnn = False
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mlsim_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _field(self, t: torch.Tensor, name: str) -> torch.Tensor:
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+                and tuple(t.shape) == self.shape and t.device.index == self.cfg.device):
+            raise ValueError(f"{name} must be a contiguous float32 CUDA tensor of shape {self.shape} on cuda:{self.cfg.device}")
+        return t
+
+    def new_field(self) -> torch.Tensor:
+        return torch.empty(self.shape, dtype=torch.float32, device=self.device)
+
+    @staticmethod
+    def _stream() -> int:
+        return torch.cuda.current_stream().cuda_stream
+
+    # ------------------------------------------------------------------ correction network
+    def set_cnn(self, layers: Sequence[Tuple[torch.Tensor, torch.Tensor]]):
+        """layers: [(weight[cout,cin,3,3], bias[cout]), ...] on the host, any float dtype (BN already folded)."""
+        n = len(layers)
+        _lib.check(self._lib.mlsim_cnn_begin(self._h, n))
+        for i, (w, b) in enumerate(layers):
+            w64 = w.detach().to("cpu", torch.float64).contiguous()
+            b64 = b.detach().to("cpu", torch.float64).contiguous()
+            cout, cin, kh, kw = w64.shape
+            if kh != 3 or kw != 3:
+                raise ValueError("only 3x3 convolutions are on the hot path")
+            _lib.check(self._lib.mlsim_cnn_set_layer(self._h, i, cin, cout, 3, w64.data_ptr(), b64.data_ptr(), 1,
+                                                      1 if i < n - 1 else 0))
+        _lib.check(self._lib.mlsim_cnn_finalize(self._h))
+        self.cnn_out_channels = int(layers[-1][0].shape[0])
+        self.has_cnn = True
+
+    # ------------------------------------------------------------------ hot path
+    def step(self, u: torch.Tensor, v: torch.Tensor, nsteps: int = 1, apply_cnn: bool = False,
+             input_scale: float = 1.0, p: Optional[torch.Tensor] = None):
+        """In place: ``for _ in range(nsteps): v, p = step_fn.forward(v, dt, ns2d); v += model(v)``
+        (reference src/inference.py:100-102)."""
+        self._field(u, "u"); self._field(v, "v")
+        if p is not None:
+            self._field(p, "p")
+        _lib.check(self._lib.mlsim_step(self._h, u.data_ptr(), v.data_ptr(), _ptr(p), nsteps, int(apply_cnn),
+                                        float(input_scale), self._stream()))
+
+    def rollout_host(self, hu: torch.Tensor, hv: torch.Tensor, nsteps: int, apply_cnn: bool = False,
+                     input_scale: float = 1.0, hp: Optional[torch.Tensor] = None):
+        """Same loop through host tensors (H2D, nsteps, D2H inside); in place on hu, hv."""
+        for t in (hu, hv) + ((hp,) if hp is not None else ()):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != self.shape:
+                raise ValueError(f"host fields must be contiguous float32 CPU tensors of shape {self.shape}")
+        _lib.check(self._lib.mlsim_rollout_host(self._h, hu.data_ptr(), hv.data_ptr(), _ptr(hp), nsteps,
+                                                int(apply_cnn), float(input_scale)))
+
+    # ------------------------------------------------------------------ pieces (parity hooks)
+    def explicit_terms(self, u, v):
+        self._field(u, "u"); self._field(v, "v")
+        du, dv = self.new_field(), self.new_field()
+        _lib.check(self._lib.mlsim_explicit_terms(self._h, u.data_ptr(), v.data_ptr(), du.data_ptr(), dv.data_ptr(),
+                                                  self._stream()))
+        return du, dv
+
+    def project(self, u, v, want_p: bool = True):
+        """In place on u, v; returns p (or None)."""
+        self._field(u, "u"); self._field(v, "v")
+        p = self.new_field() if want_p else None
+        _lib.check(self._lib.mlsim_project(self._h, u.data_ptr(), v.data_ptr(), _ptr(p), self._stream()))
+        return p
+
+    def divergence(self, u, v):
+        self._field(u, "u"); self._field(v, "v")
+        d = self.new_field()
+        _lib.check(self._lib.mlsim_divergence(self._h, u.data_ptr(), v.data_ptr(), d.data_ptr(), self._stream()))
+        return d
+
+    def cnn_forward(self, u, v, input_scale: float = 1.0):
+        """y = model(stack((u, v), 1) * input_scale) -> [batch, cout, nx, ny] float32."""
+        self._field(u, "u"); self._field(v, "v")
+        y = torch.empty((self.cfg.batch, self.cnn_out_channels, self.cfg.nx, self.cfg.ny), dtype=torch.float32,
+                        device=self.device)
+        _lib.check(self._lib.mlsim_cnn_forward(self._h, u.data_ptr(), v.data_ptr(), y.data_ptr(), float(input_scale),
+                                               self._stream()))
+        return y
+
+    def cnn_correct(self, u, v, input_scale: float = 1.0):
+        self._field(u, "u"); self._field(v, "v")
+        _lib.check(self._lib.mlsim_cnn_correct(self._h, u.data_ptr(), v.data_ptr(), float(input_scale), self._stream()))
+
+    # ------------------------------------------------------------------ introspection
+    def launches_per_step(self, apply_cnn: bool) -> int:
+        return int(self._lib.mlsim_launches_per_step(self._h, int(apply_cnn)))
+
+    def workspace_bytes(self) -> int:
+        return int(self._lib.mlsim_workspace_bytes(self._h))
+
+    def time_kernel(self, which: int, warmup: int = 3, iters: int = 10) -> float:
+        ms = C.c_float(0.0)
+        _lib.check(self._lib.mlsim_time_kernel(self._h, which, warmup, iters, C.byref(ms), self._stream()))
+        return float(ms.value)

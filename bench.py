@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Benchmark of the rollout hot path: grid cell-steps/s for (RK4 solver step + learned-correction CNN).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of reference src/inference.py:100-102 over the whole batch:
+    v, p = step_fn.forward(v, dt, equation=ns2d);  v += model(v)
+Workload (BASELINE.json configs[1]): 256x256 periodic grid, 64 independent trajectories per GPU, MLACFD
+correction CNN, synthetic band-limited initial condition (seed 42), seed-2025 weights.  With N > 1 every
+rank runs its own 64 trajectories (independent units, no collective on the step path) -> weak scaling.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NX = NY = 256
+BATCH = 64
+METRIC = "grid cell-steps/sec (solver+NN correction)"
+UNIT = "cell-steps/s"
+SOLVER_BYTES_PER_CELL_STEP = 312            # 74 fp32 words solver + 4 words correction add
+CNN_FLOP_PER_CELL = 373248                  # MLACFD: 2*9*(2*64 + 5*64*64 + 64*2)
+MID_FLOP_PER_CELL = 2 * 9 * 64 * 64         # one 64->64 layer (the dominant kernel)
+WORKLOAD = f"{NX}x{NY} grid, batch {BATCH} trajectories per GPU, RK4 solver step + MLACFD correction CNN"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "tensor_tflops": p["bf16_tflops_sustained"],
+                "tensor_tflops_burst": p["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tensor_tflops": 1400.0, "tensor_tflops_burst": 1590.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                smax = float(f[1])
+                if t0 - 0.1 <= ts <= t1 + 0.3:
+                    sm.append(float(f[0]))
+                    for nm, val in zip(names, f[3:7]):
+                        if val.lower().startswith("active"):
+                            reasons.add(nm)
+            except ValueError:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def _dist():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def _oracle_state(batch, seed=42):
+    """CPU legs only: band-limited divergence-free IC of the reference's family, fp64."""
+    from oracle import solver as S
+    cfg = S.SolverConfig(nx=NX, ny=NY)
+    u, v = S.filtered_velocity_field(cfg, batch, seed=seed)
+    return cfg, u, v
+
+
+def _device_state(batch, seed, dev):
+    """Product arm: the same IC family from the package's own setup code (CUDA projection kernels)."""
+    import torch
+    from ml_accelerated_simulation_b200 import grids
+    from ml_accelerated_simulation_b200.initial_conditions import filtered_velocity_field
+    import math
+    grid = grids.Grid((NX, NY), domain=((0, 2 * math.pi), (0, 2 * math.pi)), device=dev)
+    v0 = filtered_velocity_field(grid, 7.0, 4.0, iterations=16, random_state=seed, device=dev, batch_size=batch,
+                                 dtype=torch.float32)
+    return v0[0].data.contiguous(), v0[1].data.contiguous()
+
+
+def _model_state():
+    import safetensors.torch as st
+    g = os.path.join(ROOT, "tests", "golden")
+    cfgj = json.load(open(os.path.join(g, "MLACFD.json")))
+    sd = st.load_file(os.path.join(g, "mlacfd_weights.safetensors"))     # seed 2025 init, last layer x1e-2
+    return cfgj, sd
+
+
+def cpu_oracle_rate(nsample: int, steps: int, warmup: int, state=None):
+    """cell-steps/s of the fp64 oracle (restated solver + CNN, the reference's CPU path) on the host cores."""
+    import torch
+    from oracle import cnn as OC
+    from oracle import solver as S
+    if state is None:
+        cfg, u, v = _oracle_state(nsample)
+    else:
+        cfg, u, v = S.SolverConfig(nx=NX, ny=NY), state[0].double(), state[1].double()
+    cfgj, sd = _model_state()
+    with torch.inference_mode():
+        for _ in range(warmup):
+            u, v, _ = OC.rollout(u, v, cfg, 1, cfgj, sd, 1.0)
+        t = time.perf_counter()
+        for _ in range(steps):
+            u, v, _ = OC.rollout(u, v, cfg, 1, cfgj, sd, 1.0)
+        dt = time.perf_counter() - t
+    assert bool(torch.isfinite(u).all())
+    return nsample * NX * NY * steps / dt, dt / steps, torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (fp64 torch ops on the host;
+    solver restated in oracle/solver.py because torch_cfd is not installable here, CNN = oracle/cnn.py pinned
+    to src/models), all host threads, each step a bounded sample (1 of the 64 trajectories)."""
+    rank, world, _ = _dist()
+    if rank != 0:
+        return
+    nsample = 1
+    rate, sec_per_step, threads = cpu_oracle_rate(nsample, args.steps, min(args.warmup, 2))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": sec_per_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "timed_on": "host CPU"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{nsample} of {BATCH} trajectories per step, {args.steps} steps"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from ml_accelerated_simulation_b200 import Plan, PlanConfig, models
+
+    rank, world, local = _dist()
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    peaks = _peaks()
+
+    cfgj, sd = _model_state()
+    model = models.buildModel(cfgj)
+    model.load_state_dict(sd)
+    plan = Plan(PlanConfig(nx=NX, ny=NY, batch=BATCH, device=local))
+    model.attach(plan)
+    u0, v0 = _device_state(BATCH, 42 + rank, dev)
+    u, v = u0.clone(), v0.clone()
+    cells = BATCH * NX * NY
+    K, W = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident throughput (value) ----------------
+    plan.step(u, v, nsteps=W, apply_cnn=True)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    plan.profile_enable(5, 5 * K + 8)                      # CUDA events around every mid-conv launch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    e0.record()
+    plan.step(u, v, nsteps=K, apply_cnn=True)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    mid_ms, mid_n = plan.profile_read()
+    plan.profile_enable(-1, 0)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    assert bool(torch.isfinite(u).all()), "rollout diverged"
+    value = world * cells * K / (ms_total * 1e-3)
+
+    # ---------------- solver-only pass: HBM roofline of the stencil + projection + correction add ----------------
+    us, vs = u0.clone(), v0.clone()
+    plan.step(us, vs, nsteps=3, apply_cnn=False)
+    barrier()
+    e0.record()
+    plan.step(us, vs, nsteps=K, apply_cnn=False)
+    e1.record()
+    barrier()
+    solver_ms = max_over_ranks(e0.elapsed_time(e1)) / K
+
+    # ---------------- end to end through host buffers (e2e) ----------------
+    hu, hv = u0.cpu().pin_memory(), v0.cpu().pin_memory()
+    plan.rollout_host(hu, hv, 1, apply_cnn=True)
+    barrier()
+    t = time.perf_counter()
+    ke = max(3, min(K, 20))
+    for _ in range(ke):
+        plan.rollout_host(hu, hv, 1, apply_cnn=True)       # H2D(u,v) + step + D2H(u,v), synchronised
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t)
+    e2e = world * cells * ke / e2e_s
+    field_bytes = cells * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    mid_avg_ms = mid_ms / max(mid_n, 1)
+    mid_tflops = MID_FLOP_PER_CELL * cells / (mid_avg_ms * 1e-3) / 1e12
+    solver_rate = cells / (solver_ms * 1e-3)
+    cpu_rate, cpu_sec, cpu_threads = cpu_oracle_rate(2, 2, 1, state=(u0[:2].cpu(), v0[:2].cpu()))
+    launches_per_step = plan.launches_per_step(True)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 solver + bf16 conv (fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "l2": "per-step working set ~1.2 GB (2 x 541 MB bf16 activations) > 126 MB L2; no flush",
+                   "input_scale": 1.0, "weights": "MLACFD seed 2025, last layer x1e-2"},
+        "roofline": {"kernel": "k_conv_mid<64> (3x3 conv 64->64, tcgen05 implicit GEMM)", "bound": "tensor",
+                     "achieved": mid_tflops, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
+                     "frac": mid_tflops / peaks["tensor_tflops"], "frac_of_burst": mid_tflops / peaks["tensor_tflops_burst"],
+                     "traffic": None, "launches_timed": mid_n, "avg_launch_ms": mid_avg_ms,
+                     "share_of_step": mid_ms / ms_total, "peak_source": peaks["source"]},
+        "solver_roofline": {"bound": "hbm", "ms_per_step": solver_ms, "cell_steps_per_s": solver_rate,
+                            "achieved": SOLVER_BYTES_PER_CELL_STEP * solver_rate / 1e9, "peak": peaks["hbm_gbs"],
+                            "unit": "GB/s", "frac": SOLVER_BYTES_PER_CELL_STEP * solver_rate / 1e9 / peaks["hbm_gbs"],
+                            "note": "algorithmic 312 B/cell-step (solver + correction add); state (33.5 MB) is L2-resident at this config"},
+        "cnn_tensor_frac": CNN_FLOP_PER_CELL * (cells / ((ms_total / K - solver_ms) * 1e-3)) / 1e12 / peaks["tensor_tflops"],
+        "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": cpu_threads, "kind": "port",
+                         "sample": "2 of 64 trajectories, 2 steps of fp64 oracle (solver + CNN)"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * field_bytes, "d2h_bytes_per_step": 2 * field_bytes,
+                "steps": ke, "api": "Plan.rollout_host -> mlsim_rollout_host (pinned host buffers)"},
+        "gpu_launches": launches_per_step * K,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -104,6 +104,12 @@ int64_t mlsim_workspace_bytes(mlsim_plan* plan);
  * 6 last conv + correction add.  Runs `iters` launches after `warmup`, returns mean ms in *ms_out. */
 int  mlsim_time_kernel(mlsim_plan* plan, int32_t which, int32_t warmup, int32_t iters, float* ms_out, void* stream);
 
+/* In-step profiling: bracket every launch of one kernel class (numbering as in mlsim_time_kernel; -1 = off)
+ * with CUDA events on the launching stream, for up to max_samples launches; mlsim_profile_read synchronises
+ * on the recorded events, returns the summed device time and the number of launches, and resets the count. */
+int  mlsim_profile_enable(mlsim_plan* plan, int32_t kernel_class, int32_t max_samples);
+int  mlsim_profile_read(mlsim_plan* plan, float* total_ms, int32_t* count);
+
 const char* mlsim_last_error(void);
 const char* mlsim_version(void);
 

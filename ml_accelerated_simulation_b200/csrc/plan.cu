@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -51,6 +52,10 @@ struct mlsim_plan {
   cudaStream_t own_stream = nullptr;
   // timing scratch
   float* d_tu = nullptr; float* d_tv = nullptr;
+  // in-step kernel profiling (mlsim_profile_*): CUDA events around every launch of one kernel class
+  int prof_class = -1;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  size_t prof_used = 0;
 };
 
 namespace {
@@ -111,6 +116,17 @@ int build_tables(mlsim_plan* pl) {
   return MLSIM_OK;
 }
 
+struct ProfScope {
+  mlsim_plan* pl; cudaStream_t st; bool on; size_t idx;
+  ProfScope(mlsim_plan* pl_, int cls, cudaStream_t st_) : pl(pl_), st(st_), on(false), idx(0) {
+    if (pl->prof_class == cls && pl->prof_used < pl->prof_events.size()) {
+      on = true; idx = pl->prof_used++;
+      cudaEventRecord(pl->prof_events[idx].first, st);
+    }
+  }
+  ~ProfScope() { if (on) cudaEventRecord(pl->prof_events[idx].second, st); }
+};
+
 int check_field(const void* p, const char* name) {
   if (p == nullptr) {
     set_error(std::string(name) + " is null");
@@ -126,9 +142,15 @@ int check_field(const void* p, const char* name) {
 // P(u,v) in place on (u,v): K2 -> K3 -> K4
 int project(mlsim_plan* pl, float* u, float* v, float* p_or_null, cudaStream_t st) {
   int rc;
-  if ((rc = launch_div_rfft(u, v, pl->d_spec, pl->d_twy, pl->sp, st))) return rc;
-  if ((rc = launch_col_solve(pl->d_spec, pl->d_inv_eig, pl->d_twx, pl->sp, st))) return rc;
+  { ProfScope ps(pl, 1, st); if ((rc = launch_div_rfft(u, v, pl->d_spec, pl->d_twy, pl->sp, st))) return rc; }
+  { ProfScope ps(pl, 2, st); if ((rc = launch_col_solve(pl->d_spec, pl->d_inv_eig, pl->d_twx, pl->sp, st))) return rc; }
+  ProfScope ps(pl, 3, st);
   return launch_irfft_grad(pl->d_spec, u, v, u, v, p_or_null, pl->d_twy, pl->sp, st);
+}
+
+int explicit_prof(mlsim_plan* pl, const StageArgs& a, cudaStream_t st) {
+  ProfScope ps(pl, 0, st);
+  return launch_explicit(a, pl->sp, pl->d_forcing, st);
 }
 
 // One classic-RK4 step with a projection after every stage, in place on (u,v).
@@ -140,22 +162,22 @@ int solver_step(mlsim_plan* pl, float* u, float* v, float* p_or_null, cudaStream
   // stage 1: k1 = F(u0); acc = u0 + dt/6 k1; u* = u0 + dt/2 k1
   a.us = u; a.vs = v; a.outu = pl->d_w1u; a.outv = pl->d_w1v;
   a.ca = dt / 6.0f; a.cs = 0.5f * dt; a.mode = 1;
-  if ((rc = launch_explicit(a, pl->sp, pl->d_forcing, st))) return rc;
+  if ((rc = explicit_prof(pl, a, st))) return rc;
   if ((rc = project(pl, pl->d_w1u, pl->d_w1v, nullptr, st))) return rc;
   // stage 2: k2 = F(u1); acc += dt/3 k2; u* = u0 + dt/2 k2
   a.us = pl->d_w1u; a.vs = pl->d_w1v; a.outu = pl->d_w2u; a.outv = pl->d_w2v;
   a.ca = dt / 3.0f; a.cs = 0.5f * dt; a.mode = 2;
-  if ((rc = launch_explicit(a, pl->sp, pl->d_forcing, st))) return rc;
+  if ((rc = explicit_prof(pl, a, st))) return rc;
   if ((rc = project(pl, pl->d_w2u, pl->d_w2v, nullptr, st))) return rc;
   // stage 3: k3 = F(u2); acc += dt/3 k3; u* = u0 + dt k3
   a.us = pl->d_w2u; a.vs = pl->d_w2v; a.outu = pl->d_w1u; a.outv = pl->d_w1v;
   a.ca = dt / 3.0f; a.cs = dt; a.mode = 2;
-  if ((rc = launch_explicit(a, pl->sp, pl->d_forcing, st))) return rc;
+  if ((rc = explicit_prof(pl, a, st))) return rc;
   if ((rc = project(pl, pl->d_w1u, pl->d_w1v, nullptr, st))) return rc;
   // stage 4: k4 = F(u3); u* = acc + dt/6 k4  -> written over the caller's state, then projected
   a.us = pl->d_w1u; a.vs = pl->d_w1v; a.outu = u; a.outv = v;
   a.ca = 0.0f; a.cs = dt / 6.0f; a.mode = 3;
-  if ((rc = launch_explicit(a, pl->sp, pl->d_forcing, st))) return rc;
+  if ((rc = explicit_prof(pl, a, st))) return rc;
   return project(pl, u, v, p_or_null, st);
 }
 
@@ -172,7 +194,7 @@ int cnn_apply(mlsim_plan* pl, const float* u_in, const float* v_in, float* u, fl
   ConvFirstArgs f;
   f.u = u_in; f.v = v_in; f.out = pl->d_act[0]; f.wimg = pl->layers[0].d_wimg; f.scale = (float)scale;
   f.nx = c.nx; f.ny = c.ny; f.batch = c.batch;
-  if ((rc = launch_conv_first(f, pl->sm_count, st))) return rc;
+  { ProfScope ps(pl, 4, st); if ((rc = launch_conv_first(f, pl->sm_count, st))) return rc; }
   int cur = 0;
   for (int l = 1; l < L; ++l) {
     ConvMidArgs m;
@@ -182,8 +204,10 @@ int cnn_apply(mlsim_plan* pl, const float* u_in, const float* v_in, float* u, fl
     m.nx = c.nx; m.ny = c.ny; m.batch = c.batch; m.rs = pl->rs;
     m.cout = pl->layers[l].cout; m.relu = pl->layers[l].relu;
     if (l < L - 1) {
+      ProfScope ps(pl, 5, st);
       if ((rc = launch_conv_mid(m, pl->sm_count, st))) return rc;
     } else {
+      ProfScope ps(pl, 6, st);
       if ((rc = launch_conv_last(m, pl->sm_count, st))) return rc;
     }
     cur ^= 1;
@@ -269,6 +293,7 @@ int mlsim_plan_destroy(mlsim_plan* pl) {
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& l : pl->layers) if (l.d_wimg) cudaFree(l.d_wimg);
   if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
+  for (auto& e : pl->prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   delete pl;
   return MLSIM_OK;
 }
@@ -475,6 +500,36 @@ int mlsim_launches_per_step(mlsim_plan* pl, int32_t apply_cnn) {
 }
 
 int64_t mlsim_workspace_bytes(mlsim_plan* pl) { return pl ? pl->ws_bytes : 0; }
+
+int mlsim_profile_enable(mlsim_plan* pl, int32_t kernel_class, int32_t max_samples) {
+  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_REQUIRE(kernel_class >= -1 && kernel_class <= 6 && max_samples >= 0 && max_samples <= (1 << 20), "bad arguments");
+  MLSIM_CUDA_CHECK(cudaSetDevice(pl->cfg.device));
+  while ((int)pl->prof_events.size() < max_samples) {
+    cudaEvent_t a, b;
+    MLSIM_CUDA_CHECK(cudaEventCreate(&a));
+    MLSIM_CUDA_CHECK(cudaEventCreate(&b));
+    pl->prof_events.emplace_back(a, b);
+  }
+  pl->prof_class = kernel_class;
+  pl->prof_used = 0;
+  return MLSIM_OK;
+}
+
+int mlsim_profile_read(mlsim_plan* pl, float* total_ms, int32_t* count) {
+  if (!pl || !total_ms || !count) { set_error("null argument"); return MLSIM_EINVAL; }
+  float tot = 0.f;
+  for (size_t i = 0; i < pl->prof_used; ++i) {
+    MLSIM_CUDA_CHECK(cudaEventSynchronize(pl->prof_events[i].second));
+    float ms = 0.f;
+    MLSIM_CUDA_CHECK(cudaEventElapsedTime(&ms, pl->prof_events[i].first, pl->prof_events[i].second));
+    tot += ms;
+  }
+  *total_ms = tot;
+  *count = (int32_t)pl->prof_used;
+  pl->prof_used = 0;
+  return MLSIM_OK;
+}
 
 int mlsim_time_kernel(mlsim_plan* pl, int32_t which, int32_t warmup, int32_t iters, float* ms_out, void* stream) {
   if (!pl || !ms_out) { set_error("null argument"); return MLSIM_EINVAL; }

@@ -171,6 +171,15 @@ class Plan:
     def workspace_bytes(self) -> int:
         return int(self._lib.mlsim_workspace_bytes(self._h))
 
+    def profile_enable(self, kernel_class: int, max_samples: int = 4096) -> None:
+        _lib.check(self._lib.mlsim_profile_enable(self._h, kernel_class, max_samples))
+
+    def profile_read(self):
+        """(total device ms, launches) of the profiled kernel class since the last read."""
+        ms, n = C.c_float(0.0), C.c_int32(0)
+        _lib.check(self._lib.mlsim_profile_read(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
     def time_kernel(self, which: int, warmup: int = 3, iters: int = 10) -> float:
         ms = C.c_float(0.0)
         _lib.check(self._lib.mlsim_time_kernel(self._h, which, warmup, iters, C.byref(ms), self._stream()))

@@ -1,0 +1,373 @@
+"""GPU parity tests: every piece of the hot path, called through the C ABI (ctypes -> libmlsim_b200.so),
+against the CPU oracle on identical seeded inputs.
+
+Tolerance protocol (stated here):
+  * solver (fp32 kernels vs fp64 oracle):  relL2(K32, O64) <= 4 * relL2(O32, O64) + 2e-7 on u and v, where O32 is
+    the SAME oracle run in fp32 (self-calibrating: the kernels may be at most ~4x worse than a plain fp32
+    evaluation of the reference algorithm); after a projection  max|div| * h / max|v| <= 1e-5;
+  * CNN (bf16 tensor-core kernels): relL2(K, O_bf16emu) <= 1e-3 on the correction, O_bf16emu = oracle with
+    weights and inter-layer activations rounded to bf16 (fp64 accumulate);
+  * end to end: velocity after n steps of solver + correction, relL2 <= 4 * relL2(O32, O64) + 1e-6.
+"""
+import json
+import math
+import os
+
+import pytest
+import safetensors.torch as st
+import torch
+
+from oracle import cnn as OC
+from oracle import solver as S
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
+@pytest.fixture(scope="module")
+def mlsim(built_lib):
+    import ml_accelerated_simulation_b200 as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def mlacfd(golden_dir):
+    cfg = json.load(open(os.path.join(golden_dir, "MLACFD.json")))
+    sd = st.load_file(os.path.join(golden_dir, "mlacfd_weights.safetensors"))
+    return cfg, sd
+
+
+def _ic(nx, ny, batch, seed=42, **kw):
+    cfg = S.SolverConfig(nx=nx, ny=ny, **kw)
+    u, v = S.filtered_velocity_field(cfg, batch, seed=seed)
+    return cfg, u, v
+
+
+def _plan(mlsim, cfg, batch, **kw):
+    return mlsim.Plan(mlsim.PlanConfig(nx=cfg.nx, ny=cfg.ny, batch=batch, viscosity=cfg.viscosity, drag=cfg.drag,
+                                       forcing_scale=cfg.forcing_scale, advection=cfg.advection,
+                                       lw_dt_scale=cfg.lw_dt_scale, max_velocity=cfg.max_velocity, **kw))
+
+
+# --------------------------------------------------------------------------------------------- solver pieces
+@pytest.mark.parametrize("nx,ny,batch", [(64, 64, 1), (128, 128, 3), (64, 256, 2), (256, 64, 2), (512, 512, 1)])
+def test_explicit_terms(mlsim, nx, ny, batch):
+    cfg, u64, v64 = _ic(nx, ny, batch)
+    plan = _plan(mlsim, cfg, batch)
+    du, dv = plan.explicit_terms(u64.float().to(DEV), v64.float().to(DEV))
+    ou, ov = S.explicit_terms(u64, v64, cfg, cfg.dt)
+    qu, qv = S.explicit_terms(u64.float(), v64.float(), cfg, cfg.dt)
+    assert rel(du, ou) <= 4 * rel(qu, ou) + 2e-7
+    assert rel(dv, ov) <= 4 * rel(qv, ov) + 2e-7
+    plan.close()
+
+
+@pytest.mark.parametrize("advection,lw", [("upwind", 1.0), ("lax_wendroff", 1.0), ("lax_wendroff", 0.0), ("van_leer", 0.0)])
+def test_explicit_terms_scheme_switches(mlsim, advection, lw):
+    cfg, u64, v64 = _ic(64, 128, 2, advection=advection, lw_dt_scale=lw)
+    plan = _plan(mlsim, cfg, 2)
+    du, dv = plan.explicit_terms(u64.float().to(DEV), v64.float().to(DEV))
+    ou, ov = S.explicit_terms(u64, v64, cfg, cfg.dt)
+    assert rel(du, ou) < 5e-6 and rel(dv, ov) < 5e-6
+    plan.close()
+
+
+def test_explicit_terms_random_nonsolenoidal_and_zero_fields(mlsim):
+    cfg = S.SolverConfig(nx=128, ny=64)
+    g = torch.Generator().manual_seed(5)
+    u64 = torch.randn(2, 128, 64, generator=g, dtype=torch.float64) * 3
+    v64 = torch.randn(2, 128, 64, generator=g, dtype=torch.float64) * 3
+    u64[1] = 0.0                      # exercises the safe-division branches (all differences zero)
+    plan = _plan(mlsim, cfg, 2)
+    du, dv = plan.explicit_terms(u64.float().to(DEV), v64.float().to(DEV))
+    ou, ov = S.explicit_terms(u64.float().double(), v64.float().double(), cfg, cfg.dt)
+    assert torch.isfinite(du).all() and torch.isfinite(dv).all()
+    assert rel(du, ou) < 1e-5 and rel(dv, ov) < 1e-5
+    plan.close()
+
+
+@pytest.mark.parametrize("nx,ny,batch", [(64, 64, 1), (128, 256, 2), (256, 128, 3), (1024, 1024, 1), (2048, 64, 1)])
+def test_projection(mlsim, nx, ny, batch):
+    cfg = S.SolverConfig(nx=nx, ny=ny)
+    g = torch.Generator().manual_seed(nx + ny)
+    u64 = torch.randn(batch, nx, ny, generator=g, dtype=torch.float64)
+    v64 = torch.randn(batch, nx, ny, generator=g, dtype=torch.float64)
+    plan = _plan(mlsim, cfg, batch)
+    u, v = u64.float().to(DEV), v64.float().to(DEV)
+    p = plan.project(u, v)
+    ou, ov, op = S.pressure_projection(u64, v64, cfg)
+    qu, qv, qp = S.pressure_projection(u64.float(), v64.float(), cfg)
+    assert rel(u, ou) <= 4 * rel(qu, ou) + 2e-7
+    assert rel(v, ov) <= 4 * rel(qv, ov) + 2e-7
+    assert rel(p, op) <= 4 * rel(qp, op) + 1e-6
+    # invariants: divergence free, idempotent, zero-mean pressure
+    d = plan.divergence(u, v)
+    assert d.abs().max().item() * min(cfg.hx, cfg.hy) / u.abs().max().item() <= 1e-5
+    u2, v2 = u.clone(), v.clone()
+    plan.project(u2, v2, want_p=False)
+    assert rel(u2, u) < 2e-6 and rel(v2, v) < 2e-6
+    assert abs(p.mean().item()) <= 1e-6 * p.abs().max().item()
+    plan.close()
+
+
+def test_divergence_kernel(mlsim):
+    cfg, u64, v64 = _ic(64, 128, 2)
+    g = torch.Generator().manual_seed(9)
+    u64 = u64 + torch.randn(u64.shape, generator=g, dtype=torch.float64)
+    plan = _plan(mlsim, cfg, 2)
+    d = plan.divergence(u64.float().to(DEV), v64.float().to(DEV))
+    assert rel(d, S.divergence(u64.float().double(), v64.float().double(), cfg)) < 1e-5
+    plan.close()
+
+
+# --------------------------------------------------------------------------------------------- solver step
+@pytest.mark.parametrize("nx,ny,batch,checkpoints", [(64, 64, 1, (1, 10, 100)), (128, 128, 2, (1, 10)),
+                                                      (256, 256, 2, (1, 10)), (128, 512, 1, (1, 5))])
+def test_rk4_step_parity(mlsim, nx, ny, batch, checkpoints):
+    cfg, u64, v64 = _ic(nx, ny, batch)
+    plan = _plan(mlsim, cfg, batch)
+    u, v = u64.float().to(DEV), v64.float().to(DEV)
+    ou, ov = u64.clone(), v64.clone()
+    qu, qv = u64.float(), v64.float()
+    inv64, inv32 = S.inverse_eigenvalues(cfg), S.inverse_eigenvalues(cfg, torch.float32)
+    done = 0
+    for n in checkpoints:
+        plan.step(u, v, nsteps=n - done)
+        for _ in range(n - done):
+            ou, ov, op = S.rk4_step(ou, ov, cfg, None, inv64)
+            qu, qv, _ = S.rk4_step(qu, qv, cfg, None, inv32)
+        done = n
+        assert rel(u, ou) <= 4 * rel(qu, ou) + 2e-7, f"u after {n} steps"
+        assert rel(v, ov) <= 4 * rel(qv, ov) + 2e-7, f"v after {n} steps"
+    p = plan.new_field()
+    plan.step(u, v, nsteps=1, p=p)
+    ou, ov, op = S.rk4_step(ou, ov, cfg, None, inv64)
+    assert rel(p, op) < 2e-5
+    d = plan.divergence(u, v)
+    assert d.abs().max().item() * cfg.hx / u.abs().max().item() <= 1e-5
+    plan.close()
+
+
+def test_kolmogorov_laminar_fixed_point(mlsim):
+    """u = A sin(4 y_j), v = 0 is an exact fixed point of the discrete scheme."""
+    cfg = S.SolverConfig()
+    A = 1.0 / (cfg.viscosity * (4 / cfg.hx ** 2) * math.sin(4 * cfg.hx / 2) ** 2 + cfg.drag)
+    u0 = (A * S.forcing_profile(cfg))[None, None, :].expand(1, 64, 64).contiguous().float().to(DEV)
+    v0 = torch.zeros_like(u0)
+    plan = _plan(mlsim, cfg, 1)
+    u, v = u0.clone(), v0.clone()
+    plan.step(u, v, nsteps=20)
+    assert (u - u0).abs().max().item() < 2e-5 * A
+    assert v.abs().max().item() < 2e-5 * A
+    plan.close()
+
+
+def test_sim_test_smoke_property(mlsim):
+    """reference test/sim_test.py:79-85: 128^2, vmax 3, 2000 RK4 steps stay finite."""
+    cfg = S.SolverConfig(nx=128, ny=128, max_velocity=3.0)
+    u64, v64 = S.filtered_velocity_field(cfg, 1, seed=41, iterations=3)
+    plan = _plan(mlsim, cfg, 1)
+    u, v = u64.float().to(DEV), v64.float().to(DEV)
+    plan.step(u, v, nsteps=2000)
+    assert torch.isfinite(u).all() and torch.isfinite(v).all()
+    assert 0.1 < u.abs().max().item() < 10.0
+    plan.close()
+
+
+# --------------------------------------------------------------------------------------------- CNN
+@pytest.mark.parametrize("nx,ny,batch,scale", [(64, 64, 1, 1.0), (128, 128, 2, 1.0 / 7), (64, 256, 3, 1.0),
+                                               (256, 64, 1, 1.0), (512, 128, 1, 1.0)])
+def test_cnn_forward_mlacfd(mlsim, mlacfd, nx, ny, batch, scale):
+    from ml_accelerated_simulation_b200 import models
+    cfgj, sd = mlacfd
+    model = models.buildModel(cfgj)
+    model.load_state_dict(sd)
+    plan = mlsim.Plan(mlsim.PlanConfig(nx=nx, ny=ny, batch=batch))
+    model.attach(plan)
+    g = torch.Generator().manual_seed(7)
+    u = (torch.randn(batch, nx, ny, generator=g) * 3).to(DEV)
+    v = (torch.randn(batch, nx, ny, generator=g) * 3).to(DEV)
+    y = plan.cnn_forward(u, v, scale)
+    x = torch.stack((u.cpu().double(), v.cpu().double()), 1) * scale
+    y_emu = OC.model_forward(x, cfgj, sd, round_bf16=True)
+    y_64 = OC.model_forward(x, cfgj, sd)
+    assert rel(y, y_emu) <= 1e-3
+    assert rel(y, y_64) <= 1e-2                                 # bf16 storage error itself, reported not hidden
+    # zero padding at every domain edge (H5): compare the border ring on its own
+    yc = y.double().cpu()
+    for sl in ((..., 0, slice(None)), (..., -1, slice(None)), (..., slice(None), 0), (..., slice(None), -1)):
+        assert ((yc[sl] - y_emu[sl]).norm() / y_emu[sl].norm()).item() <= 2e-3
+    # fused correction add == separate add
+    uu, vv = u.clone(), v.clone()
+    plan.cnn_correct(uu, vv, scale)
+    assert rel(uu - u, y_emu[:, 0]) <= 2e-3 and rel(vv - v, y_emu[:, 1]) <= 2e-3
+    assert torch.allclose(uu, u + y[:, 0], atol=1e-6) and torch.allclose(vv, v + y[:, 1], atol=1e-6)
+    plan.close()
+
+
+def test_cnn_bn_folded_narrow_channels(mlsim, golden_dir):
+    """cnn1.json: channels 2-4-10-10-4-2 with BatchNorm (folded on load) -- ragged channel counts."""
+    from ml_accelerated_simulation_b200 import models
+    cfgj = json.load(open(os.path.join(golden_dir, "cnn1.json")))
+    sd = st.load_file(os.path.join(golden_dir, "cnn1_bn_weights.safetensors"))
+    model = models.buildModel(cfgj)
+    model.load_state_dict(sd)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 2, 64, 128, generator=g, dtype=torch.float64).to(DEV)
+    y = model(x)                                               # reference call shape: model([B,2,H,W]) -> [B,2,H,W]
+    assert y.shape == x.shape and y.dtype == x.dtype
+    y_emu = OC.model_forward(x.cpu().float().double(), cfgj, sd, round_bf16=True)
+    assert rel(y, y_emu) <= 1e-3
+
+
+def test_buildmodel_dropin_and_checkpoint_roundtrip(mlsim, mlacfd, tmp_path):
+    from ml_accelerated_simulation_b200 import models
+    cfgj, sd = mlacfd
+    torch.manual_seed(2025)
+    model = models.buildModel(cfgj)
+    # same module tree / key names as the reference => its checkpoints load, ours are readable by it
+    assert sorted(model.state_dict().keys()) == sorted(sd.keys())
+    model.load_state_dict(sd)
+    path = str(tmp_path / "CNN_roundtrip.safetensors")
+    st.save_model(model, path)                                  # what reference src/train.py:50 calls
+    again = st.load_file(path)
+    assert all(torch.equal(again[k], sd[k].to(again[k].dtype)) for k in sd)
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(1, 2, 64, 64))                        # CPU tensor: no fallback
+    with pytest.raises(NotImplementedError):
+        models.buildModel([{**cfgj[0], "kernel_sizes": 5}])
+
+
+# --------------------------------------------------------------------------------------------- end to end
+@pytest.mark.parametrize("nx,ny,batch,nsteps", [(64, 64, 1, 100), (128, 128, 2, 10)])
+def test_rollout_solver_plus_correction(mlsim, mlacfd, nx, ny, batch, nsteps):
+    """The hot loop of reference src/inference.py:100-102 (BASELINE config 1 at 64^2, 100 steps)."""
+    from ml_accelerated_simulation_b200 import models
+    from ml_accelerated_simulation_b200.rollout import Rollout
+    cfgj, sd = mlacfd
+    model = models.buildModel(cfgj)
+    model.load_state_dict(sd)
+    cfg, u64, v64 = _ic(nx, ny, batch)
+    ro = Rollout(mlsim.PlanConfig(nx=nx, ny=ny, batch=batch), model, input_scale=1.0)
+    u, v = u64.float().to(DEV), v64.float().to(DEV)
+    ro.step(u, v, nsteps)
+    ou, ov, _ = OC.rollout(u64, v64, cfg, nsteps, cfgj, sd, 1.0)
+    qu, qv, _ = OC.rollout(u64.float(), v64.float(), cfg, nsteps, cfgj, sd, 1.0)
+    assert torch.isfinite(u).all()
+    assert rel(u, ou) <= 4 * rel(qu, ou) + 1e-6
+    assert rel(v, ov) <= 4 * rel(qv, ov) + 1e-6
+    # host-buffer entry point gives the same answer
+    hu, hv = u64.float().clone(), v64.float().clone()
+    ro.step_host(hu, hv, nsteps)
+    assert rel(hu, u) < 1e-6 and rel(hv, v) < 1e-6
+
+
+def test_compat_layer_reads_like_the_reference_script(mlsim):
+    """Same calls as reference test/sim_test.py:36-81 with the package standing in for torch_cfd."""
+    from ml_accelerated_simulation_b200 import boundaries, grids
+    from ml_accelerated_simulation_b200 import finite_differences as fdm
+    from ml_accelerated_simulation_b200.equations import stable_time_step
+    from ml_accelerated_simulation_b200.forcings import KolmogorovForcing
+    from ml_accelerated_simulation_b200.fvm import NavierStokes2DFVMProjection, RKStepper
+    from ml_accelerated_simulation_b200.initial_conditions import filtered_velocity_field
+    n, diam = 128, 2 * math.pi
+    grid = grids.Grid((n, n), domain=((0, diam), (0, diam)), device=DEV)
+    v0 = filtered_velocity_field(grid, 3.0, 4.0, iterations=3, random_state=41, device=DEV, batch_size=2,
+                                 dtype=torch.float64)
+    assert v0.shape == (2, n, n) and v0.dtype == torch.float64
+    assert torch.linalg.norm(fdm.divergence(v0).data).item() < 1e-2
+    speed = torch.sqrt(v0[0].data ** 2 + v0[1].data ** 2).amax(dim=(-2, -1))
+    assert torch.allclose(speed, torch.full_like(speed, 3.0), rtol=1e-5)
+    boundaries.get_pressure_bc_from_velocity(v0)
+    dt = stable_time_step(dx=min(grid.step), max_velocity=3.0, max_courant_number=0.5, viscosity=1e-3)
+    step_fn = RKStepper.from_method(method="classic_rk4", requires_grad=False, dtype=torch.float64)
+    forcing_fn = KolmogorovForcing(diam=diam, wave_number=4, grid=grid, offsets=(v0[0].offset, v0[1].offset))
+    ns2d = NavierStokes2DFVMProjection(viscosity=1e-3, grid=grid, bcs=(v0[0].bc, v0[1].bc), density=1.0, drag=0.1,
+                                       forcing=forcing_fn, solver=step_fn).to(v0.device)
+    v = v0
+    for _ in range(3):
+        v, p = step_fn.forward(v, dt, equation=ns2d)
+    assert not torch.isnan(v[0].data).any()
+    cfg = S.SolverConfig(nx=n, ny=n, max_velocity=3.0)
+    ou, ov = v0[0].data.cpu(), v0[1].data.cpu()
+    for _ in range(3):
+        ou, ov, op = S.rk4_step(ou, ov, cfg, dt)
+    assert rel(v[0].data, ou) < 2e-6 and rel(v[1].data, ov) < 2e-6 and rel(p.data, op) < 5e-5
+
+
+def test_argument_errors_are_loud(mlsim):
+    plan = mlsim.Plan(mlsim.PlanConfig(nx=64, ny=64, batch=1))
+    good = plan.new_field().zero_()
+    with pytest.raises(ValueError):
+        plan.step(good.double(), good)                       # wrong dtype
+    with pytest.raises(ValueError):
+        plan.step(good[:, :32], good)                        # wrong shape
+    with pytest.raises(ValueError):
+        plan.step(good.cpu(), good)                          # host tensor on the device entry point
+    from ml_accelerated_simulation_b200._lib import MlsimError
+    with pytest.raises(MlsimError):
+        plan.step(good, good.clone(), apply_cnn=True)        # no network attached
+    with pytest.raises(MlsimError):
+        mlsim.Plan(mlsim.PlanConfig(nx=96, ny=64))
+    plan.close()
+
+
+# --------------------------------------------------------------------------------------------- full size
+def test_full_size_config2_properties(mlsim, mlacfd):
+    """BASELINE config 2 shape (256x256, batch 64): size-independent properties + spot parity."""
+    from ml_accelerated_simulation_b200 import models
+    cfgj, sd = mlacfd
+    model = models.buildModel(cfgj)
+    model.load_state_dict(sd)
+    nx = ny = 256
+    batch = 64
+    cfg, u2, v2 = _ic(nx, ny, 2)
+    idx = torch.arange(batch) % 2                               # trajectories 0,1,0,1,... : batch independence
+    u64, v64 = u2[idx], v2[idx]
+    plan = mlsim.Plan(mlsim.PlanConfig(nx=nx, ny=ny, batch=batch))
+    model.attach(plan)
+    u, v = u64.float().to(DEV), v64.float().to(DEV)
+    plan.step(u, v, nsteps=2, apply_cnn=False)
+    d = plan.divergence(u, v)
+    assert d.abs().max().item() * cfg.hx / u.abs().max().item() <= 1e-5
+    assert torch.equal(u[0], u[62]) and torch.equal(v[1], v[63])         # identical inputs -> identical outputs
+    ou, ov = u2, v2
+    for _ in range(2):
+        ou, ov, _ = S.rk4_step(ou, ov, cfg)
+    assert rel(u[:2], ou) < 1e-6 and rel(v[:2], ov) < 1e-6
+    plan.step(u, v, nsteps=1, apply_cnn=True)
+    assert torch.isfinite(u).all() and torch.isfinite(v).all()
+    assert torch.equal(u[0], u[62]) and torch.equal(v[1], v[63])
+    ou, ov, _ = OC.rollout(ou, ov, cfg, 1, cfgj, sd, 1.0)
+    assert rel(u[:2], ou) < 2e-6 and rel(v[:2], ov) < 2e-6
+    plan.close()
+
+
+def test_full_size_config3_cnn_crops(mlsim, mlacfd):
+    """BASELINE config 3 shape (1024x1024, batch 16): the CNN is local (7-pixel receptive radius), so the
+    oracle on corner / interior crops checks the full-size kernels including the zero-padded domain corners."""
+    from ml_accelerated_simulation_b200 import models
+    cfgj, sd = mlacfd
+    model = models.buildModel(cfgj)
+    model.load_state_dict(sd)
+    n, batch, m = 1024, 16, 7
+    plan = mlsim.Plan(mlsim.PlanConfig(nx=n, ny=n, batch=batch))
+    model.attach(plan)
+    g = torch.Generator().manual_seed(11)
+    u = (torch.randn(batch, n, n, generator=g) * 3).to(DEV)
+    v = (torch.randn(batch, n, n, generator=g) * 3).to(DEV)
+    y = plan.cnn_forward(u, v, 1.0).cpu().double()
+    for b, (x0, y0) in ((0, (0, 0)), (15, (n - 80, n - 80)), (7, (500, 120)), (3, (0, n - 80))):
+        x = torch.stack((u[b, x0:x0 + 80, y0:y0 + 80].cpu().double(), v[b, x0:x0 + 80, y0:y0 + 80].cpu().double()))[None]
+        ye = OC.model_forward(x, cfgj, sd, round_bf16=True)[0]
+        xs = slice(0 if x0 == 0 else m, 80 if x0 + 80 == n else 80 - m)
+        ys = slice(0 if y0 == 0 else m, 80 if y0 + 80 == n else 80 - m)
+        got = y[b, :, x0:x0 + 80, y0:y0 + 80][:, xs, ys]
+        assert ((got - ye[:, xs, ys]).norm() / ye[:, xs, ys].norm()).item() <= 1e-3
+    plan.close()

@@ -253,64 +253,76 @@ k_conv_mid(ConvMidArgs a) {
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
-      mbar_wait(wbar, 0);
-      tc_fence_after();
-      const uint32_t wbase = smem_u32(sW);
-      uint32_t m = 0, nb = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int strip = (item / nyt) % nstrips;
-        const int x0 = strip * a.rs;
-        const int x1 = min(x0 + a.rs, a.nx);
-        const int xlo = max(x0 - 1, 0), xhi = min(x1, a.nx - 1);
-        for (int X = xlo; X <= xhi; ++X, ++m) {
-          const uint32_t stage = m % CM_STAGES, use = m / CM_STAGES;
-          const int lo = max(X - 1, x0), hi = min(X + 1, x1 - 1);
-          // rows whose accumulation starts with this input row need their TMEM slot drained
-          for (int x = lo; x <= hi; ++x) {
-            const bool is_new = (x == X + 1) || (x == X && X == 0);
-            if (is_new) {
-              const uint32_t n = nb + (uint32_t)(x - x0);
-              mbar_wait(&tempty[n % CM_SLOTS], ((n / CM_SLOTS) & 1) ^ 1);
-            }
+    // The whole warp runs the (uniform) control flow; one elected lane issues tcgen05.mma / commit.
+    // Per input row the accumulator segments are resolved ONCE, then the 12 MMAs are issued back to back
+    // with descriptors that differ only by compile-time constants.
+    const bool leader = elect_one();
+    mbar_wait(wbar, 0);
+    tc_fence_after();
+    constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
+    const uint32_t b_lo0 = (smem_u32(sW) >> 4) | ((uint32_t)(L::LBO_B >> 4) << 16);
+    const uint32_t a_lo_stage0 = (smem_u32(sStage) >> 4) | ((uint32_t)(CM_PLANE >> 4) << 16);
+    uint32_t m = 0, nb = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int strip = (item / nyt) % nstrips;
+      const int x0 = strip * a.rs;
+      const int x1 = min(x0 + a.rs, a.nx);
+      const int xlo = max(x0 - 1, 0), xhi = min(x1, a.nx - 1);
+      for (int X = xlo; X <= xhi; ++X, ++m) {
+        const uint32_t stage = m % CM_STAGES, use = m / CM_STAGES;
+        const int lo = max(X - 1, x0), hi = min(X + 1, x1 - 1);
+        // ---- resolve accumulator segments (scalars only: no local-memory arrays on the issue path) ----
+        // rows lo..hi map to consecutive TMEM slots except across the ring wrap (slot 7 -> 0).
+        const uint32_t nlo = nb + (uint32_t)(lo - x0);
+        const int wrap_row = lo + (int)(CM_SLOTS - (nlo % CM_SLOTS));        // first row > lo whose slot is 0
+        const int c1 = (wrap_row <= hi) ? wrap_row : hi + 1;                 // ring-wrap cut
+        const int c2 = (X != 0 && X + 1 > lo && X + 1 <= hi) ? X + 1 : hi + 1;   // accumulate-flag cut (row X+1 is new)
+        auto seg_d = [&](int s0) { return tmem + ((nb + (uint32_t)(s0 - x0)) % CM_SLOTS) * NB; };
+        auto seg_i = [&](int s0, int s1) { return umma_idesc_bf16((s1 - s0 + 1) * NB); };
+        auto seg_b = [&](int s0) { return (uint32_t)((s0 - (X - 1)) * NB); };  // B row-block offset, 16-B units
+        auto is_new = [&](int x) { return (x == X + 1) || (x == X && X == 0); };
+        // other 11 MMAs: at most two segments
+        const int r0e = c1 - 1;
+        const uint32_t rd0 = seg_d(lo), ri0 = seg_i(lo, r0e), rb0 = seg_b(lo);
+        const bool has_r1 = c1 <= hi;
+        const uint32_t rd1 = seg_d(c1), ri1 = seg_i(c1, hi), rb1 = seg_b(c1);
+        // first MMA: at most three segments, cut at ca <= cb
+        const int ca = min(c1, c2), cb = max(c1, c2);
+        // rows whose accumulation starts with this input row need their TMEM slot drained
+        for (int x = lo; x <= hi; ++x) {
+          if ((x == X + 1) || (x == X && X == 0)) {
+            const uint32_t n = nb + (uint32_t)(x - x0);
+            mbar_wait(&tempty[n % CM_SLOTS], ((n / CM_SLOTS) & 1) ^ 1);
           }
-          mbar_wait(&full[stage], use & 1);
-          tc_fence_after();
-          const uint32_t abase = smem_u32(sStage + stage * CM_STAGE_BYTES);
-#pragma unroll 1
-          for (int dyi = 0; dyi < 3; ++dyi) {
-#pragma unroll 1
-            for (int k16 = 0; k16 < 4; ++k16) {
-              const bool first = (dyi == 0 && k16 == 0);
-              const uint64_t da = umma_desc(abase + dyi * 16 + k16 * 2 * CM_PLANE, CM_PLANE, 128);
-              int s0 = lo;
-              while (s0 <= hi) {
-                const uint32_t n0 = nb + (uint32_t)(s0 - x0);
-                const uint32_t slot0 = n0 % CM_SLOTS;
-                const bool new0 = (s0 == X + 1) || (s0 == X && X == 0);
-                int s1 = s0;
-                while (s1 + 1 <= hi) {
-                  const uint32_t slotn = (nb + (uint32_t)(s1 + 1 - x0)) % CM_SLOTS;
-                  if (slotn == 0) break;                               // ring wrap: columns not adjacent
-                  const bool newn = (s1 + 1 == X + 1) || (s1 + 1 == X && X == 0);
-                  if (first && newn != new0) break;                    // different accumulate flag
-                  ++s1;
-                }
-                const int nrows = s1 - s0 + 1;
-                const int bi = s0 - (X - 1);                           // dx block: 0 <-> dx=+1, 1 <-> 0, 2 <-> -1
-                const uint64_t db = umma_desc(wbase + dyi * L::WDY + k16 * 2 * L::LBO_B + bi * NB * 16, L::LBO_B, 128);
-                const uint32_t acc = first ? (new0 ? 0u : 1u) : 1u;
-                umma_bf16(tmem + slot0 * NB, da, db, umma_idesc_bf16(nrows * NB), acc);
-                s0 = s1 + 1;
-              }
+        }
+        mbar_wait(&full[stage], use & 1);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t a_lo = a_lo_stage0 + stage * (CM_STAGE_BYTES >> 4);
+#pragma unroll
+          for (int t = 0; t < 12; ++t) {
+            const int dyi = t >> 2, k16 = t & 3;
+            const uint32_t aoff = (uint32_t)((dyi * 16 + k16 * 2 * CM_PLANE) >> 4);
+            const uint32_t boff = (uint32_t)((dyi * L::WDY + k16 * 2 * L::LBO_B) >> 4);
+            const uint64_t da = ((uint64_t)DESC_HI << 32) | (uint64_t)(a_lo + aoff);
+            const uint64_t db0 = ((uint64_t)DESC_HI << 32) | (uint64_t)(b_lo0 + boff);
+            if (t == 0) {
+              umma_bf16(seg_d(lo), da, db0 + seg_b(lo), seg_i(lo, ca - 1), is_new(lo) ? 0u : 1u);
+              const bool three = (cb > ca) && (cb <= hi);
+              if (ca <= hi) umma_bf16(seg_d(ca), da, db0 + seg_b(ca), seg_i(ca, three ? cb - 1 : hi), is_new(ca) ? 0u : 1u);
+              if (three) umma_bf16(seg_d(cb), da, db0 + seg_b(cb), seg_i(cb, hi), is_new(cb) ? 0u : 1u);
+            } else {
+              umma_bf16(rd0, da, db0 + rb0, ri0, 1u);
+              if (has_r1) umma_bf16(rd1, da, db0 + rb1, ri1, 1u);
             }
           }
           umma_commit(&empty[stage]);                                  // smem stage free once the MMAs retire
           if (X - 1 >= x0) umma_commit(&tfull[(nb + (uint32_t)(X - 1 - x0)) % CM_SLOTS]);
           if (X == xhi && xhi == x1 - 1) umma_commit(&tfull[(nb + (uint32_t)(X - x0)) % CM_SLOTS]);
         }
-        nb += (uint32_t)(x1 - x0);
+        __syncwarp();
       }
+      nb += (uint32_t)(x1 - x0);
     }
   } else {
     // ------------------------------ epilogue (4 warps = 128 TMEM lanes) ------------------------------

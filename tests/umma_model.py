@@ -173,28 +173,34 @@ def conv_mid_model(act_in: np.ndarray, wimg: np.ndarray, B, nx, ny, rs, NB, relu
                 def is_new(x):
                     return (x == X + 1) or (x == X and X == 0)
 
-                for dyi in range(3):
-                    for k16 in range(4):
-                        first = dyi == 0 and k16 == 0
-                        da = make_desc(sbase + dyi * 16 + k16 * 2 * CM_PLANE, CM_PLANE, 128)
-                        s0 = lo
-                        while s0 <= hi:
-                            slot0 = (nb + s0 - x0) % CM_SLOTS
-                            new0 = is_new(s0)
-                            s1 = s0
-                            while s1 + 1 <= hi:
-                                slotn = (nb + s1 + 1 - x0) % CM_SLOTS
-                                if slotn == 0:
-                                    break
-                                if first and is_new(s1 + 1) != new0:
-                                    break
-                                s1 += 1
-                            nrows = s1 - s0 + 1
-                            bi = s0 - (X - 1)
-                            db = make_desc(dyi * WDY + k16 * 2 * LBO_B + bi * NB * 16, LBO_B, 128)
-                            acc = (not new0) if first else True
-                            umma(tmem, slot0 * NB, da, db, nrows * NB, smem, acc)
-                            s0 = s1 + 1
+                # closed-form segments, exactly as the kernel's MMA issuer computes them
+                nlo = nb + lo - x0
+                wrap_row = lo + (CM_SLOTS - nlo % CM_SLOTS)
+                c1 = wrap_row if wrap_row <= hi else hi + 1
+                c2 = X + 1 if (X != 0 and X + 1 > lo and X + 1 <= hi) else hi + 1
+                ca, cb = min(c1, c2), max(c1, c2)
+                three = cb > ca and cb <= hi
+
+                def issue(s0, s1, acc, da, dyi, k16):
+                    assert lo <= s0 <= s1 <= hi
+                    slot0 = (nb + s0 - x0) % CM_SLOTS
+                    bi = s0 - (X - 1)
+                    db = make_desc(dyi * WDY + k16 * 2 * LBO_B + bi * NB * 16, LBO_B, 128)
+                    umma(tmem, slot0 * NB, da, db, (s1 - s0 + 1) * NB, smem, acc)
+
+                for t in range(12):
+                    dyi, k16 = t >> 2, t & 3
+                    da = make_desc(sbase + dyi * 16 + k16 * 2 * CM_PLANE, CM_PLANE, 128)
+                    if t == 0:
+                        issue(lo, ca - 1, not is_new(lo), da, dyi, k16)
+                        if ca <= hi:
+                            issue(ca, cb - 1 if three else hi, not is_new(ca), da, dyi, k16)
+                        if three:
+                            issue(cb, hi, not is_new(cb), da, dyi, k16)
+                    else:
+                        issue(lo, c1 - 1, True, da, dyi, k16)
+                        if c1 <= hi:
+                            issue(c1, hi, True, da, dyi, k16)
                 if X - 1 >= x0:
                     done_rows.append(X - 1)
                 if X == xhi and xhi == x1 - 1:

@@ -262,71 +262,71 @@ k_conv_mid(ConvMidArgs a) {
     constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
     const uint32_t b_lo0 = (smem_u32(sW) >> 4) | ((uint32_t)(L::LBO_B >> 4) << 16);
     const uint32_t a_lo_stage0 = (smem_u32(sStage) >> 4) | ((uint32_t)(CM_PLANE >> 4) << 16);
-    uint32_t m = 0, nb = 0;
+    uint32_t nb = 0;
+    constexpr int A_K16_STEP = (2 * CM_PLANE) / 16, B_STEP = (2 * L::LBO_B) / 16;
+    uint32_t stage = 0, full_parity = 0;
+    static_assert((CM_SLOTS & (CM_SLOTS - 1)) == 0, "slot ring must be a power of two");
+    static_assert(8 * L::LBO_B == L::WDY, "B offsets must be uniformly spaced over (dy, k16)");
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const int strip = (item / nyt) % nstrips;
       const int x0 = strip * a.rs;
       const int x1 = min(x0 + a.rs, a.nx);
       const int xlo = max(x0 - 1, 0), xhi = min(x1, a.nx - 1);
-      for (int X = xlo; X <= xhi; ++X, ++m) {
-        const uint32_t stage = m % CM_STAGES, use = m / CM_STAGES;
+      for (int X = xlo; X <= xhi; ++X) {
         const int lo = max(X - 1, x0), hi = min(X + 1, x1 - 1);
-        // ---- resolve accumulator segments (scalars only: no local-memory arrays on the issue path) ----
-        // rows lo..hi map to consecutive TMEM slots except across the ring wrap (slot 7 -> 0).
+        // ---- accumulator segments: rows lo..hi sit in consecutive TMEM slots except across the ring wrap.
+        // Every slot is zero when a row starts using it (the epilogue re-zeroes it after draining), so all
+        // MMAs accumulate and one input row needs at most two segments of 12 MMAs each.
         const uint32_t nlo = nb + (uint32_t)(lo - x0);
-        const int wrap_row = lo + (int)(CM_SLOTS - (nlo % CM_SLOTS));        // first row > lo whose slot is 0
-        const int c1 = (wrap_row <= hi) ? wrap_row : hi + 1;                 // ring-wrap cut
-        const int c2 = (X != 0 && X + 1 > lo && X + 1 <= hi) ? X + 1 : hi + 1;   // accumulate-flag cut (row X+1 is new)
-        auto seg_d = [&](int s0) { return tmem + ((nb + (uint32_t)(s0 - x0)) % CM_SLOTS) * NB; };
-        auto seg_i = [&](int s0, int s1) { return umma_idesc_bf16((s1 - s0 + 1) * NB); };
-        auto seg_b = [&](int s0) { return (uint32_t)((s0 - (X - 1)) * NB); };  // B row-block offset, 16-B units
-        auto is_new = [&](int x) { return (x == X + 1) || (x == X && X == 0); };
-        // other 11 MMAs: at most two segments
-        const int r0e = c1 - 1;
-        const uint32_t rd0 = seg_d(lo), ri0 = seg_i(lo, r0e), rb0 = seg_b(lo);
-        const bool has_r1 = c1 <= hi;
-        const uint32_t rd1 = seg_d(c1), ri1 = seg_i(c1, hi), rb1 = seg_b(c1);
-        // first MMA: at most three segments, cut at ca <= cb
-        const int ca = min(c1, c2), cb = max(c1, c2);
-        // rows whose accumulation starts with this input row need their TMEM slot drained
-        for (int x = lo; x <= hi; ++x) {
-          if ((x == X + 1) || (x == X && X == 0)) {
-            const uint32_t n = nb + (uint32_t)(x - x0);
-            mbar_wait(&tempty[n % CM_SLOTS], ((n / CM_SLOTS) & 1) ^ 1);
-          }
+        const uint32_t slot_lo = nlo & (CM_SLOTS - 1);
+        const int nrows = hi - lo + 1;
+        const int first = min(nrows, (int)(CM_SLOTS - slot_lo));
+        const uint32_t rb0 = (uint32_t)((lo - (X - 1)) * NB);            // B row-block offset, 16-byte units
+        // the row that starts accumulating with this input row needs its slot drained + zeroed:
+        // tempty phase u completes when the slot is ready for its u-th use (phase 0 = initial zero fill)
+        if (X + 1 <= hi) {
+          const uint32_t n = nb + (uint32_t)(X + 1 - x0);
+          mbar_wait(&tempty[n & (CM_SLOTS - 1)], (n / CM_SLOTS) & 1);
         }
-        mbar_wait(&full[stage], use & 1);
+        if (X == 0) {
+          const uint32_t n = nb + (uint32_t)(0 - x0);
+          mbar_wait(&tempty[n & (CM_SLOTS - 1)], (n / CM_SLOTS) & 1);
+        }
+        mbar_wait(&full[stage], full_parity);
         tc_fence_after();
         if (leader) {
-          const uint32_t a_lo = a_lo_stage0 + stage * (CM_STAGE_BYTES >> 4);
-#pragma unroll
-          for (int t = 0; t < 12; ++t) {
-            const int dyi = t >> 2, k16 = t & 3;
-            const uint32_t aoff = (uint32_t)((dyi * 16 + k16 * 2 * CM_PLANE) >> 4);
-            const uint32_t boff = (uint32_t)((dyi * L::WDY + k16 * 2 * L::LBO_B) >> 4);
-            const uint64_t da = ((uint64_t)DESC_HI << 32) | (uint64_t)(a_lo + aoff);
-            const uint64_t db0 = ((uint64_t)DESC_HI << 32) | (uint64_t)(b_lo0 + boff);
-            if (t == 0) {
-              umma_bf16(seg_d(lo), da, db0 + seg_b(lo), seg_i(lo, ca - 1), is_new(lo) ? 0u : 1u);
-              const bool three = (cb > ca) && (cb <= hi);
-              if (ca <= hi) umma_bf16(seg_d(ca), da, db0 + seg_b(ca), seg_i(ca, three ? cb - 1 : hi), is_new(ca) ? 0u : 1u);
-              if (three) umma_bf16(seg_d(cb), da, db0 + seg_b(cb), seg_i(cb, hi), is_new(cb) ? 0u : 1u);
-            } else {
-              umma_bf16(rd0, da, db0 + rb0, ri0, 1u);
-              if (has_r1) umma_bf16(rd1, da, db0 + rb1, ri1, 1u);
-            }
-          }
+          const uint64_t da = ((uint64_t)DESC_HI << 32) | (uint64_t)(a_lo_stage0 + stage * (CM_STAGE_BYTES >> 4));
+          const uint64_t db = ((uint64_t)DESC_HI << 32) | (uint64_t)(b_lo0 + rb0);
+          umma_bf16_row12<A_K16_STEP, B_STEP>(tmem + slot_lo * NB, da, db, umma_idesc_bf16(first * NB));
+          if (first < nrows)                                            // ring wrap: remaining rows start at slot 0
+            umma_bf16_row12<A_K16_STEP, B_STEP>(tmem, da, db + (uint32_t)(first * NB),
+                                                                       umma_idesc_bf16((nrows - first) * NB));
           umma_commit(&empty[stage]);                                  // smem stage free once the MMAs retire
-          if (X - 1 >= x0) umma_commit(&tfull[(nb + (uint32_t)(X - 1 - x0)) % CM_SLOTS]);
-          if (X == xhi && xhi == x1 - 1) umma_commit(&tfull[(nb + (uint32_t)(X - x0)) % CM_SLOTS]);
+          if (X - 1 >= x0) umma_commit(&tfull[(nb + (uint32_t)(X - 1 - x0)) & (CM_SLOTS - 1)]);
+          if (X == xhi && xhi == x1 - 1) umma_commit(&tfull[(nb + (uint32_t)(X - x0)) & (CM_SLOTS - 1)]);
         }
         __syncwarp();
+        if (++stage == CM_STAGES) { stage = 0; full_parity ^= 1; }
       }
       nb += (uint32_t)(x1 - x0);
     }
   } else {
     // ------------------------------ epilogue (4 warps = 128 TMEM lanes) ------------------------------
     const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
+    // zero every accumulator slot once; afterwards each slot is re-zeroed right after it is drained
+    {
+      const uint32_t t0 = tmem + ((uint32_t)(quarter * 32) << 16);
+      if constexpr (NB == 64) {
+#pragma unroll
+        for (int c = 0; c < 512; c += 32) tmem_st32_fill(t0 + c, 0u);
+      } else {
+#pragma unroll
+        for (int c = 0; c < NB * CM_SLOTS; c += 16) tmem_st16_fill(t0 + c, 0u);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      if (lane == 0) for (int sl = 0; sl < CM_SLOTS; ++sl) mbar_arrive(&tempty[sl]);
+    }
     mbar_wait(wbar, 0);                               // bias lives behind the weight image
     uint32_t nb = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -347,6 +347,9 @@ k_conv_mid(ConvMidArgs a) {
           tmem_ld32(taddr, r0);
           tmem_ld32(taddr + 32, r1);
           tmem_ld_wait();
+          tmem_st32_fill(taddr, 0u);
+          tmem_st32_fill(taddr + 32, 0u);
+          tmem_st_wait();
           tc_fence_before();
           if (lane == 0) mbar_arrive(&tempty[slot]);
           if (y < a.ny) {
@@ -372,6 +375,8 @@ k_conv_mid(ConvMidArgs a) {
           uint32_t r[16];
           tmem_ld16(taddr, r);
           tmem_ld_wait();
+          tmem_st16_fill(taddr, 0u);
+          tmem_st_wait();
           tc_fence_before();
           if (lane == 0) mbar_arrive(&tempty[slot]);
           if (y < a.ny) {
@@ -408,7 +413,14 @@ k_conv_mid(ConvMidArgs a) {
 int launch_conv_first(const ConvFirstArgs& a, int sm_count, cudaStream_t st) {
   const int nyt = (a.ny + 127) / 128;
   const long ntiles = (long)a.batch * a.nx * nyt;
-  int grid = (int)(ntiles < (long)sm_count * 6 ? ntiles : (long)sm_count * 6);
+  static int occ = 0;
+  if (occ == 0) {
+    MLSIM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_conv_first, CF_THREADS, 0));
+    if (occ < 1) occ = 1;
+    if (occ > 8) occ = 8;               // 8 x 64 TMEM columns per SM
+  }
+  const long resident = (long)sm_count * occ;
+  int grid = (int)(ntiles < resident ? ntiles : resident);
   k_conv_first<<<grid, CF_THREADS, 0, st>>>(a);
   MLSIM_CUDA_CHECK(cudaGetLastError());
   return MLSIM_OK;

@@ -122,6 +122,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// Store 32 lanes x 32 columns of one 32-bit value (used to zero accumulator slots).
+__device__ __forceinline__ void tmem_st32_fill(uint32_t taddr, uint32_t v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(v)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16_fill(uint32_t taddr, uint32_t v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(v)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -162,6 +181,33 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The 12 accumulate-MMAs one staged input row feeds into one accumulator segment (3 dy shifts x 4 K16 slices),
+// issued back to back from ONE asm block so the issuing thread spends ~3 instructions per MMA.
+// Descriptor start-address fields advance by compile-time constants (16-byte units):
+//   A: +A_K16 per K16 slice, +1 per dy (one pixel = 16 B);   B: +B_STEP per (dy, K16) step.
+template <int A_K16, int B_STEP>
+__device__ __forceinline__ void umma_bf16_row12(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+#define MLSIM_MMA "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+#define MLSIM_NEXT_K "add.u64 da, da, %4;\n\tadd.u64 db, db, %5;\n\t"
+#define MLSIM_NEXT_DY "sub.u64 da, da, %6;\n\tadd.u64 db, db, %5;\n\t"
+  asm volatile(
+      "{\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .pred p;\n\t"
+      "setp.eq.u32 p, 1, 1;\n\t"
+      "mov.b64 da, %1;\n\t"
+      "mov.b64 db, %2;\n\t"
+      MLSIM_MMA MLSIM_NEXT_K MLSIM_MMA MLSIM_NEXT_K MLSIM_MMA MLSIM_NEXT_K MLSIM_MMA MLSIM_NEXT_DY
+      MLSIM_MMA MLSIM_NEXT_K MLSIM_MMA MLSIM_NEXT_K MLSIM_MMA MLSIM_NEXT_K MLSIM_MMA MLSIM_NEXT_DY
+      MLSIM_MMA MLSIM_NEXT_K MLSIM_MMA MLSIM_NEXT_K MLSIM_MMA MLSIM_NEXT_K MLSIM_MMA
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(A_K16), "n"(B_STEP), "n"(3 * A_K16 - 1)
+      : "memory");
+#undef MLSIM_MMA
+#undef MLSIM_NEXT_K
+#undef MLSIM_NEXT_DY
+}
+
 // Make `bar` track completion of all tcgen05 async ops issued so far by this thread.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

@@ -2,8 +2,8 @@
 
 It mirrors csrc/conv_kernels.cu step for step -- the activation layout in HBM, the bulk copies into the
 shared-memory stage, the UMMA shared-memory descriptors (no-swizzle K-major canonical layout), the
-input-stationary N = 3*NB issue sequence over the 8-slot TMEM ring with its accumulate flags and ring-wrap
-splits, and the epilogue -- but executes sequentially.  Because the operand images are the REAL bytes
+input-stationary N = 3*NB issue sequence over the 8-slot TMEM ring (zeroed slots, always-accumulate MMAs,
+ring-wrap splits), and the epilogue -- but executes sequentially.  Because the operand images are the REAL bytes
 produced by the C ABI's host packer (mlsim_cnn_pack_host) and the result is compared with the CPU oracle,
 this pins the index arithmetic of the kernels before any GPU time is spent.  It does not model
 synchronisation.
@@ -147,7 +147,7 @@ def conv_mid_model(act_in: np.ndarray, wimg: np.ndarray, B, nx, ny, rs, NB, relu
     plane = ny + 2
     rng = np.random.default_rng(0)
     for cta in range(grid):
-        tmem = np.full((128, NB * CM_SLOTS), np.nan)      # fresh TMEM is garbage
+        tmem = np.zeros((128, NB * CM_SLOTS))             # the epilogue warps zero every slot at kernel start
         smem[stage_off:] = rng.integers(0, 255, smem.size - stage_off, dtype=np.uint8)   # stale stage bytes
         m = 0
         nb = 0
@@ -173,34 +173,25 @@ def conv_mid_model(act_in: np.ndarray, wimg: np.ndarray, B, nx, ny, rs, NB, relu
                 def is_new(x):
                     return (x == X + 1) or (x == X and X == 0)
 
-                # closed-form segments, exactly as the kernel's MMA issuer computes them
+                # closed-form segments, exactly as the kernel's MMA issuer computes them: every slot is zero when a
+                # row starts using it, all MMAs accumulate, the only cut is the ring wrap (slot 7 -> 0)
                 nlo = nb + lo - x0
                 wrap_row = lo + (CM_SLOTS - nlo % CM_SLOTS)
                 c1 = wrap_row if wrap_row <= hi else hi + 1
-                c2 = X + 1 if (X != 0 and X + 1 > lo and X + 1 <= hi) else hi + 1
-                ca, cb = min(c1, c2), max(c1, c2)
-                three = cb > ca and cb <= hi
 
-                def issue(s0, s1, acc, da, dyi, k16):
+                def issue(s0, s1, da, dyi, k16):
                     assert lo <= s0 <= s1 <= hi
                     slot0 = (nb + s0 - x0) % CM_SLOTS
                     bi = s0 - (X - 1)
                     db = make_desc(dyi * WDY + k16 * 2 * LBO_B + bi * NB * 16, LBO_B, 128)
-                    umma(tmem, slot0 * NB, da, db, (s1 - s0 + 1) * NB, smem, acc)
+                    umma(tmem, slot0 * NB, da, db, (s1 - s0 + 1) * NB, smem, True)
 
                 for t in range(12):
                     dyi, k16 = t >> 2, t & 3
                     da = make_desc(sbase + dyi * 16 + k16 * 2 * CM_PLANE, CM_PLANE, 128)
-                    if t == 0:
-                        issue(lo, ca - 1, not is_new(lo), da, dyi, k16)
-                        if ca <= hi:
-                            issue(ca, cb - 1 if three else hi, not is_new(ca), da, dyi, k16)
-                        if three:
-                            issue(cb, hi, not is_new(cb), da, dyi, k16)
-                    else:
-                        issue(lo, c1 - 1, True, da, dyi, k16)
-                        if c1 <= hi:
-                            issue(c1, hi, True, da, dyi, k16)
+                    issue(lo, c1 - 1, da, dyi, k16)
+                    if c1 <= hi:
+                        issue(c1, hi, da, dyi, k16)
                 if X - 1 >= x0:
                     done_rows.append(X - 1)
                 if X == xhi and xhi == x1 - 1:
@@ -222,7 +213,7 @@ def conv_mid_model(act_in: np.ndarray, wimg: np.ndarray, B, nx, ny, rs, NB, relu
                                 out_act[o:o + 16] = h[c * 8:(c + 1) * 8].view(np.uint8)
                         else:
                             out_y[b, :, x, y] = acc
-                    tmem[:, slot * NB:(slot + 1) * NB] = np.nan       # slot drained: next user must overwrite
+                    tmem[:, slot * NB:(slot + 1) * NB] = 0.0          # slot re-zeroed right after it is drained
                 done_rows = []
                 m += 1
             nb += x1 - x0

@@ -38,12 +38,14 @@ constexpr int CF_LBO_A = 128 * 16;     // chunk plane stride of the A tile
 constexpr int CF_LBO_B = 64 * 16;      // chunk plane stride of the weight image
 constexpr int CF_WBYTES = 4 * CF_LBO_B;
 
+// Software pipeline per CTA (2 A buffers, 2 TMEM accumulators): while the MMAs of tile i run, the threads
+// already hold tile i+1's global loads in flight; tile i's epilogue stores overlap tile i+1's MMAs.
 __global__ void __launch_bounds__(CF_THREADS)
 k_conv_first(ConvFirstArgs a) {
-  __shared__ __align__(128) uint8_t sA[4 * CF_LBO_A];
+  __shared__ __align__(128) uint8_t sA[2][4 * CF_LBO_A];
   __shared__ __align__(128) uint8_t sW[CF_WBYTES];
   __shared__ float sBias[64];
-  __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t mbar[2];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -51,13 +53,15 @@ k_conv_first(ConvFirstArgs a) {
     reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(a.wimg) + i);
   if (tid < 64) sBias[tid] = __ldg(reinterpret_cast<const float*>(a.wimg + CF_WBYTES) + tid);
   if (tid == 0) {
-    mbar_init(&mbar, 1);
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
     fence_mbar_init();
   }
   if (warp == 0) {
-    tmem_alloc(&tmem_slot, 64);
+    tmem_alloc(&tmem_slot, 128);
     tmem_relinquish();
   }
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -67,16 +71,13 @@ k_conv_first(ConvFirstArgs a) {
   const int nyt = (a.ny + 127) >> 7;
   const int ntiles = a.batch * a.nx * nyt;
   const size_t plane = (size_t)(a.ny + 2);
-  uint32_t parity = 0;
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  // ---- im2col row of this thread's pixel: k = (i*3 + j)*2 + ch, i <-> dx+1, j <-> dy+1 ----
+  auto load_vals = [&](int tile, float (&val)[18]) {
     const int yt = tile % nyt;
     const int x = (tile / nyt) % a.nx;
     const int b = tile / (nyt * a.nx);
     const int y = yt * 128 + tid;
-
-    // ---- im2col row of this pixel: k = (i*3 + j)*2 + ch, i <-> dx+1, j <-> dy+1 ----
-    float val[18];
     const float* __restrict__ gu = a.u + (size_t)b * a.nx * a.ny;
     const float* __restrict__ gv = a.v + (size_t)b * a.nx * a.ny;
 #pragma unroll
@@ -87,43 +88,72 @@ k_conv_first(ConvFirstArgs a) {
         const int yy = y + j - 1;
         const bool in = (xx >= 0) && (xx < a.nx) && (yy >= 0) && (yy < a.ny);
         const size_t off = (size_t)xx * a.ny + yy;
-        val[(i * 3 + j) * 2 + 0] = in ? __ldg(gu + off) * a.scale : 0.0f;
-        val[(i * 3 + j) * 2 + 1] = in ? __ldg(gv + off) * a.scale : 0.0f;
+        val[(i * 3 + j) * 2 + 0] = in ? __ldg(gu + off) : 0.0f;
+        val[(i * 3 + j) * 2 + 1] = in ? __ldg(gv + off) : 0.0f;
       }
     }
+  };
+  auto store_a = [&](int buf, const float (&val)[18]) {
+    float s[18];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) s[k] = val[k] * a.scale;
     uint4 c0, c1, c2;
-    c0.x = pack_bf16(val[0], val[1]);   c0.y = pack_bf16(val[2], val[3]);
-    c0.z = pack_bf16(val[4], val[5]);   c0.w = pack_bf16(val[6], val[7]);
-    c1.x = pack_bf16(val[8], val[9]);   c1.y = pack_bf16(val[10], val[11]);
-    c1.z = pack_bf16(val[12], val[13]); c1.w = pack_bf16(val[14], val[15]);
-    c2.x = pack_bf16(val[16], val[17]); c2.y = 0u; c2.z = 0u; c2.w = 0u;
-    *reinterpret_cast<uint4*>(sA + 0 * CF_LBO_A + tid * 16) = c0;
-    *reinterpret_cast<uint4*>(sA + 1 * CF_LBO_A + tid * 16) = c1;
-    *reinterpret_cast<uint4*>(sA + 2 * CF_LBO_A + tid * 16) = c2;
-    *reinterpret_cast<uint4*>(sA + 3 * CF_LBO_A + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+    c0.x = pack_bf16(s[0], s[1]);   c0.y = pack_bf16(s[2], s[3]);
+    c0.z = pack_bf16(s[4], s[5]);   c0.w = pack_bf16(s[6], s[7]);
+    c1.x = pack_bf16(s[8], s[9]);   c1.y = pack_bf16(s[10], s[11]);
+    c1.z = pack_bf16(s[12], s[13]); c1.w = pack_bf16(s[14], s[15]);
+    c2.x = pack_bf16(s[16], s[17]); c2.y = 0u; c2.z = 0u; c2.w = 0u;
+    uint8_t* A = sA[buf];
+    *reinterpret_cast<uint4*>(A + 0 * CF_LBO_A + tid * 16) = c0;
+    *reinterpret_cast<uint4*>(A + 1 * CF_LBO_A + tid * 16) = c1;
+    *reinterpret_cast<uint4*>(A + 2 * CF_LBO_A + tid * 16) = c2;
+    *reinterpret_cast<uint4*>(A + 3 * CF_LBO_A + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async_smem();           // generic-proxy writes -> visible to the tensor core (async proxy)
-    __syncthreads();
-
+  };
+  auto issue = [&](int buf) {
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
       for (int k16 = 0; k16 < 2; ++k16) {
-        const uint64_t da = umma_desc(smem_u32(sA) + k16 * 2 * CF_LBO_A, CF_LBO_A, 128);
+        const uint64_t da = umma_desc(smem_u32(sA[buf]) + k16 * 2 * CF_LBO_A, CF_LBO_A, 128);
         const uint64_t db = umma_desc(smem_u32(sW) + k16 * 2 * CF_LBO_B, CF_LBO_B, 128);
-        umma_bf16(tmem, da, db, idesc, k16 > 0);
+        umma_bf16(tmem + buf * 64, da, db, idesc, k16 > 0);
       }
-      umma_commit(&mbar);
+      umma_commit(&mbar[buf]);
     }
-    mbar_wait(&mbar, parity);
-    parity ^= 1;
-    tc_fence_after();
+  };
 
+  int tile = blockIdx.x;
+  float val[18];
+  if (tile < ntiles) {
+    load_vals(tile, val);
+    store_a(0, val);
+    __syncthreads();
+    issue(0);
+  }
+  uint32_t parity0 = 0, parity1 = 0;
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int next = tile + gridDim.x;
+    const bool has_next = next < ntiles;
+    if (has_next) load_vals(next, val);                 // loads fly while we wait for this tile's MMAs
+    if (buf == 0) { mbar_wait(&mbar[0], parity0); parity0 ^= 1; }
+    else          { mbar_wait(&mbar[1], parity1); parity1 ^= 1; }
+    tc_fence_after();
     uint32_t r0[32], r1[32];
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + buf * 64;
     tmem_ld32(taddr, r0);
     tmem_ld32(taddr + 32, r1);
     tmem_ld_wait();
+    if (has_next) store_a(buf ^ 1, val);
+    tc_fence_before();
+    __syncthreads();                                    // A[buf^1] complete; accumulator `buf` fully read
+    if (has_next) issue(buf ^ 1);
 
+    const int yt = tile % nyt;
+    const int x = (tile / nyt) % a.nx;
+    const int b = tile / (nyt * a.nx);
+    const int y = yt * 128 + tid;
     if (y < a.ny) {
       uint8_t* orow = reinterpret_cast<uint8_t*>(a.out) +
                       ((((size_t)b * a.nx + x) * 8) * plane + (size_t)(y + 1)) * 16;
@@ -142,14 +172,13 @@ k_conv_first(ConvFirstArgs a) {
         *reinterpret_cast<uint4*>(orow + (size_t)c * plane * 16) = o;
       }
     }
-    tc_fence_before();
-    __syncthreads();                    // TMEM reads + smem A reuse ordered before the next tile's MMA
   }
 
+  tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     __syncwarp();
-    tmem_dealloc(tmem, 64);
+    tmem_dealloc(tmem, 128);
   }
 }
 
@@ -413,13 +442,7 @@ k_conv_mid(ConvMidArgs a) {
 int launch_conv_first(const ConvFirstArgs& a, int sm_count, cudaStream_t st) {
   const int nyt = (a.ny + 127) / 128;
   const long ntiles = (long)a.batch * a.nx * nyt;
-  static int occ = 0;
-  if (occ == 0) {
-    MLSIM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_conv_first, CF_THREADS, 0));
-    if (occ < 1) occ = 1;
-    if (occ > 8) occ = 8;               // 8 x 64 TMEM columns per SM
-  }
-  const long resident = (long)sm_count * occ;
+  const long resident = (long)sm_count * 4;      // 4 CTAs/SM: 2 x 64 TMEM columns each, ~110 registers/thread
   int grid = (int)(ntiles < resident ? ntiles : resident);
   k_conv_first<<<grid, CF_THREADS, 0, st>>>(a);
   MLSIM_CUDA_CHECK(cudaGetLastError());

@@ -21,25 +21,27 @@ constexpr int K1_TX = 32;
 constexpr int K1_HALO = 2;
 constexpr int K1_THREADS = 256;
 
-__device__ __forceinline__ float face_flux(float cl, float c, float cr, float crr, float w, float cfl,
-                                           int adv) {
-  // TVD face value times face velocity (App. A.3.2).  phi(r) = 2r/(1+r) is evaluated as
-  // 2*num/(d+num): identical for r = num/d > 0 and free of the inf/inf hazard when d is tiny.
+template <int ADV>
+__device__ __forceinline__ float face_flux(float cl, float c, float cr, float crr, float w, float cfl) {
+  // TVD face value times face velocity (App. A.3.2):  face = low - (low - high) * phi.
+  // With t = +-0.5*(1 -+ C) and d = cr - c:  high = low + t*d, so  face = low + (t*phi)*d.
+  // phi(r) = 2r/(1+r), r = num/d, is evaluated as 2*num/(d+num): identical for r > 0, one division, and
+  // free of the inf/inf hazard when d is tiny.  __fdividef: <= 2 ulp, |d+num| >= |num| so no overflow.
   const bool pos = w > 0.0f;
   const float low = pos ? c : cr;
-  if (adv == MLSIM_ADV_UPWIND) return low * w;
+  if (ADV == MLSIM_ADV_UPWIND) return low * w;
   const float d = cr - c;
-  const float courant = cfl * w;
-  const float high = pos ? fmaf(0.5f * (1.0f - courant), d, c) : fmaf(-0.5f * (1.0f + courant), d, cr);
-  if (adv == MLSIM_ADV_LAX_WENDROFF) return high * w;
+  const float hc = 0.5f * cfl * w;                          // half the Courant number
+  const float t = pos ? (0.5f - hc) : (-0.5f - hc);
+  if (ADV == MLSIM_ADV_LAX_WENDROFF) return fmaf(t, d, low) * w;
   const float num = pos ? (c - cl) : (crr - cr);
   const bool same = (num > 0.0f && d > 0.0f) || (num < 0.0f && d < 0.0f);
-  const float phi = same ? (2.0f * num) / (d + num) : 0.0f;
-  return (low - (low - high) * phi) * w;
+  const float phi = same ? __fdividef(2.0f * num, d + num) : 0.0f;
+  return fmaf(t * phi, d, low) * w;
 }
 
-template <int TY>
-__global__ void __launch_bounds__(K1_THREADS)
+template <int TY, int ADV>
+__global__ void __launch_bounds__(K1_THREADS, 3)
 k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
   constexpr int NTY = TY / 4;                 // threads along y
   constexpr int NG = K1_THREADS / NTY;        // row groups
@@ -75,7 +77,6 @@ k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
   const int g = threadIdx.x / NTY;
   const int lj = 4 + 4 * ty;                  // smem column of the thread's first cell
   const int li0 = K1_HALO + g * RPG;          // smem row of the thread's first cell
-  const int adv = p.advection;
 
 #define SU(i, j) su[(i) * SW + (j)]
 #define SV(i, j) sv[(i) * SW + (j)]
@@ -88,9 +89,9 @@ k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
     for (int k = 0; k < 4; ++k) {
       const int j = lj + k;
       const float wxu = 0.5f * (SU(i, j) + SU(i + 1, j));
-      fxu_prev[k] = face_flux(SU(i - 1, j), SU(i, j), SU(i + 1, j), SU(i + 2, j), wxu, p.dt_hx, adv);
+      fxu_prev[k] = face_flux<ADV>(SU(i - 1, j), SU(i, j), SU(i + 1, j), SU(i + 2, j), wxu, p.dt_hx);
       const float wxv = 0.5f * (SU(i, j) + SU(i, j + 1));
-      fxv_prev[k] = face_flux(SV(i - 1, j), SV(i, j), SV(i + 1, j), SV(i + 2, j), wxv, p.dt_hx, adv);
+      fxv_prev[k] = face_flux<ADV>(SV(i - 1, j), SV(i, j), SV(i + 1, j), SV(i + 2, j), wxv, p.dt_hx);
     }
   }
 
@@ -98,25 +99,36 @@ k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) frc[k] = __ldg(&forcing[j0 + 4 * ty + k]);
 
-#pragma unroll 2
+#pragma unroll 1
   for (int rr = 0; rr < RPG; ++rr) {
     const int i = li0 + rr;
+    // issue this row's RK operand loads first so their latency hides behind the flux arithmetic
+    const size_t off = img + (size_t)(i0 + (i - K1_HALO)) * p.ny + (j0 + 4 * ty);
+    float4 bu = make_float4(0.f, 0.f, 0.f, 0.f), bv = bu, au = bu, av = bu;
+    if (a.mode == 2) {
+      bu = __ldg(reinterpret_cast<const float4*>(a.u0 + off));
+      bv = __ldg(reinterpret_cast<const float4*>(a.v0 + off));
+    }
+    if (a.mode >= 2) {
+      au = *reinterpret_cast<const float4*>(a.accu + off);
+      av = *reinterpret_cast<const float4*>(a.accv + off);
+    }
     float fxu[4], fxv[4], fyu[5], fyv[5];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int j = lj + k;
       const float wxu = 0.5f * (SU(i, j) + SU(i + 1, j));
-      fxu[k] = face_flux(SU(i - 1, j), SU(i, j), SU(i + 1, j), SU(i + 2, j), wxu, p.dt_hx, adv);
+      fxu[k] = face_flux<ADV>(SU(i - 1, j), SU(i, j), SU(i + 1, j), SU(i + 2, j), wxu, p.dt_hx);
       const float wxv = 0.5f * (SU(i, j) + SU(i, j + 1));
-      fxv[k] = face_flux(SV(i - 1, j), SV(i, j), SV(i + 1, j), SV(i + 2, j), wxv, p.dt_hx, adv);
+      fxv[k] = face_flux<ADV>(SV(i - 1, j), SV(i, j), SV(i + 1, j), SV(i + 2, j), wxv, p.dt_hx);
     }
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
       const int j = lj - 1 + k;               // y-face between columns j and j+1
       const float wyu = 0.5f * (SV(i, j) + SV(i + 1, j));
-      fyu[k] = face_flux(SU(i, j - 1), SU(i, j), SU(i, j + 1), SU(i, j + 2), wyu, p.dt_hy, adv);
+      fyu[k] = face_flux<ADV>(SU(i, j - 1), SU(i, j), SU(i, j + 1), SU(i, j + 2), wyu, p.dt_hy);
       const float wyv = 0.5f * (SV(i, j) + SV(i, j + 1));
-      fyv[k] = face_flux(SV(i, j - 1), SV(i, j), SV(i, j + 1), SV(i, j + 2), wyv, p.dt_hy, adv);
+      fyv[k] = face_flux<ADV>(SV(i, j - 1), SV(i, j), SV(i, j + 1), SV(i, j + 2), wyv, p.dt_hy);
     }
     float ku[4], kv[4];
 #pragma unroll
@@ -134,31 +146,20 @@ k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
       fxu_prev[k] = fxu[k];
       fxv_prev[k] = fxv[k];
     }
-    // ---- RK combine + float4 I/O ----
-    const int gi = i0 + (i - K1_HALO);
-    const size_t off = img + (size_t)gi * p.ny + (j0 + 4 * ty);
+    // ---- RK combine + float4 I/O (the u0 / acc loads were issued at the top of the row) ----
     float4 ou, ov;
     if (a.mode == 0) {
       ou = make_float4(ku[0], ku[1], ku[2], ku[3]);
       ov = make_float4(kv[0], kv[1], kv[2], kv[3]);
     } else if (a.mode == 3) {
-      const float4 au = *reinterpret_cast<const float4*>(a.accu + off);
-      const float4 av = *reinterpret_cast<const float4*>(a.accv + off);
       ou = make_float4(fmaf(a.cs, ku[0], au.x), fmaf(a.cs, ku[1], au.y), fmaf(a.cs, ku[2], au.z), fmaf(a.cs, ku[3], au.w));
       ov = make_float4(fmaf(a.cs, kv[0], av.x), fmaf(a.cs, kv[1], av.y), fmaf(a.cs, kv[2], av.z), fmaf(a.cs, kv[3], av.w));
     } else {
-      float4 bu, bv;            // u0, v0
       if (a.mode == 1) {        // u_s == u0: already in shared memory
         bu = make_float4(SU(i, lj), SU(i, lj + 1), SU(i, lj + 2), SU(i, lj + 3));
         bv = make_float4(SV(i, lj), SV(i, lj + 1), SV(i, lj + 2), SV(i, lj + 3));
-      } else {
-        bu = __ldg(reinterpret_cast<const float4*>(a.u0 + off));
-        bv = __ldg(reinterpret_cast<const float4*>(a.v0 + off));
-      }
-      float4 au = bu, av = bv;
-      if (a.mode == 2) {
-        au = *reinterpret_cast<const float4*>(a.accu + off);
-        av = *reinterpret_cast<const float4*>(a.accv + off);
+        au = bu;
+        av = bv;
       }
       au = make_float4(fmaf(a.ca, ku[0], au.x), fmaf(a.ca, ku[1], au.y), fmaf(a.ca, ku[2], au.z), fmaf(a.ca, ku[3], au.w));
       av = make_float4(fmaf(a.ca, kv[0], av.x), fmaf(a.ca, kv[1], av.y), fmaf(a.ca, kv[2], av.z), fmaf(a.ca, kv[3], av.w));
@@ -174,25 +175,33 @@ k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
 #undef SV
 }
 
-template <int TY>
+template <int TY, int ADV>
 static int launch_explicit_ty(const StageArgs& a, const SolverParams& p, const float* forcing, cudaStream_t st) {
   constexpr int SW = TY + 8, SH = K1_TX + 2 * K1_HALO;
   const size_t smem = (size_t)2 * SH * SW * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
-    MLSIM_CUDA_CHECK(cudaFuncSetAttribute(k_explicit_rk<TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MLSIM_CUDA_CHECK(cudaFuncSetAttribute(k_explicit_rk<TY, ADV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   dim3 grid(p.ny / TY, p.nx / K1_TX, p.batch);
-  k_explicit_rk<TY><<<grid, K1_THREADS, smem, st>>>(a, p, forcing);
+  k_explicit_rk<TY, ADV><<<grid, K1_THREADS, smem, st>>>(a, p, forcing);
   MLSIM_CUDA_CHECK(cudaGetLastError());
   return MLSIM_OK;
 }
 
+template <int ADV>
+static int launch_explicit_adv(const StageArgs& a, const SolverParams& p, const float* forcing, cudaStream_t st) {
+  if (p.ny >= 128) return launch_explicit_ty<128, ADV>(a, p, forcing, st);
+  return launch_explicit_ty<64, ADV>(a, p, forcing, st);
+}
+
 int launch_explicit(const StageArgs& a, const SolverParams& p, const float* forcing, cudaStream_t st) {
-  if (p.ny >= 256) return launch_explicit_ty<256>(a, p, forcing, st);
-  if (p.ny == 128) return launch_explicit_ty<128>(a, p, forcing, st);
-  return launch_explicit_ty<64>(a, p, forcing, st);
+  switch (p.advection) {
+    case MLSIM_ADV_UPWIND: return launch_explicit_adv<MLSIM_ADV_UPWIND>(a, p, forcing, st);
+    case MLSIM_ADV_LAX_WENDROFF: return launch_explicit_adv<MLSIM_ADV_LAX_WENDROFF>(a, p, forcing, st);
+    default: return launch_explicit_adv<MLSIM_ADV_VAN_LEER>(a, p, forcing, st);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -7,7 +7,9 @@ Tolerance protocol (stated here):
     evaluation of the reference algorithm); after a projection  max|div| * h / max|v| <= 1e-5;
   * CNN (bf16 tensor-core kernels): relL2(K, O_bf16emu) <= 1e-3 on the correction, O_bf16emu = oracle with
     weights and inter-layer activations rounded to bf16 (fp64 accumulate);
-  * end to end: velocity after n steps of solver + correction, relL2 <= 4 * relL2(O32, O64) + 1e-6.
+  * end to end: velocity after n steps of solver + correction: relL2(K, O64 with bf16-emulated CNN) <=
+    4 * relL2(O32, O64) + 1e-6 (kernel round-off only), and relL2(K, O64) <= 2 * relL2(O64 bf16-emu, O64) + 1e-6
+    (the bf16 storage of weights/activations is the dominant, stated, error: ~1.9e-5 after 100 steps at 64^2).
 """
 import json
 import math
@@ -113,7 +115,7 @@ def test_projection(mlsim, nx, ny, batch):
     assert d.abs().max().item() <= max(4 * dq, 1e-5 * vmax / min(cfg.hx, cfg.hy))
     u2, v2 = u.clone(), v.clone()
     plan.project(u2, v2, want_p=False)
-    assert rel(u2, u) < 2e-6 and rel(v2, v) < 2e-6
+    assert rel(u2, u) <= 4 * rel(qu, ou) + 2e-6 and rel(v2, v) <= 4 * rel(qv, ov) + 2e-6
     assert abs(p.mean().item()) <= 1e-6 * p.abs().max().item()
     plan.close()
 
@@ -259,11 +261,16 @@ def test_rollout_solver_plus_correction(mlsim, mlacfd, nx, ny, batch, nsteps):
     ro = Rollout(mlsim.PlanConfig(nx=nx, ny=ny, batch=batch), model, input_scale=1.0)
     u, v = u64.float().to(DEV), v64.float().to(DEV)
     ro.step(u, v, nsteps)
-    ou, ov, _ = OC.rollout(u64, v64, cfg, nsteps, cfgj, sd, 1.0)
-    qu, qv, _ = OC.rollout(u64.float(), v64.float(), cfg, nsteps, cfgj, sd, 1.0)
+    ou, ov, _ = OC.rollout(u64, v64, cfg, nsteps, cfgj, sd, 1.0)                      # fp64 reference semantics
+    bu, bv, _ = OC.rollout(u64, v64, cfg, nsteps, cfgj, sd, 1.0, round_bf16=True)     # fp64 solver, bf16-storage CNN
+    qu, qv, _ = OC.rollout(u64.float(), v64.float(), cfg, nsteps, cfgj, sd, 1.0)      # plain fp32 evaluation
     assert torch.isfinite(u).all()
-    assert rel(u, ou) <= 4 * rel(qu, ou) + 1e-6
-    assert rel(v, ov) <= 4 * rel(qv, ov) + 1e-6
+    # kernels vs the oracle with the SAME storage precision in the CNN: fp32 round-off only
+    assert rel(u, bu) <= 4 * rel(qu, ou) + 1e-6
+    assert rel(v, bv) <= 4 * rel(qv, ov) + 1e-6
+    # vs the all-fp64 reference: dominated by (and no worse than 2x) the stated bf16 storage error of the CNN
+    assert rel(u, ou) <= 2 * rel(bu, ou) + 1e-6
+    assert rel(v, ov) <= 2 * rel(bv, ov) + 1e-6
     # host-buffer entry point gives the same answer
     hu, hv = u64.float().clone(), v64.float().clone()
     ro.step_host(hu, hv, nsteps)

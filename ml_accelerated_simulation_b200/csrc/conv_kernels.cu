@@ -191,7 +191,8 @@ constexpr int CM_STAGES = 6;
 constexpr int CM_NPX = 130;
 constexpr int CM_PLANE = CM_NPX * 16;            // 2080 B: LBO of the A operand
 constexpr int CM_STAGE_BYTES = 8 * CM_PLANE;     // 16640 B
-constexpr int CM_SLOTS = 8;
+constexpr int CM_SLOTS = 8;                      // TMEM accumulator slots of NB columns
+constexpr int CM_RING = 6;                       // rows cycle with period 6; slots 6,7 mirror ring positions 0,1
 
 template <int NB> struct ConvMidSmem {
   static constexpr int LBO_B = 3 * NB * 16;
@@ -291,53 +292,58 @@ k_conv_mid(ConvMidArgs a) {
     constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
     const uint32_t b_lo0 = (smem_u32(sW) >> 4) | ((uint32_t)(L::LBO_B >> 4) << 16);
     const uint32_t a_lo_stage0 = (smem_u32(sStage) >> 4) | ((uint32_t)(CM_PLANE >> 4) << 16);
-    uint32_t nb = 0;
     constexpr int A_K16_STEP = (2 * CM_PLANE) / 16, B_STEP = (2 * L::LBO_B) / 16;
-    uint32_t stage = 0, full_parity = 0;
-    static_assert((CM_SLOTS & (CM_SLOTS - 1)) == 0, "slot ring must be a power of two");
+    static_assert(CM_RING + 2 == CM_SLOTS, "window q0..q0+2 must fit the slots");
     static_assert(8 * L::LBO_B == L::WDY, "B offsets must be uniformly spaced over (dy, k16)");
+    // Incremental state (no division on the per-row path):
+    //   stage / full_parity : smem ring position of the next input row
+    //   qn                  : ring position (mod 6) of the next output row that will START accumulating
+    //   ready_par           : bit q = parity of the tempty[q] phase that row's slot(s) must have completed
+    uint32_t stage = 0, full_parity = 0;
+    uint32_t qn = 0, ready_par = 0;
+    const uint32_t da_hi = DESC_HI;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const int strip = (item / nyt) % nstrips;
       const int x0 = strip * a.rs;
       const int x1 = min(x0 + a.rs, a.nx);
       const int xlo = max(x0 - 1, 0), xhi = min(x1, a.nx - 1);
+      // q_first = ring position of output row x0 (== qn: rows start accumulating in order)
+      uint32_t q_first = qn;
       for (int X = xlo; X <= xhi; ++X) {
         const int lo = max(X - 1, x0), hi = min(X + 1, x1 - 1);
-        // ---- accumulator segments: rows lo..hi sit in consecutive TMEM slots except across the ring wrap.
-        // Every slot is zero when a row starts using it (the epilogue re-zeroes it after draining), so all
-        // MMAs accumulate and one input row needs at most two segments of 12 MMAs each.
-        const uint32_t nlo = nb + (uint32_t)(lo - x0);
-        const uint32_t slot_lo = nlo & (CM_SLOTS - 1);
+        // ---- accumulator window.  Output row with running index n has ring position q = n % 6.  The window of
+        // input row X is (X-1, X, X+1) at window positions 0..2 and ALWAYS occupies the three adjacent slots
+        // q0..q0+2 <= 7, q0 = ring position of row X-1: slots 6 and 7 mirror ring positions 0 and 1 (a row with
+        // q < 2 collects its first contributions in slot 6+q, its last in slot q; the epilogue adds the two).
+        // Hence ONE N = nrows*NB segment of 12 MMAs per input row.  Every slot is zero when a row starts using
+        // it (the epilogue re-zeroes after draining), so all MMAs accumulate.
+        const int dq = X - 1 - x0;                                       // -2 .. rs-1
+        uint32_t q0 = q_first + (uint32_t)(dq + CM_RING);                // ring position of (virtual) row X-1
+        q0 -= (q0 >= 2 * CM_RING) ? 2 * CM_RING : ((q0 >= CM_RING) ? CM_RING : 0);
+        while (q0 >= CM_RING) q0 -= CM_RING;                             // rs may exceed 6: at most a few iterations
+        const int pos_lo = lo - (X - 1);                                 // 0..2
         const int nrows = hi - lo + 1;
-        const int first = min(nrows, (int)(CM_SLOTS - slot_lo));
-        const uint32_t rb0 = (uint32_t)((lo - (X - 1)) * NB);            // B row-block offset, 16-byte units
-        // the row that starts accumulating with this input row needs its slot drained + zeroed:
-        // tempty phase u completes when the slot is ready for its u-th use (phase 0 = initial zero fill)
-        if (X + 1 <= hi) {
-          const uint32_t n = nb + (uint32_t)(X + 1 - x0);
-          mbar_wait(&tempty[n & (CM_SLOTS - 1)], (n / CM_SLOTS) & 1);
-        }
-        if (X == 0) {
-          const uint32_t n = nb + (uint32_t)(0 - x0);
-          mbar_wait(&tempty[n & (CM_SLOTS - 1)], (n / CM_SLOTS) & 1);
+        // rows that start accumulating with this input row (X+1, and row 0 of the image) need their slots drained
+        // and re-zeroed: tempty[q] completes phase u when ring position q is ready for its u-th use
+        const int nnew = ((X + 1 <= hi) ? 1 : 0) + ((X == 0) ? 1 : 0);
+        for (int k = 0; k < nnew; ++k) {
+          mbar_wait(&tempty[qn], (ready_par >> qn) & 1u);
+          ready_par ^= 1u << qn;
+          qn = (qn + 1 == CM_RING) ? 0 : qn + 1;
         }
         mbar_wait(&full[stage], full_parity);
         tc_fence_after();
         if (leader) {
-          const uint64_t da = ((uint64_t)DESC_HI << 32) | (uint64_t)(a_lo_stage0 + stage * (CM_STAGE_BYTES >> 4));
-          const uint64_t db = ((uint64_t)DESC_HI << 32) | (uint64_t)(b_lo0 + rb0);
-          umma_bf16_row12<A_K16_STEP, B_STEP>(tmem + slot_lo * NB, da, db, umma_idesc_bf16(first * NB));
-          if (first < nrows)                                            // ring wrap: remaining rows start at slot 0
-            umma_bf16_row12<A_K16_STEP, B_STEP>(tmem, da, db + (uint32_t)(first * NB),
-                                                                       umma_idesc_bf16((nrows - first) * NB));
+          const uint64_t da = ((uint64_t)da_hi << 32) | (uint64_t)(a_lo_stage0 + stage * (CM_STAGE_BYTES >> 4));
+          const uint64_t db = ((uint64_t)da_hi << 32) | (uint64_t)(b_lo0 + (uint32_t)(pos_lo * NB));
+          umma_bf16_row12<A_K16_STEP, B_STEP>(tmem + (q0 + (uint32_t)pos_lo) * NB, da, db, umma_idesc_bf16(nrows * NB));
           umma_commit(&empty[stage]);                                  // smem stage free once the MMAs retire
-          if (X - 1 >= x0) umma_commit(&tfull[(nb + (uint32_t)(X - 1 - x0)) & (CM_SLOTS - 1)]);
-          if (X == xhi && xhi == x1 - 1) umma_commit(&tfull[(nb + (uint32_t)(X - x0)) & (CM_SLOTS - 1)]);
+          if (X - 1 >= x0) umma_commit(&tfull[q0]);                    // output row X-1 complete
+          if (X == xhi && xhi == x1 - 1) umma_commit(&tfull[(q0 + 1 == CM_RING) ? 0 : q0 + 1]);   // image bottom: row X too
         }
         __syncwarp();
         if (++stage == CM_STAGES) { stage = 0; full_parity ^= 1; }
       }
-      nb += (uint32_t)(x1 - x0);
     }
   } else {
     // ------------------------------ epilogue (4 warps = 128 TMEM lanes) ------------------------------
@@ -357,7 +363,7 @@ k_conv_mid(ConvMidArgs a) {
       if (lane == 0) for (int sl = 0; sl < CM_SLOTS; ++sl) mbar_arrive(&tempty[sl]);
     }
     mbar_wait(wbar, 0);                               // bias lives behind the weight image
-    uint32_t nb = 0;
+    uint32_t slot = 0, done_par = 0;                  // ring position of the next row to drain; per-position phase parity
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const int yt = item % nyt;
       const int strip = (item / nyt) % nstrips;
@@ -366,11 +372,12 @@ k_conv_mid(ConvMidArgs a) {
       const int x1 = min(x0 + a.rs, a.nx);
       const int y = yt * 128 + quarter * 32 + lane;
       for (int x = x0; x < x1; ++x) {
-        const uint32_t n = nb + (uint32_t)(x - x0);
-        const uint32_t slot = n % CM_SLOTS;
-        mbar_wait(&tfull[slot], (n / CM_SLOTS) & 1);
+        // ring position `slot` (q); q < 2 also owns mirror slot 6+q
+        mbar_wait(&tfull[slot], (done_par >> slot) & 1u);
+        done_par ^= 1u << slot;
         tc_fence_after();
         const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + slot * NB;
+        const uint32_t maddr = taddr + CM_RING * NB;         // mirror slot (meaningful when slot < 2)
         if constexpr (!LAST) {
           uint32_t r0[32], r1[32];
           tmem_ld32(taddr, r0);
@@ -378,6 +385,19 @@ k_conv_mid(ConvMidArgs a) {
           tmem_ld_wait();
           tmem_st32_fill(taddr, 0u);
           tmem_st32_fill(taddr + 32, 0u);
+          if (slot < 2) {                                    // add the partial sums parked in the mirror slot
+            uint32_t t[32];
+            tmem_ld32(maddr, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) r0[k] = __float_as_uint(__uint_as_float(r0[k]) + __uint_as_float(t[k]));
+            tmem_ld32(maddr + 32, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) r1[k] = __float_as_uint(__uint_as_float(r1[k]) + __uint_as_float(t[k]));
+            tmem_st32_fill(maddr, 0u);
+            tmem_st32_fill(maddr + 32, 0u);
+          }
           tmem_st_wait();
           tc_fence_before();
           if (lane == 0) mbar_arrive(&tempty[slot]);
@@ -405,6 +425,14 @@ k_conv_mid(ConvMidArgs a) {
           tmem_ld16(taddr, r);
           tmem_ld_wait();
           tmem_st16_fill(taddr, 0u);
+          if (slot < 2) {
+            uint32_t t[16];
+            tmem_ld16(maddr, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) + __uint_as_float(t[k]));
+            tmem_st16_fill(maddr, 0u);
+          }
           tmem_st_wait();
           tc_fence_before();
           if (lane == 0) mbar_arrive(&tempty[slot]);
@@ -423,8 +451,8 @@ k_conv_mid(ConvMidArgs a) {
             }
           }
         }
+        slot = (slot + 1 == CM_RING) ? 0 : slot + 1;
       }
-      nb += (uint32_t)(x1 - x0);
     }
   }
 

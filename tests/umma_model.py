@@ -16,6 +16,7 @@ CM_NPX = 130
 CM_PLANE = CM_NPX * 16
 CM_STAGE_BYTES = 8 * CM_PLANE
 CM_SLOTS = 8
+CM_RING = 6
 
 
 def bf16_round(x: np.ndarray) -> np.ndarray:
@@ -173,32 +174,27 @@ def conv_mid_model(act_in: np.ndarray, wimg: np.ndarray, B, nx, ny, rs, NB, relu
                 def is_new(x):
                     return (x == X + 1) or (x == X and X == 0)
 
-                # closed-form segments, exactly as the kernel's MMA issuer computes them: every slot is zero when a
-                # row starts using it, all MMAs accumulate, the only cut is the ring wrap (slot 7 -> 0)
-                nlo = nb + lo - x0
-                wrap_row = lo + (CM_SLOTS - nlo % CM_SLOTS)
-                c1 = wrap_row if wrap_row <= hi else hi + 1
-
-                def issue(s0, s1, da, dyi, k16):
-                    assert lo <= s0 <= s1 <= hi
-                    slot0 = (nb + s0 - x0) % CM_SLOTS
-                    bi = s0 - (X - 1)
-                    db = make_desc(dyi * WDY + k16 * 2 * LBO_B + bi * NB * 16, LBO_B, 128)
-                    umma(tmem, slot0 * NB, da, db, (s1 - s0 + 1) * NB, smem, True)
-
+                # accumulator window, exactly as the kernel's MMA issuer computes it: ring period 6, slots 6 and 7
+                # mirror ring positions 0 and 1, so the window (X-1, X, X+1) is always slots q0..q0+2 (one segment)
+                q0 = (nb + CM_RING + X - 1 - x0) % CM_RING
+                pos_lo = lo - (X - 1)
+                nrows = hi - lo + 1
+                assert q0 + pos_lo + nrows <= CM_SLOTS
                 for t in range(12):
                     dyi, k16 = t >> 2, t & 3
                     da = make_desc(sbase + dyi * 16 + k16 * 2 * CM_PLANE, CM_PLANE, 128)
-                    issue(lo, c1 - 1, da, dyi, k16)
-                    if c1 <= hi:
-                        issue(c1, hi, da, dyi, k16)
+                    db = make_desc(dyi * WDY + k16 * 2 * LBO_B + pos_lo * NB * 16, LBO_B, 128)
+                    umma(tmem, (q0 + pos_lo) * NB, da, db, nrows * NB, smem, True)
                 if X - 1 >= x0:
                     done_rows.append(X - 1)
                 if X == xhi and xhi == x1 - 1:
                     done_rows.append(X)
                 # epilogue for rows completed by this input row
                 for x in done_rows:
-                    slot = (nb + x - x0) % CM_SLOTS
+                    slot = (nb + x - x0) % CM_RING
+                    if slot < 2:        # partial sums parked in the mirror slot
+                        tmem[:, slot * NB:(slot + 1) * NB] += tmem[:, (CM_RING + slot) * NB:(CM_RING + slot + 1) * NB]
+                        tmem[:, (CM_RING + slot) * NB:(CM_RING + slot + 1) * NB] = 0.0
                     for mm in range(128):
                         y = y0 + mm
                         if y >= ny:

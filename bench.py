@@ -33,6 +33,7 @@ UNIT = "cell-steps/s"
 SOLVER_BYTES_PER_CELL_STEP = 312            # 74 fp32 words solver + 4 words correction add
 CNN_FLOP_PER_CELL = 373248                  # MLACFD: 2*9*(2*64 + 5*64*64 + 64*2)
 MID_FLOP_PER_CELL = 2 * 9 * 64 * 64         # one 64->64 layer (the dominant kernel)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 1.0698e9     # dram__bytes_read.sum + dram__bytes_write.sum of k_conv_mid<64> at this workload
 WORKLOAD = f"{NX}x{NY} grid, batch {BATCH} trajectories per GPU, RK4 solver step + MLACFD correction CNN"
 
 
@@ -57,7 +58,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -155,14 +156,15 @@ def run_reference(args):
     if rank != 0:
         return
     nsample = 1
-    rate, sec_per_step, threads = cpu_oracle_rate(nsample, args.steps, min(args.warmup, 2))
+    steps = min(args.steps, 40)                 # bounded: ~1.3 s of 16-core CPU work per sampled step
+    rate, sec_per_step, threads = cpu_oracle_rate(nsample, steps, min(args.warmup, 2))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": sec_per_step * 1e3,
+        "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": sec_per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "timed_on": "host CPU"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{nsample} of {BATCH} trajectories per step, {args.steps} steps"},
+                         "sample": f"{nsample} of {BATCH} trajectories per step, {steps} steps (requested {args.steps})"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -265,7 +267,7 @@ def run_ours(args):
         "roofline": {"kernel": "k_conv_mid<64> (3x3 conv 64->64, tcgen05 implicit GEMM)", "bound": "tensor",
                      "achieved": mid_tflops, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
                      "frac": mid_tflops / peaks["tensor_tflops"], "frac_of_burst": mid_tflops / peaks["tensor_tflops_burst"],
-                     "traffic": None, "launches_timed": mid_n, "avg_launch_ms": mid_avg_ms,
+                     "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_unit": "B/launch (ncu dram read+write, profiles/r01_ncu_summary.txt); algorithmic 1.074e9 B (541 MB bf16 activations in + out)", "launches_timed": mid_n, "avg_launch_ms": mid_avg_ms,
                      "share_of_step": mid_ms / ms_total, "peak_source": peaks["source"]},
         "solver_roofline": {"bound": "hbm", "ms_per_step": solver_ms, "cell_steps_per_s": solver_rate,
                             "achieved": SOLVER_BYTES_PER_CELL_STEP * solver_rate / 1e9, "peak": peaks["hbm_gbs"],
@@ -288,7 +290,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

@@ -187,7 +187,8 @@ k_conv_first(ConvFirstArgs a) {
 // Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer, warps 2..5 = epilogue.
 // =============================================================================================
 constexpr int CM_THREADS = 192;
-constexpr int CM_STAGES = 6;
+constexpr int CM_STAGES_MID = 6;                 // smem input-row ring depth, mid layers (1 CTA/SM)
+constexpr int CM_STAGES_LAST = 5;                // last layer: 2 CTAs/SM (issue-bound N=48 MMAs), 101.6 KB each
 constexpr int CM_NPX = 130;
 constexpr int CM_PLANE = CM_NPX * 16;            // 2080 B: LBO of the A operand
 constexpr int CM_STAGE_BYTES = 8 * CM_PLANE;     // 16640 B
@@ -195,6 +196,7 @@ constexpr int CM_SLOTS = 8;                      // TMEM accumulator slots of NB
 constexpr int CM_RING = 6;                       // rows cycle with period 6; slots 6,7 mirror ring positions 0,1
 
 template <int NB> struct ConvMidSmem {
+  static constexpr int CM_STAGES = (NB == 64) ? CM_STAGES_MID : CM_STAGES_LAST;
   static constexpr int LBO_B = 3 * NB * 16;
   static constexpr int WDY = 8 * LBO_B;
   static constexpr int WBYTES = 3 * WDY;
@@ -209,6 +211,7 @@ template <int NB, bool LAST>
 __global__ void __launch_bounds__(CM_THREADS, 1)
 k_conv_mid(ConvMidArgs a) {
   using L = ConvMidSmem<NB>;
+  constexpr int CM_STAGES = L::CM_STAGES;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sW = smem;
   const float* sBias = reinterpret_cast<const float*>(smem + L::BIAS_OFF);
@@ -495,7 +498,8 @@ static int launch_conv_mid_t(const ConvMidArgs& a, int sm_count, cudaStream_t st
   const int nyt = (a.ny + 127) / 128;
   const int nstrips = (a.nx + a.rs - 1) / a.rs;
   const long nitems = (long)a.batch * nstrips * nyt;
-  const int grid = (int)(nitems < sm_count ? nitems : sm_count);
+  const long resident = (long)sm_count * (LAST ? 2 : 1);
+  const int grid = (int)(nitems < resident ? nitems : resident);
   k_conv_mid<NB, LAST><<<grid, CM_THREADS, L::TOTAL, st>>>(a);
   MLSIM_CUDA_CHECK(cudaGetLastError());
   return MLSIM_OK;

@@ -193,17 +193,17 @@ def run_ours(args):
     cells = BATCH * NX * NY
     K, W = args.steps, max(args.warmup, 3)
 
+    from ml_accelerated_simulation_b200 import ensemble
+
+    # ensemble of BATCH*world independent trajectories, contiguous block per rank, no data-path collective
+    _, my_batch = ensemble.shard_batch(BATCH * world, rank, world)
+    assert my_batch == BATCH
+
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        ensemble.barrier(dev)
 
     def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return ensemble.max_over_ranks(x, dev)
 
     # ---------------- device-resident throughput (value) ----------------
     plan.step(u, v, nsteps=W, apply_cnn=True)

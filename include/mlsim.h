@@ -104,6 +104,11 @@ int64_t mlsim_workspace_bytes(mlsim_plan* plan);
  * 6 last conv + correction add.  Runs `iters` launches after `warmup`, returns mean ms in *ms_out. */
 int  mlsim_time_kernel(mlsim_plan* plan, int32_t which, int32_t warmup, int32_t iters, float* ms_out, void* stream);
 
+/* Developer aid: mean per-CTA cycle counters of the last conv kernel run by mlsim_time_kernel(5|6):
+ * out8 = {MMA-warp total, waiting for drained accumulators, waiting for staged input rows, issuing,
+ * input rows, epilogue-warp total, epilogue waiting for finished accumulators, unused}.  Returns #CTAs. */
+int  mlsim_conv_debug(mlsim_plan* plan, double* out8);
+
 /* In-step profiling: bracket every launch of one kernel class (numbering as in mlsim_time_kernel; -1 = off)
  * with CUDA events on the launching stream, for up to max_samples launches; mlsim_profile_read synchronises
  * on the recorded events, returns the summed device time and the number of launches, and resets the count. */

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "mlsim_launches_per_step": (C.c_int, [C.c_void_p, C.c_int32]),
     "mlsim_workspace_bytes": (C.c_int64, [C.c_void_p]),
     "mlsim_time_kernel": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_void_p]),
+    "mlsim_conv_debug": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "mlsim_profile_enable": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "mlsim_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "mlsim_last_error": (C.c_char_p, []),

@@ -184,9 +184,11 @@ k_conv_first(ConvFirstArgs a) {
 
 // =============================================================================================
 // Mid / last layers: 64 -> NB channels per dx block (NB = 64 mid, 16 last).
-// Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer, warps 2..5 = epilogue.
+// Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer, warps 2.. = epilogue (mid layers: 8 warps,
+// two per TMEM lane quarter, each draining one 32-column half of the slot; last layer: 4 warps).
 // =============================================================================================
-constexpr int CM_THREADS = 192;
+constexpr int CM_THREADS_MID = 64 + 8 * 32;       // producer + MMA + 8 epilogue warps
+constexpr int CM_THREADS_LAST = 64 + 4 * 32;
 constexpr int CM_STAGES_MID = 6;                 // smem input-row ring depth, mid layers (1 CTA/SM)
 constexpr int CM_STAGES_LAST = 5;                // last layer: 2 CTAs/SM (issue-bound N=48 MMAs), 101.6 KB each
 constexpr int CM_NPX = 130;
@@ -208,8 +210,9 @@ template <int NB> struct ConvMidSmem {
 };
 
 template <int NB, bool LAST>
-__global__ void __launch_bounds__(CM_THREADS, 1)
+__global__ void __launch_bounds__(LAST ? CM_THREADS_LAST : CM_THREADS_MID, 1)
 k_conv_mid(ConvMidArgs a) {
+  constexpr int EPI_WARPS = LAST ? 4 : 8;
   using L = ConvMidSmem<NB>;
   constexpr int CM_STAGES = L::CM_STAGES;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -229,7 +232,7 @@ k_conv_mid(ConvMidArgs a) {
 
   if (tid == 0) {
     for (int s = 0; s < CM_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < CM_SLOTS; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    for (int s = 0; s < CM_SLOTS; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EPI_WARPS); }
     mbar_init(wbar, 1);
     fence_mbar_init();
   }
@@ -247,21 +250,32 @@ k_conv_mid(ConvMidArgs a) {
   const int nitems = a.batch * nstrips * nyt;
   const size_t plane = (size_t)(a.ny + 2);
 
+  // Bookkeeping shared by the roles (all incremental, no division on the per-row paths):
+  //  * input rows go through the smem ring `stage` (parity flips on wrap);
+  //  * output row with running index n has ring position q = n % 6 and accumulates in TMEM slot q, except that a
+  //    row with q < 2 collects its first contributions in mirror slot 6+q (so that the window of input row X --
+  //    rows X-1, X, X+1 at window positions 0..2 -- ALWAYS occupies the three adjacent slots q0..q0+2 <= 7,
+  //    q0 = ring position of row X-1, and needs ONE N = nrows*NB segment of 12 MMAs); the epilogue adds the two;
+  //  * every slot is zero when a row starts using it (the epilogue re-zeroes after draining): all MMAs accumulate.
   if (warp == 0) {
-    // ------------------------------ producer ------------------------------
+    // ------------------------------ producer (one thread) ------------------------------
+    // Also owns the "accumulator slot is free" check: input row X is only staged once the slot(s) of the output
+    // row that STARTS accumulating with it (row X+1; and row 0 of the image) have been drained and re-zeroed
+    // (tempty[q] phase u = ring position q ready for its u-th use, phase 0 = initial zero fill).  The MMA warp
+    // then has a single barrier to wait for per input row (full[stage]), keeping its inter-row gap short.
     if (lane == 0) {
       mbar_arrive_expect_tx(wbar, (uint32_t)(L::WBYTES + NB * 4));
       {
-        // weight image + bias, in pieces of at most 32 KB
         uint32_t off = 0;
         const uint32_t total = L::WBYTES + NB * 4;
-        while (off < total) {
+        while (off < total) {                       // weight image + bias, in pieces of at most 32 KB
           const uint32_t n = (total - off) > 32768u ? 32768u : (total - off);
           bulk_g2s(sW + off, a.wimg + off, n, wbar);
           off += n;
         }
       }
-      uint32_t m = 0;
+      uint32_t stage = 0, empty_parity = 1;          // fresh barrier: waiting on parity 1 passes immediately
+      uint32_t qn = 0, ready_par = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int yt = item % nyt;
         const int strip = (item / nyt) % nstrips;
@@ -272,91 +286,90 @@ k_conv_mid(ConvMidArgs a) {
         const int y0 = yt * 128;
         const int npx = min(CM_NPX, a.ny + 2 - y0);
         const uint32_t bytes = (uint32_t)npx * 16u;
-        for (int X = xlo; X <= xhi; ++X, ++m) {
-          const uint32_t stage = m % CM_STAGES, use = m / CM_STAGES;
-          mbar_wait(&empty[stage], (use & 1) ^ 1);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.in) +
+                             ((((size_t)b * a.nx + xlo) * 8) * plane + (size_t)y0) * 16;
+        for (int X = xlo; X <= xhi; ++X) {
+          const int nnew = ((X + 1 <= x1 - 1) ? 1 : 0) + ((X == 0) ? 1 : 0);
+          for (int k = 0; k < nnew; ++k) {
+            mbar_wait(&tempty[qn], (ready_par >> qn) & 1u);
+            ready_par ^= 1u << qn;
+            qn = (qn + 1 == CM_RING) ? 0 : qn + 1;
+          }
+          mbar_wait(&empty[stage], empty_parity);
           mbar_arrive_expect_tx(&full[stage], 8 * bytes);
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.in) +
-                               ((((size_t)b * a.nx + X) * 8) * plane + (size_t)y0) * 16;
           uint8_t* dst = sStage + stage * CM_STAGE_BYTES;
 #pragma unroll
           for (int c = 0; c < 8; ++c) bulk_g2s(dst + c * CM_PLANE, src + (size_t)c * plane * 16, bytes, &full[stage]);
+          src += (size_t)8 * plane * 16;
+          if (++stage == CM_STAGES) { stage = 0; empty_parity ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer ------------------------------
-    // The whole warp runs the (uniform) control flow; one elected lane issues tcgen05.mma / commit.
-    // Per input row the accumulator segments are resolved ONCE, then the 12 MMAs are issued back to back
-    // with descriptors that differ only by compile-time constants.
-    const bool leader = elect_one();
-    mbar_wait(wbar, 0);
-    tc_fence_after();
-    constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
-    const uint32_t b_lo0 = (smem_u32(sW) >> 4) | ((uint32_t)(L::LBO_B >> 4) << 16);
-    const uint32_t a_lo_stage0 = (smem_u32(sStage) >> 4) | ((uint32_t)(CM_PLANE >> 4) << 16);
-    constexpr int A_K16_STEP = (2 * CM_PLANE) / 16, B_STEP = (2 * L::LBO_B) / 16;
-    static_assert(CM_RING + 2 == CM_SLOTS, "window q0..q0+2 must fit the slots");
-    static_assert(8 * L::LBO_B == L::WDY, "B offsets must be uniformly spaced over (dy, k16)");
-    // Incremental state (no division on the per-row path):
-    //   stage / full_parity : smem ring position of the next input row
-    //   qn                  : ring position (mod 6) of the next output row that will START accumulating
-    //   ready_par           : bit q = parity of the tempty[q] phase that row's slot(s) must have completed
-    uint32_t stage = 0, full_parity = 0;
-    uint32_t qn = 0, ready_par = 0;
-    const uint32_t da_hi = DESC_HI;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-      const int strip = (item / nyt) % nstrips;
-      const int x0 = strip * a.rs;
-      const int x1 = min(x0 + a.rs, a.nx);
-      const int xlo = max(x0 - 1, 0), xhi = min(x1, a.nx - 1);
-      // q_first = ring position of output row x0 (== qn: rows start accumulating in order)
-      uint32_t q_first = qn;
-      for (int X = xlo; X <= xhi; ++X) {
-        const int lo = max(X - 1, x0), hi = min(X + 1, x1 - 1);
-        // ---- accumulator window.  Output row with running index n has ring position q = n % 6.  The window of
-        // input row X is (X-1, X, X+1) at window positions 0..2 and ALWAYS occupies the three adjacent slots
-        // q0..q0+2 <= 7, q0 = ring position of row X-1: slots 6 and 7 mirror ring positions 0 and 1 (a row with
-        // q < 2 collects its first contributions in slot 6+q, its last in slot q; the epilogue adds the two).
-        // Hence ONE N = nrows*NB segment of 12 MMAs per input row.  Every slot is zero when a row starts using
-        // it (the epilogue re-zeroes after draining), so all MMAs accumulate.
-        const int dq = X - 1 - x0;                                       // -2 .. rs-1
-        uint32_t q0 = q_first + (uint32_t)(dq + CM_RING);                // ring position of (virtual) row X-1
-        q0 -= (q0 >= 2 * CM_RING) ? 2 * CM_RING : ((q0 >= CM_RING) ? CM_RING : 0);
-        while (q0 >= CM_RING) q0 -= CM_RING;                             // rs may exceed 6: at most a few iterations
-        const int pos_lo = lo - (X - 1);                                 // 0..2
-        const int nrows = hi - lo + 1;
-        // rows that start accumulating with this input row (X+1, and row 0 of the image) need their slots drained
-        // and re-zeroed: tempty[q] completes phase u when ring position q is ready for its u-th use
-        const int nnew = ((X + 1 <= hi) ? 1 : 0) + ((X == 0) ? 1 : 0);
-        for (int k = 0; k < nnew; ++k) {
-          mbar_wait(&tempty[qn], (ready_par >> qn) & 1u);
-          ready_par ^= 1u << qn;
-          qn = (qn + 1 == CM_RING) ? 0 : qn + 1;
-        }
-        mbar_wait(&full[stage], full_parity);
-        tc_fence_after();
-        if (leader) {
-          const uint64_t da = ((uint64_t)da_hi << 32) | (uint64_t)(a_lo_stage0 + stage * (CM_STAGE_BYTES >> 4));
-          const uint64_t db = ((uint64_t)da_hi << 32) | (uint64_t)(b_lo0 + (uint32_t)(pos_lo * NB));
+    // ------------------------------ MMA issuer (one thread) ------------------------------
+    if (lane == 0) {
+      mbar_wait(wbar, 0);
+      tc_fence_after();
+      constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
+      constexpr int A_K16_STEP = (2 * CM_PLANE) / 16, B_STEP = (2 * L::LBO_B) / 16;
+      static_assert(CM_RING + 2 == CM_SLOTS, "window q0..q0+2 must fit the slots");
+      static_assert(8 * L::LBO_B == L::WDY, "B offsets must be uniformly spaced over (dy, k16)");
+      const uint64_t db0 = ((uint64_t)DESC_HI << 32) | (uint64_t)((smem_u32(sW) >> 4) | ((uint32_t)(L::LBO_B >> 4) << 16));
+      const uint64_t da0 = ((uint64_t)DESC_HI << 32) | (uint64_t)((smem_u32(sStage) >> 4) | ((uint32_t)(CM_PLANE >> 4) << 16));
+      uint32_t stage = 0, full_parity = 0;
+      uint32_t qrow = 0;                                // ring position of output row x0 of the current item
+      long long t_full = 0, t_issue = 0, t_rows = 0;
+      const long long t_begin = clock64();
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int strip = (item / nyt) % nstrips;
+        const int x0 = strip * a.rs;
+        const int x1 = min(x0 + a.rs, a.nx);
+        const int xlo = max(x0 - 1, 0), xhi = min(x1, a.nx - 1);
+        // q0 = ring position of (virtual) row X-1 for the first input row of the item
+        uint32_t q0 = qrow + (uint32_t)(CM_RING + xlo - 1 - x0);
+        q0 = (q0 >= 2 * CM_RING) ? q0 - 2 * CM_RING : ((q0 >= CM_RING) ? q0 - CM_RING : q0);
+        for (int X = xlo; X <= xhi; ++X) {
+          const int lo = max(X - 1, x0), hi = min(X + 1, x1 - 1);
+          const int pos_lo = lo - (X - 1);                               // 0..2: window position of row lo
+          const int nrows = hi - lo + 1;
+          const long long tb = clock64();
+          mbar_wait(&full[stage], full_parity);
+          tc_fence_after();
+          const long long tc0 = clock64();
+          const uint64_t da = da0 + (uint64_t)(stage * (CM_STAGE_BYTES >> 4));
+          const uint64_t db = db0 + (uint64_t)(pos_lo * NB);
           umma_bf16_row12<A_K16_STEP, B_STEP>(tmem + (q0 + (uint32_t)pos_lo) * NB, da, db, umma_idesc_bf16(nrows * NB));
           umma_commit(&empty[stage]);                                  // smem stage free once the MMAs retire
           if (X - 1 >= x0) umma_commit(&tfull[q0]);                    // output row X-1 complete
           if (X == xhi && xhi == x1 - 1) umma_commit(&tfull[(q0 + 1 == CM_RING) ? 0 : q0 + 1]);   // image bottom: row X too
+          t_full += tc0 - tb;
+          t_issue += clock64() - tc0;
+          ++t_rows;
+          q0 = (q0 + 1 == CM_RING) ? 0 : q0 + 1;
+          if (++stage == CM_STAGES) { stage = 0; full_parity ^= 1; }
         }
-        __syncwarp();
-        if (++stage == CM_STAGES) { stage = 0; full_parity ^= 1; }
+        qrow += (uint32_t)(x1 - x0);
+        while (qrow >= CM_RING) qrow -= CM_RING;
+      }
+      if (a.dbg != nullptr) {
+        unsigned long long* d = a.dbg + (size_t)blockIdx.x * 8;
+        d[0] = (unsigned long long)(clock64() - t_begin);
+        d[1] = 0ull;
+        d[2] = (unsigned long long)t_full;
+        d[3] = (unsigned long long)t_issue;
+        d[4] = (unsigned long long)t_rows;
       }
     }
   } else {
-    // ------------------------------ epilogue (4 warps = 128 TMEM lanes) ------------------------------
+    // ------------------------------ epilogue (EPI_WARPS warps over the 128 TMEM lanes) ------------------------------
     const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
+    const int half = LAST ? 0 : ((warp - 2) >> 2);    // mid layers: which 32-column half of the 64-column slot
     // zero every accumulator slot once; afterwards each slot is re-zeroed right after it is drained
     {
       const uint32_t t0 = tmem + ((uint32_t)(quarter * 32) << 16);
       if constexpr (NB == 64) {
 #pragma unroll
-        for (int c = 0; c < 512; c += 32) tmem_st32_fill(t0 + c, 0u);
+        for (int c = 0; c < 512; c += 64) tmem_st32_fill(t0 + c + half * 32, 0u);
       } else {
 #pragma unroll
         for (int c = 0; c < NB * CM_SLOTS; c += 16) tmem_st16_fill(t0 + c, 0u);
@@ -367,6 +380,8 @@ k_conv_mid(ConvMidArgs a) {
     }
     mbar_wait(wbar, 0);                               // bias lives behind the weight image
     uint32_t slot = 0, done_par = 0;                  // ring position of the next row to drain; per-position phase parity
+    long long t_epi_wait = 0;
+    const long long t_epi_begin = clock64();
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const int yt = item % nyt;
       const int strip = (item / nyt) % nstrips;
@@ -375,46 +390,50 @@ k_conv_mid(ConvMidArgs a) {
       const int x1 = min(x0 + a.rs, a.nx);
       const int y = yt * 128 + quarter * 32 + lane;
       for (int x = x0; x < x1; ++x) {
+        // last layer: fetch the state this row's correction is added to BEFORE waiting for the accumulator, so the
+        // global-load latency hides behind the wait instead of serialising the epilogue
+        float u_old = 0.0f, v_old = 0.0f;
+        if constexpr (LAST) {
+          if (a.y_nchw == nullptr && y < a.ny) {
+            const size_t off0 = ((size_t)b * a.nx + x) * a.ny + y;
+            u_old = a.u[off0];
+            v_old = a.v[off0];
+          }
+        }
         // ring position `slot` (q); q < 2 also owns mirror slot 6+q
+        const long long te0 = clock64();
         mbar_wait(&tfull[slot], (done_par >> slot) & 1u);
+        t_epi_wait += clock64() - te0;
         done_par ^= 1u << slot;
         tc_fence_after();
         const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + slot * NB;
         const uint32_t maddr = taddr + CM_RING * NB;         // mirror slot (meaningful when slot < 2)
         if constexpr (!LAST) {
-          uint32_t r0[32], r1[32];
-          tmem_ld32(taddr, r0);
-          tmem_ld32(taddr + 32, r1);
+          uint32_t r[32];
+          const uint32_t hoff = (uint32_t)(half * 32);
+          tmem_ld32(taddr + hoff, r);
           tmem_ld_wait();
-          tmem_st32_fill(taddr, 0u);
-          tmem_st32_fill(taddr + 32, 0u);
+          tmem_st32_fill(taddr + hoff, 0u);
           if (slot < 2) {                                    // add the partial sums parked in the mirror slot
             uint32_t t[32];
-            tmem_ld32(maddr, t);
+            tmem_ld32(maddr + hoff, t);
             tmem_ld_wait();
 #pragma unroll
-            for (int k = 0; k < 32; ++k) r0[k] = __float_as_uint(__uint_as_float(r0[k]) + __uint_as_float(t[k]));
-            tmem_ld32(maddr + 32, t);
-            tmem_ld_wait();
-#pragma unroll
-            for (int k = 0; k < 32; ++k) r1[k] = __float_as_uint(__uint_as_float(r1[k]) + __uint_as_float(t[k]));
-            tmem_st32_fill(maddr, 0u);
-            tmem_st32_fill(maddr + 32, 0u);
+            for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) + __uint_as_float(t[k]));
+            tmem_st32_fill(maddr + hoff, 0u);
           }
           tmem_st_wait();
           tc_fence_before();
           if (lane == 0) mbar_arrive(&tempty[slot]);
           if (y < a.ny) {
             uint8_t* orow = reinterpret_cast<uint8_t*>(a.out) +
-                            ((((size_t)b * a.nx + x) * 8) * plane + (size_t)(y + 1)) * 16;
+                            ((((size_t)b * a.nx + x) * 8 + (size_t)(half * 4)) * plane + (size_t)(y + 1)) * 16;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < 4; ++c) {
               float f[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                const int ch = c * 8 + e;
-                const float acc = __uint_as_float(ch < 32 ? r0[ch & 31] : r1[ch & 31]);
-                f[e] = acc + sBias[ch];
+                f[e] = __uint_as_float(r[c * 8 + e]) + sBias[half * 32 + c * 8 + e];
                 if (a.relu) f[e] = fmaxf(f[e], 0.0f);
               }
               uint4 o;
@@ -449,13 +468,18 @@ k_conv_mid(ConvMidArgs a) {
                   a.y_nchw[((size_t)b * a.cout + co) * img + (size_t)x * a.ny + y] = __uint_as_float(r[co]) + sBias[co];
             } else {
               // fused correction add (reference src/inference.py:102): v += model(v)
-              a.u[off] += __uint_as_float(r[0]) + sBias[0];
-              a.v[off] += __uint_as_float(r[1]) + sBias[1];
+              a.u[off] = u_old + (__uint_as_float(r[0]) + sBias[0]);
+              a.v[off] = v_old + (__uint_as_float(r[1]) + sBias[1]);
             }
           }
         }
         slot = (slot + 1 == CM_RING) ? 0 : slot + 1;
       }
+    }
+    if (a.dbg != nullptr && warp == 2 && lane == 0) {
+      unsigned long long* d = a.dbg + (size_t)blockIdx.x * 8;
+      d[5] = (unsigned long long)(clock64() - t_epi_begin);
+      d[6] = (unsigned long long)t_epi_wait;
     }
   }
 
@@ -500,7 +524,7 @@ static int launch_conv_mid_t(const ConvMidArgs& a, int sm_count, cudaStream_t st
   const long nitems = (long)a.batch * nstrips * nyt;
   const long resident = (long)sm_count * (LAST ? 2 : 1);
   const int grid = (int)(nitems < resident ? nitems : resident);
-  k_conv_mid<NB, LAST><<<grid, CM_THREADS, L::TOTAL, st>>>(a);
+  k_conv_mid<NB, LAST><<<grid, LAST ? CM_THREADS_LAST : CM_THREADS_MID, L::TOTAL, st>>>(a);
   MLSIM_CUDA_CHECK(cudaGetLastError());
   return MLSIM_OK;
 }

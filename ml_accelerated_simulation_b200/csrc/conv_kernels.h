@@ -22,6 +22,7 @@ struct ConvMidArgs {
   int rs;                             // output rows per work item (strip length)
   int cout;                           // real output channels of this layer
   int relu;
+  unsigned long long* dbg;            // optional [grid][8] cycle counters (nullptr = off): see mlsim_conv_debug
 };
 
 int launch_conv_first(const ConvFirstArgs& a, int sm_count, cudaStream_t st);

@@ -1,5 +1,6 @@
 // Plan management and the C ABI of include/mlsim.h.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -49,9 +50,12 @@ struct mlsim_plan {
   int rs = 32;
   // host-rollout staging
   float* d_hu = nullptr; float* d_hv = nullptr; float* d_hp = nullptr;
-  cudaStream_t own_stream = nullptr;
+  cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
+  static constexpr int MAX_CHUNKS = 4;
+  cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_done[MAX_CHUNKS] = {};
   // timing scratch
   float* d_tu = nullptr; float* d_tv = nullptr;
+  unsigned long long* d_dbg = nullptr;   // per-CTA cycle counters of the conv kernels under mlsim_time_kernel
   // in-step kernel profiling (mlsim_profile_*): CUDA events around every launch of one kernel class
   int prof_class = -1;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -139,51 +143,64 @@ int check_field(const void* p, const char* name) {
   return MLSIM_OK;
 }
 
+// A contiguous block [b0, b0+nb) of the batch.  Field pointers handed to the helpers below are already
+// offset to the block; plan-owned workspaces are offset here.
+struct Chunk {
+  int b0, nb;
+  size_t foff(const mlsim_plan* pl) const { return (size_t)b0 * pl->cfg.nx * pl->cfg.ny; }
+  size_t soff(const mlsim_plan* pl) const { return (size_t)b0 * pl->cfg.nx * pl->sp.nycp; }
+  SolverParams sp(const mlsim_plan* pl) const { SolverParams q = pl->sp; q.batch = nb; return q; }
+};
+
 // P(u,v) in place on (u,v): K2 -> K3 -> K4
-int project(mlsim_plan* pl, float* u, float* v, float* p_or_null, cudaStream_t st) {
+int project(mlsim_plan* pl, float* u, float* v, float* p_or_null, cudaStream_t st, Chunk c) {
   int rc;
-  { ProfScope ps(pl, 1, st); if ((rc = launch_div_rfft(u, v, pl->d_spec, pl->d_twy, pl->sp, st))) return rc; }
-  { ProfScope ps(pl, 2, st); if ((rc = launch_col_solve(pl->d_spec, pl->d_inv_eig, pl->d_twx, pl->sp, st))) return rc; }
+  const SolverParams sp = c.sp(pl);
+  float2* spec = pl->d_spec + c.soff(pl);
+  { ProfScope ps(pl, 1, st); if ((rc = launch_div_rfft(u, v, spec, pl->d_twy, sp, st))) return rc; }
+  { ProfScope ps(pl, 2, st); if ((rc = launch_col_solve(spec, pl->d_inv_eig, pl->d_twx, sp, st))) return rc; }
   ProfScope ps(pl, 3, st);
-  return launch_irfft_grad(pl->d_spec, u, v, u, v, p_or_null, pl->d_twy, pl->sp, st);
+  return launch_irfft_grad(spec, u, v, u, v, p_or_null, pl->d_twy, sp, st);
 }
 
-int explicit_prof(mlsim_plan* pl, const StageArgs& a, cudaStream_t st) {
+int explicit_prof(mlsim_plan* pl, const StageArgs& a, cudaStream_t st, Chunk c) {
   ProfScope ps(pl, 0, st);
-  return launch_explicit(a, pl->sp, pl->d_forcing, st);
+  return launch_explicit(a, c.sp(pl), pl->d_forcing, st);
 }
 
 // One classic-RK4 step with a projection after every stage, in place on (u,v).
-int solver_step(mlsim_plan* pl, float* u, float* v, float* p_or_null, cudaStream_t st) {
+int solver_step(mlsim_plan* pl, float* u, float* v, float* p_or_null, cudaStream_t st, Chunk c) {
   const float dt = (float)pl->cfg.dt;
+  const size_t o = c.foff(pl);
+  float *w1u = pl->d_w1u + o, *w1v = pl->d_w1v + o, *w2u = pl->d_w2u + o, *w2v = pl->d_w2v + o;
   int rc;
   StageArgs a;
-  a.u0 = u; a.v0 = v; a.accu = pl->d_accu; a.accv = pl->d_accv;
+  a.u0 = u; a.v0 = v; a.accu = pl->d_accu + o; a.accv = pl->d_accv + o;
   // stage 1: k1 = F(u0); acc = u0 + dt/6 k1; u* = u0 + dt/2 k1
-  a.us = u; a.vs = v; a.outu = pl->d_w1u; a.outv = pl->d_w1v;
+  a.us = u; a.vs = v; a.outu = w1u; a.outv = w1v;
   a.ca = dt / 6.0f; a.cs = 0.5f * dt; a.mode = 1;
-  if ((rc = explicit_prof(pl, a, st))) return rc;
-  if ((rc = project(pl, pl->d_w1u, pl->d_w1v, nullptr, st))) return rc;
+  if ((rc = explicit_prof(pl, a, st, c))) return rc;
+  if ((rc = project(pl, w1u, w1v, nullptr, st, c))) return rc;
   // stage 2: k2 = F(u1); acc += dt/3 k2; u* = u0 + dt/2 k2
-  a.us = pl->d_w1u; a.vs = pl->d_w1v; a.outu = pl->d_w2u; a.outv = pl->d_w2v;
+  a.us = w1u; a.vs = w1v; a.outu = w2u; a.outv = w2v;
   a.ca = dt / 3.0f; a.cs = 0.5f * dt; a.mode = 2;
-  if ((rc = explicit_prof(pl, a, st))) return rc;
-  if ((rc = project(pl, pl->d_w2u, pl->d_w2v, nullptr, st))) return rc;
+  if ((rc = explicit_prof(pl, a, st, c))) return rc;
+  if ((rc = project(pl, w2u, w2v, nullptr, st, c))) return rc;
   // stage 3: k3 = F(u2); acc += dt/3 k3; u* = u0 + dt k3
-  a.us = pl->d_w2u; a.vs = pl->d_w2v; a.outu = pl->d_w1u; a.outv = pl->d_w1v;
+  a.us = w2u; a.vs = w2v; a.outu = w1u; a.outv = w1v;
   a.ca = dt / 3.0f; a.cs = dt; a.mode = 2;
-  if ((rc = explicit_prof(pl, a, st))) return rc;
-  if ((rc = project(pl, pl->d_w1u, pl->d_w1v, nullptr, st))) return rc;
+  if ((rc = explicit_prof(pl, a, st, c))) return rc;
+  if ((rc = project(pl, w1u, w1v, nullptr, st, c))) return rc;
   // stage 4: k4 = F(u3); u* = acc + dt/6 k4  -> written over the caller's state, then projected
-  a.us = pl->d_w1u; a.vs = pl->d_w1v; a.outu = u; a.outv = v;
+  a.us = w1u; a.vs = w1v; a.outu = u; a.outv = v;
   a.ca = 0.0f; a.cs = dt / 6.0f; a.mode = 3;
-  if ((rc = explicit_prof(pl, a, st))) return rc;
-  return project(pl, u, v, p_or_null, st);
+  if ((rc = explicit_prof(pl, a, st, c))) return rc;
+  return project(pl, u, v, p_or_null, st, c);
 }
 
 // y = model(stack((u,v),1)*scale); either y_nchw (test hook) or fused u += y0, v += y1.
 int cnn_apply(mlsim_plan* pl, const float* u_in, const float* v_in, float* u, float* v, float* y_nchw, double scale,
-              cudaStream_t st) {
+              cudaStream_t st, Chunk ck) {
   if (!pl->cnn_ready) {
     set_error("correction network not finalised (mlsim_cnn_begin / set_layer / finalize)");
     return MLSIM_ESTATE;
@@ -191,18 +208,20 @@ int cnn_apply(mlsim_plan* pl, const float* u_in, const float* v_in, float* u, fl
   const mlsim_config& c = pl->cfg;
   const int L = (int)pl->layers.size();
   int rc;
+  const size_t aoff = (size_t)ck.b0 * c.nx * 8 * (size_t)(c.ny + 2) * 8;      // bf16 elements per image block
+  __nv_bfloat16* act[2] = {pl->d_act[0] + aoff, pl->d_act[1] + aoff};
   ConvFirstArgs f;
-  f.u = u_in; f.v = v_in; f.out = pl->d_act[0]; f.wimg = pl->layers[0].d_wimg; f.scale = (float)scale;
-  f.nx = c.nx; f.ny = c.ny; f.batch = c.batch;
+  f.u = u_in; f.v = v_in; f.out = act[0]; f.wimg = pl->layers[0].d_wimg; f.scale = (float)scale;
+  f.nx = c.nx; f.ny = c.ny; f.batch = ck.nb;
   { ProfScope ps(pl, 4, st); if ((rc = launch_conv_first(f, pl->sm_count, st))) return rc; }
   int cur = 0;
   for (int l = 1; l < L; ++l) {
     ConvMidArgs m;
-    m.in = pl->d_act[cur]; m.out = pl->d_act[cur ^ 1];
+    m.in = act[cur]; m.out = act[cur ^ 1];
     m.u = u; m.v = v; m.y_nchw = y_nchw;
     m.wimg = pl->layers[l].d_wimg;
-    m.nx = c.nx; m.ny = c.ny; m.batch = c.batch; m.rs = pl->rs;
-    m.cout = pl->layers[l].cout; m.relu = pl->layers[l].relu;
+    m.nx = c.nx; m.ny = c.ny; m.batch = ck.nb; m.rs = pl->rs;
+    m.cout = pl->layers[l].cout; m.relu = pl->layers[l].relu; m.dbg = nullptr;
     if (l < L - 1) {
       ProfScope ps(pl, 5, st);
       if ((rc = launch_conv_mid(m, pl->sm_count, st))) return rc;
@@ -211,6 +230,18 @@ int cnn_apply(mlsim_plan* pl, const float* u_in, const float* v_in, float* u, fl
       if ((rc = launch_conv_last(m, pl->sm_count, st))) return rc;
     }
     cur ^= 1;
+  }
+  return MLSIM_OK;
+}
+
+// nsteps of {solver step; optional correction} on one block of the batch (pointers already offset to it)
+int run_steps(mlsim_plan* pl, float* u, float* v, float* p_or_null, int nsteps, int apply_cnn, double scale,
+              cudaStream_t st, Chunk c) {
+  int rc;
+  for (int s = 0; s < nsteps; ++s) {
+    float* pp = (s == nsteps - 1) ? p_or_null : nullptr;
+    if ((rc = solver_step(pl, u, v, pp, st, c))) return rc;
+    if (apply_cnn && (rc = cnn_apply(pl, u, v, u, v, nullptr, scale, st, c))) return rc;
   }
   return MLSIM_OK;
 }
@@ -289,10 +320,13 @@ int mlsim_plan_destroy(mlsim_plan* pl) {
   cudaDeviceSynchronize();
   void* ptrs[] = {pl->d_forcing, pl->d_inv_eig, pl->d_twx, pl->d_twy, pl->d_w1u, pl->d_w1v, pl->d_w2u, pl->d_w2v,
                   pl->d_accu, pl->d_accv, pl->d_spec, pl->d_act[0], pl->d_act[1], pl->d_hu, pl->d_hv, pl->d_hp,
-                  pl->d_tu, pl->d_tv};
+                  pl->d_tu, pl->d_tv, pl->d_dbg};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& l : pl->layers) if (l.d_wimg) cudaFree(l.d_wimg);
   if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
+  if (pl->in_stream) cudaStreamDestroy(pl->in_stream);
+  if (pl->out_stream) cudaStreamDestroy(pl->out_stream);
+  for (int i = 0; i < mlsim_plan::MAX_CHUNKS; ++i) { if (pl->ev_in[i]) cudaEventDestroy(pl->ev_in[i]); if (pl->ev_done[i]) cudaEventDestroy(pl->ev_done[i]); }
   for (auto& e : pl->prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   delete pl;
   return MLSIM_OK;
@@ -424,31 +458,50 @@ int mlsim_step(mlsim_plan* pl, float* u, float* v, float* p_or_null, int32_t nst
   MLSIM_REQUIRE(nsteps >= 0, "nsteps must be >= 0");
   if (apply_cnn && !pl->cnn_ready) { set_error("apply_cnn set but the correction network is not finalised"); return MLSIM_ESTATE; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  for (int s = 0; s < nsteps; ++s) {
-    float* pp = (s == nsteps - 1) ? p_or_null : nullptr;
-    if ((rc = solver_step(pl, u, v, pp, st))) return rc;
-    if (apply_cnn && (rc = cnn_apply(pl, u, v, u, v, nullptr, cnn_input_scale, st))) return rc;
-  }
-  return MLSIM_OK;
+  return run_steps(pl, u, v, p_or_null, nsteps, apply_cnn, cnn_input_scale, st, Chunk{0, pl->cfg.batch});
 }
 
 int mlsim_rollout_host(mlsim_plan* pl, float* hu, float* hv, float* hp, int32_t nsteps, int32_t apply_cnn,
                        double cnn_input_scale) {
   if (!pl || !hu || !hv) { set_error("null argument"); return MLSIM_EINVAL; }
+  MLSIM_REQUIRE(nsteps >= 0, "nsteps must be >= 0");
+  if (apply_cnn && !pl->cnn_ready) { set_error("apply_cnn set but the correction network is not finalised"); return MLSIM_ESTATE; }
   MLSIM_CUDA_CHECK(cudaSetDevice(pl->cfg.device));
   const size_t n = pl->field_elems;
   int rc;
   if (!pl->d_hu) {
     if ((rc = dev_alloc(pl, &pl->d_hu, n)) || (rc = dev_alloc(pl, &pl->d_hv, n)) || (rc = dev_alloc(pl, &pl->d_hp, n))) return rc;
+    MLSIM_CUDA_CHECK(cudaStreamCreateWithFlags(&pl->in_stream, cudaStreamNonBlocking));
+    MLSIM_CUDA_CHECK(cudaStreamCreateWithFlags(&pl->out_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < mlsim_plan::MAX_CHUNKS; ++i) {
+      MLSIM_CUDA_CHECK(cudaEventCreateWithFlags(&pl->ev_in[i], cudaEventDisableTiming));
+      MLSIM_CUDA_CHECK(cudaEventCreateWithFlags(&pl->ev_done[i], cudaEventDisableTiming));
+    }
   }
-  cudaStream_t st = pl->own_stream;
-  MLSIM_CUDA_CHECK(cudaMemcpyAsync(pl->d_hu, hu, n * sizeof(float), cudaMemcpyHostToDevice, st));
-  MLSIM_CUDA_CHECK(cudaMemcpyAsync(pl->d_hv, hv, n * sizeof(float), cudaMemcpyHostToDevice, st));
-  if ((rc = mlsim_step(pl, pl->d_hu, pl->d_hv, hp ? pl->d_hp : nullptr, nsteps, apply_cnn, cnn_input_scale, st))) return rc;
-  MLSIM_CUDA_CHECK(cudaMemcpyAsync(hu, pl->d_hu, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-  MLSIM_CUDA_CHECK(cudaMemcpyAsync(hv, pl->d_hv, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (hp) MLSIM_CUDA_CHECK(cudaMemcpyAsync(hp, pl->d_hp, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-  MLSIM_CUDA_CHECK(cudaStreamSynchronize(st));
+  // Three-stage pipeline over blocks of independent trajectories: H2D (copy engine) | steps (SMs) | D2H (copy
+  // engine).  Trajectories do not interact, so block k+1 uploads while block k computes and block k-1 downloads.
+  const int B = pl->cfg.batch;
+  int nchunks = B >= 16 ? 4 : (B >= 2 ? 2 : 1);
+  if (const char* e = getenv("MLSIM_HOST_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= mlsim_plan::MAX_CHUNKS && v <= B) nchunks = v; }
+  const size_t img = (size_t)pl->cfg.nx * pl->cfg.ny;
+  cudaStream_t sc = pl->own_stream;
+  for (int k = 0; k < nchunks; ++k) {
+    const int b0 = (int)((long)B * k / nchunks), b1 = (int)((long)B * (k + 1) / nchunks);
+    const size_t off = (size_t)b0 * img, cnt = (size_t)(b1 - b0) * img;
+    MLSIM_CUDA_CHECK(cudaMemcpyAsync(pl->d_hu + off, hu + off, cnt * sizeof(float), cudaMemcpyHostToDevice, pl->in_stream));
+    MLSIM_CUDA_CHECK(cudaMemcpyAsync(pl->d_hv + off, hv + off, cnt * sizeof(float), cudaMemcpyHostToDevice, pl->in_stream));
+    MLSIM_CUDA_CHECK(cudaEventRecord(pl->ev_in[k], pl->in_stream));
+    MLSIM_CUDA_CHECK(cudaStreamWaitEvent(sc, pl->ev_in[k], 0));
+    if ((rc = run_steps(pl, pl->d_hu + off, pl->d_hv + off, hp ? pl->d_hp + off : nullptr, nsteps, apply_cnn,
+                        cnn_input_scale, sc, Chunk{b0, b1 - b0}))) return rc;
+    MLSIM_CUDA_CHECK(cudaEventRecord(pl->ev_done[k], sc));
+    MLSIM_CUDA_CHECK(cudaStreamWaitEvent(pl->out_stream, pl->ev_done[k], 0));
+    MLSIM_CUDA_CHECK(cudaMemcpyAsync(hu + off, pl->d_hu + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, pl->out_stream));
+    MLSIM_CUDA_CHECK(cudaMemcpyAsync(hv + off, pl->d_hv + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, pl->out_stream));
+    if (hp) MLSIM_CUDA_CHECK(cudaMemcpyAsync(hp + off, pl->d_hp + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, pl->out_stream));
+  }
+  MLSIM_CUDA_CHECK(cudaStreamSynchronize(pl->out_stream));
+  MLSIM_CUDA_CHECK(cudaStreamSynchronize(sc));
   return MLSIM_OK;
 }
 
@@ -466,7 +519,7 @@ int mlsim_project(mlsim_plan* pl, float* u, float* v, float* p_or_null, void* st
   if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
   int rc;
   if ((rc = check_field(u, "u")) || (rc = check_field(v, "v"))) return rc;
-  return project(pl, u, v, p_or_null, reinterpret_cast<cudaStream_t>(stream));
+  return project(pl, u, v, p_or_null, reinterpret_cast<cudaStream_t>(stream), Chunk{0, pl->cfg.batch});
 }
 
 int mlsim_divergence(mlsim_plan* pl, const float* u, const float* v, float* d, void* stream) {
@@ -480,7 +533,7 @@ int mlsim_cnn_forward(mlsim_plan* pl, const float* u, const float* v, float* y, 
   if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
   int rc;
   if ((rc = check_field(u, "u")) || (rc = check_field(v, "v")) || (rc = check_field(y, "y"))) return rc;
-  return cnn_apply(pl, u, v, nullptr, nullptr, y, scale, reinterpret_cast<cudaStream_t>(stream));
+  return cnn_apply(pl, u, v, nullptr, nullptr, y, scale, reinterpret_cast<cudaStream_t>(stream), Chunk{0, pl->cfg.batch});
 }
 
 int mlsim_cnn_correct(mlsim_plan* pl, float* u, float* v, double scale, void* stream) {
@@ -489,7 +542,7 @@ int mlsim_cnn_correct(mlsim_plan* pl, float* u, float* v, double scale, void* st
   if ((rc = check_field(u, "u")) || (rc = check_field(v, "v"))) return rc;
   if (!pl->cnn_ready) { set_error("correction network not finalised"); return MLSIM_ESTATE; }
   MLSIM_REQUIRE(pl->layers.back().cout == 2, "the fused correction add needs a 2-channel output (u, v)");
-  return cnn_apply(pl, u, v, u, v, nullptr, scale, reinterpret_cast<cudaStream_t>(stream));
+  return cnn_apply(pl, u, v, u, v, nullptr, scale, reinterpret_cast<cudaStream_t>(stream), Chunk{0, pl->cfg.batch});
 }
 
 int mlsim_launches_per_step(mlsim_plan* pl, int32_t apply_cnn) {
@@ -500,6 +553,21 @@ int mlsim_launches_per_step(mlsim_plan* pl, int32_t apply_cnn) {
 }
 
 int64_t mlsim_workspace_bytes(mlsim_plan* pl) { return pl ? pl->ws_bytes : 0; }
+
+int mlsim_conv_debug(mlsim_plan* pl, double* out8) {
+  if (!pl || !out8 || !pl->d_dbg) { set_error("no conv debug counters (run mlsim_time_kernel(5|6) first)"); return MLSIM_EINVAL; }
+  std::vector<unsigned long long> h((size_t)1024 * 8);
+  MLSIM_CUDA_CHECK(cudaMemcpy(h.data(), pl->d_dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  int n = 0;
+  for (int k = 0; k < 8; ++k) out8[k] = 0.0;
+  for (int b = 0; b < 1024; ++b) {
+    if (h[(size_t)b * 8] == 0) continue;
+    ++n;
+    for (int k = 0; k < 8; ++k) out8[k] += (double)h[(size_t)b * 8 + k];
+  }
+  for (int k = 0; k < 8; ++k) out8[k] /= (n ? n : 1);
+  return n;
+}
 
 int mlsim_profile_enable(mlsim_plan* pl, int32_t kernel_class, int32_t max_samples) {
   if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
@@ -539,7 +607,8 @@ int mlsim_time_kernel(mlsim_plan* pl, int32_t which, int32_t warmup, int32_t ite
   const size_t n = pl->field_elems;
   int rc;
   if (!pl->d_tu) {
-    if ((rc = dev_alloc(pl, &pl->d_tu, n)) || (rc = dev_alloc(pl, &pl->d_tv, n))) return rc;
+    if ((rc = dev_alloc(pl, &pl->d_tu, n)) || (rc = dev_alloc(pl, &pl->d_tv, n)) || (rc = dev_alloc(pl, &pl->d_dbg, (size_t)1024 * 8))) return rc;
+    MLSIM_CUDA_CHECK(cudaMemsetAsync(pl->d_dbg, 0, 1024 * 8 * sizeof(unsigned long long), st));
     MLSIM_CUDA_CHECK(cudaMemsetAsync(pl->d_tu, 0, n * sizeof(float), st));
     MLSIM_CUDA_CHECK(cudaMemsetAsync(pl->d_tv, 0, n * sizeof(float), st));
   }
@@ -569,7 +638,7 @@ int mlsim_time_kernel(mlsim_plan* pl, int32_t which, int32_t warmup, int32_t ite
         ConvMidArgs m;
         m.in = pl->d_act[0]; m.out = pl->d_act[1]; m.u = pl->d_w1u; m.v = pl->d_w1v; m.y_nchw = nullptr;
         m.wimg = pl->layers[l].d_wimg; m.nx = c.nx; m.ny = c.ny; m.batch = c.batch; m.rs = pl->rs;
-        m.cout = pl->layers[l].cout; m.relu = pl->layers[l].relu;
+        m.cout = pl->layers[l].cout; m.relu = pl->layers[l].relu; m.dbg = pl->d_dbg;
         return (which == 5) ? launch_conv_mid(m, pl->sm_count, st) : launch_conv_last(m, pl->sm_count, st);
       }
     }

@@ -180,6 +180,11 @@ class Plan:
         _lib.check(self._lib.mlsim_profile_read(self._h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
 
+    def conv_debug(self):
+        out = (C.c_double * 8)()
+        n = self._lib.mlsim_conv_debug(self._h, out)
+        return n, list(out)
+
     def time_kernel(self, which: int, warmup: int = 3, iters: int = 10) -> float:
         ms = C.c_float(0.0)
         _lib.check(self._lib.mlsim_time_kernel(self._h, which, warmup, iters, C.byref(ms), self._stream()))

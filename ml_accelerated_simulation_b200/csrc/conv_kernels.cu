@@ -73,7 +73,8 @@ k_conv_first(ConvFirstArgs a) {
   const size_t plane = (size_t)(a.ny + 2);
 
   // ---- im2col row of this thread's pixel: k = (i*3 + j)*2 + ch, i <-> dx+1, j <-> dy+1 ----
-  auto load_vals = [&](int tile, float (&val)[18]) {
+  auto load_vals = [&](int tile_, float (&val)[18]) {
+    const int tile = a.reverse ? (ntiles - 1 - tile_) : tile_;
     const int yt = tile % nyt;
     const int x = (tile / nyt) % a.nx;
     const int b = tile / (nyt * a.nx);
@@ -150,9 +151,10 @@ k_conv_first(ConvFirstArgs a) {
     __syncthreads();                                    // A[buf^1] complete; accumulator `buf` fully read
     if (has_next) issue(buf ^ 1);
 
-    const int yt = tile % nyt;
-    const int x = (tile / nyt) % a.nx;
-    const int b = tile / (nyt * a.nx);
+    const int tile_r = a.reverse ? (ntiles - 1 - tile) : tile;
+    const int yt = tile_r % nyt;
+    const int x = (tile_r / nyt) % a.nx;
+    const int b = tile_r / (nyt * a.nx);
     const int y = yt * 128 + tid;
     if (y < a.ny) {
       uint8_t* orow = reinterpret_cast<uint8_t*>(a.out) +
@@ -276,7 +278,8 @@ k_conv_mid(ConvMidArgs a) {
       }
       uint32_t stage = 0, empty_parity = 1;          // fresh barrier: waiting on parity 1 passes immediately
       uint32_t qn = 0, ready_par = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      for (int it_ = blockIdx.x; it_ < nitems; it_ += gridDim.x) {
+        const int item = a.reverse ? (nitems - 1 - it_) : it_;
         const int yt = item % nyt;
         const int strip = (item / nyt) % nstrips;
         const int b = item / (nyt * nstrips);
@@ -320,7 +323,8 @@ k_conv_mid(ConvMidArgs a) {
       uint32_t qrow = 0;                                // ring position of output row x0 of the current item
       long long t_full = 0, t_issue = 0, t_rows = 0;
       const long long t_begin = clock64();
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      for (int it_ = blockIdx.x; it_ < nitems; it_ += gridDim.x) {
+        const int item = a.reverse ? (nitems - 1 - it_) : it_;
         const int strip = (item / nyt) % nstrips;
         const int x0 = strip * a.rs;
         const int x1 = min(x0 + a.rs, a.nx);
@@ -382,7 +386,8 @@ k_conv_mid(ConvMidArgs a) {
     uint32_t slot = 0, done_par = 0;                  // ring position of the next row to drain; per-position phase parity
     long long t_epi_wait = 0;
     const long long t_epi_begin = clock64();
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    for (int it_ = blockIdx.x; it_ < nitems; it_ += gridDim.x) {
+        const int item = a.reverse ? (nitems - 1 - it_) : it_;
       const int yt = item % nyt;
       const int strip = (item / nyt) % nstrips;
       const int b = item / (nyt * nstrips);

@@ -10,6 +10,7 @@ struct ConvFirstArgs {
   const uint8_t* wimg;                // packed weights (conv_first_wimg_bytes)
   float scale;                        // cnn_input_scale
   int nx, ny, batch;
+  int reverse;                        // traverse tiles last-to-first (see ConvMidArgs::reverse)
 };
 
 struct ConvMidArgs {
@@ -22,6 +23,8 @@ struct ConvMidArgs {
   int rs;                             // output rows per work item (strip length)
   int cout;                           // real output channels of this layer
   int relu;
+  int reverse;                        // traverse work items last-to-first: consecutive layers alternate direction so
+                                      // each layer starts on the activations its predecessor wrote last (still in L2)
   unsigned long long* dbg;            // optional [grid][8] cycle counters (nullptr = off): see mlsim_conv_debug
 };
 

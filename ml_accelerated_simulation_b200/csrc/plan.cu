@@ -212,7 +212,7 @@ int cnn_apply(mlsim_plan* pl, const float* u_in, const float* v_in, float* u, fl
   __nv_bfloat16* act[2] = {pl->d_act[0] + aoff, pl->d_act[1] + aoff};
   ConvFirstArgs f;
   f.u = u_in; f.v = v_in; f.out = act[0]; f.wimg = pl->layers[0].d_wimg; f.scale = (float)scale;
-  f.nx = c.nx; f.ny = c.ny; f.batch = ck.nb;
+  f.nx = c.nx; f.ny = c.ny; f.batch = ck.nb; f.reverse = 0;
   { ProfScope ps(pl, 4, st); if ((rc = launch_conv_first(f, pl->sm_count, st))) return rc; }
   int cur = 0;
   for (int l = 1; l < L; ++l) {
@@ -222,6 +222,7 @@ int cnn_apply(mlsim_plan* pl, const float* u_in, const float* v_in, float* u, fl
     m.wimg = pl->layers[l].d_wimg;
     m.nx = c.nx; m.ny = c.ny; m.batch = ck.nb; m.rs = pl->rs;
     m.cout = pl->layers[l].cout; m.relu = pl->layers[l].relu; m.dbg = nullptr;
+    m.reverse = l & 1;                  // layer 0 ascending, layer 1 descending, ...
     if (l < L - 1) {
       ProfScope ps(pl, 5, st);
       if ((rc = launch_conv_mid(m, pl->sm_count, st))) return rc;
@@ -628,7 +629,7 @@ int mlsim_time_kernel(mlsim_plan* pl, int32_t which, int32_t warmup, int32_t ite
       case 4: {
         ConvFirstArgs f;
         f.u = pl->d_tu; f.v = pl->d_tv; f.out = pl->d_act[0]; f.wimg = pl->layers[0].d_wimg; f.scale = 1.0f;
-        f.nx = c.nx; f.ny = c.ny; f.batch = c.batch;
+        f.nx = c.nx; f.ny = c.ny; f.batch = c.batch; f.reverse = 0;
         return launch_conv_first(f, pl->sm_count, st);
       }
       default: {
@@ -638,7 +639,7 @@ int mlsim_time_kernel(mlsim_plan* pl, int32_t which, int32_t warmup, int32_t ite
         ConvMidArgs m;
         m.in = pl->d_act[0]; m.out = pl->d_act[1]; m.u = pl->d_w1u; m.v = pl->d_w1v; m.y_nchw = nullptr;
         m.wimg = pl->layers[l].d_wimg; m.nx = c.nx; m.ny = c.ny; m.batch = c.batch; m.rs = pl->rs;
-        m.cout = pl->layers[l].cout; m.relu = pl->layers[l].relu; m.dbg = pl->d_dbg;
+        m.cout = pl->layers[l].cout; m.relu = pl->layers[l].relu; m.dbg = pl->d_dbg; m.reverse = 0;
         return (which == 5) ? launch_conv_mid(m, pl->sm_count, st) : launch_conv_last(m, pl->sm_count, st);
       }
     }

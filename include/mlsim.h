@@ -101,7 +101,7 @@ int  mlsim_launches_per_step(mlsim_plan* plan, int32_t apply_cnn);
 int64_t mlsim_workspace_bytes(mlsim_plan* plan);
 /* time one kernel class in isolation with CUDA events on `stream`: which = 0 explicit terms (stage 2
  * form), 1 div+row FFT, 2 column solve, 3 row iFFT+gradient, 4 first conv, 5 one mid conv layer,
- * 6 last conv + correction add.  Runs `iters` launches after `warmup`, returns mean ms in *ms_out. */
+ * 6 last conv + correction add, 7 single-kernel cluster projection (small square grids).  Runs `iters` launches after `warmup`, returns mean ms in *ms_out. */
 int  mlsim_time_kernel(mlsim_plan* plan, int32_t which, int32_t warmup, int32_t iters, float* ms_out, void* stream);
 
 /* Developer aid: mean per-CTA cycle counters of the last conv kernel run by mlsim_time_kernel(5|6):

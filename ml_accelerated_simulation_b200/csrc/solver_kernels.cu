@@ -9,6 +9,8 @@
 #include "fft.cuh"
 #include "solver_kernels.h"
 
+#include <cooperative_groups.h>
+
 namespace mlsim {
 
 // ---------------------------------------------------------------------------------------------
@@ -429,6 +431,238 @@ k_col_solve(float2* __restrict__ S, const float* __restrict__ inv_eig, const flo
         for (int q = 0; q < R; ++q) base[(size_t)(j + q * NS) * p.nycp] = v[q];
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Whole projection in ONE kernel for small square grids: a thread-block cluster of CL CTAs owns one image and
+// keeps its half spectrum in (distributed) shared memory, so the field crosses L2/HBM once (R 2w + W 2w per cell
+// instead of 10w) and the three launches K2/K3/K4 become one.  CTA `rank` owns rows [rank*N/CL, (rank+1)*N/CL):
+//   phase 1  div + row FFT (as K2)            -> S_local[row][ky]                      | cluster.sync
+//   phase 2  column FFT * inv_eig * iFFT (K3) on its share of the ky columns, gathering / scattering the other
+//            CTAs' rows through DSMEM (cluster.map_shared_rank)                        | cluster.sync
+//   phase 3  row iFFT (as K4) -> p rows written over the same S_local row slots        | cluster.sync
+//   phase 4  u -= d+x p, v -= d+y p (the x-halo row of p comes from the next CTA over DSMEM)
+// ---------------------------------------------------------------------------------------------
+template <int N> struct ProjCfg {
+  static constexpr int Q = 16;                                        // complex lines (= 32 rows) per row pass
+  static constexpr int THREADS = Q * N / FftMinRadix<N>::value;       // 128 (N=64) / 256 (N=128, 256)
+  static constexpr int LS = Q + 1;
+  static constexpr int NYC = N / 2 + 1;
+  static constexpr size_t smem(int cl) { return ((size_t)(N / cl) * NYC + (size_t)N * LS) * sizeof(float2); }
+};
+
+template <int N, int CL>
+__global__ void __launch_bounds__(ProjCfg<N>::THREADS)
+k_project_cluster(float* __restrict__ u, float* __restrict__ v, float* __restrict__ pout,
+                  const float* __restrict__ inv_eig, const float2* __restrict__ tw, SolverParams p) {
+  namespace cg = cooperative_groups;
+  using P = FftPlan<N>;
+  using C = ProjCfg<N>;
+  constexpr int Q = C::Q, LS = C::LS, NT = C::THREADS, NYC = C::NYC, RPC = N / CL;
+  static_assert(RPC % (2 * Q) == 0, "rows per CTA must be a multiple of 32");
+  extern __shared__ float4 smem4[];
+  float2* S = reinterpret_cast<float2*>(smem4);            // [RPC][NYC] half spectrum of the CTA's rows, later p rows
+  float2* buf = S + (size_t)RPC * NYC;                     // [N][LS] FFT work buffer (line-fastest)
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (CL == 1) ? 0 : (int)cluster.block_rank();
+  const int b = blockIdx.x / CL;
+  const int row0 = rank * RPC;
+  const size_t img = (size_t)b * N * N;
+  float* __restrict__ gu = u + img;
+  float* __restrict__ gv = v + img;
+  float2* Sr[CL];
+#pragma unroll
+  for (int r = 0; r < CL; ++r) Sr[r] = (CL == 1) ? S : cluster.map_shared_rank(S, r);
+
+  const int c = threadIdx.x % Q, j = threadIdx.x / Q;
+
+  // ---------------- phase 1: divergence + forward row FFT ----------------
+  for (int pass = 0; pass < RPC / (2 * Q); ++pass) {
+    const int i0 = row0 + pass * 2 * Q;
+    for (int idx = threadIdx.x; idx < 2 * Q * N; idx += NT) {
+      const int r = idx / N, y = idx - r * N;
+      const int i = i0 + r;
+      const int im = (i - 1) & (N - 1), ym = (y - 1) & (N - 1);
+      const float d = (gu[(size_t)i * N + y] - gu[(size_t)im * N + y]) * p.inv_hx +
+                      (gv[(size_t)i * N + y] - gv[(size_t)i * N + ym]) * p.inv_hy;
+      reinterpret_cast<float*>(&buf[y * LS + (r >> 1)])[r & 1] = d;
+    }
+    __syncthreads();
+    stage_smem<N, P::R1, 1, -1>(buf, LS, c, j, true, tw);
+    stage_smem<N, P::R2, P::R1, -1>(buf, LS, c, j, true, tw);
+    if constexpr (P::R3 > 1) stage_smem<N, P::R3, P::R1 * P::R2, -1>(buf, LS, c, j, true, tw);
+    for (int idx = threadIdx.x; idx < Q * NYC; idx += NT) {
+      const int q = idx / NYC, k = idx - q * NYC;
+      const float2 z = buf[k * LS + q];
+      const float2 zm = buf[((N - k) & (N - 1)) * LS + q];
+      float2* row = S + (size_t)(pass * 2 * Q + 2 * q) * NYC;
+      row[k] = make_float2(0.5f * (z.x + zm.x), 0.5f * (z.y - zm.y));
+      row[NYC + k] = make_float2(0.5f * (z.y + zm.y), -0.5f * (z.x - zm.x));
+    }
+    __syncthreads();
+  }
+  if (CL > 1) cluster.sync();
+
+  // ---------------- phase 2: column transforms on this CTA's share of ky ----------------
+  {
+    constexpr int RL = (P::R3 > 1) ? P::R3 : P::R2;
+    constexpr int NSL = N / RL;
+    constexpr int CPC = (NYC + CL - 1) / CL;
+    const int c_lo = rank * CPC, c_hi = min(NYC, c_lo + CPC);
+    for (int g0 = c_lo; g0 < c_hi; g0 += Q) {
+      const int ky = g0 + c;
+      const bool valid = ky < c_hi;
+      {
+        constexpr int R = P::R1;
+        if (j < N / R) {
+          float2 w[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int row = j + r * (N / R);
+            w[r] = valid ? Sr[row / RPC][(size_t)(row % RPC) * NYC + ky] : make_float2(0.f, 0.f);
+          }
+          dft_regs<R, -1>(w);
+#pragma unroll
+          for (int q = 0; q < R; ++q) buf[(j * R + q) * LS + c] = w[q];
+        }
+        __syncthreads();
+      }
+      if constexpr (P::R3 > 1) stage_smem<N, P::R2, P::R1, -1>(buf, LS, c, j, true, tw);
+      {
+        float2 w[RL];
+        const bool on = j < N / RL;
+        if (on) {
+#pragma unroll
+          for (int r = 0; r < RL; ++r) w[r] = buf[(j + r * NSL) * LS + c];
+        }
+        __syncthreads();
+        if (on) {
+          stage_twiddle<N, RL, NSL, -1>(w, j, tw);
+          dft_regs<RL, -1>(w);
+#pragma unroll
+          for (int q = 0; q < RL; ++q) {
+            const float sc = valid ? __ldg(&inv_eig[(size_t)(j + q * NSL) * p.nyc + ky]) : 0.f;
+            w[q].x *= sc;
+            w[q].y *= sc;
+          }
+          dft_regs<RL, +1>(w);
+#pragma unroll
+          for (int q = 0; q < RL; ++q) buf[(j * RL + q) * LS + c] = w[q];
+        }
+        __syncthreads();
+      }
+      if constexpr (P::R3 > 1) stage_smem<N, P::R2, P::R3, +1>(buf, LS, c, j, true, tw);
+      {
+        constexpr int R = P::R1;
+        constexpr int NS = N / R;
+        if (j < N / R) {
+          float2 w[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) w[r] = buf[(j + r * (N / R)) * LS + c];
+          stage_twiddle<N, R, NS, +1>(w, j, tw);
+          dft_regs<R, +1>(w);
+          if (valid) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+              const int row = j + q * NS;
+              Sr[row / RPC][(size_t)(row % RPC) * NYC + ky] = w[q];
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+  if (CL > 1) cluster.sync(); else __syncthreads();
+
+  // ---------------- phase 3: inverse row FFT; p rows overwrite the row slots of S ----------------
+  for (int pass = 0; pass < RPC / (2 * Q); ++pass) {
+    for (int idx = threadIdx.x; idx < Q * NYC; idx += NT) {
+      const int q = idx / NYC, k = idx - q * NYC;
+      const float2* row = S + (size_t)(pass * 2 * Q + 2 * q) * NYC;
+      const float2 A = row[k], B = row[NYC + k];
+      if (k == 0 || k == N / 2) {
+        buf[k * LS + q] = make_float2(A.x, B.x);
+      } else {
+        buf[k * LS + q] = make_float2(A.x - B.y, A.y + B.x);
+        buf[(N - k) * LS + q] = make_float2(A.x + B.y, B.x - A.y);
+      }
+    }
+    __syncthreads();
+    if constexpr (P::R3 > 1) {
+      stage_smem<N, P::R3, 1, +1>(buf, LS, c, j, true, tw);
+      stage_smem<N, P::R2, P::R3, +1>(buf, LS, c, j, true, tw);
+      stage_smem<N, P::R1, P::R3 * P::R2, +1>(buf, LS, c, j, true, tw);
+    } else {
+      stage_smem<N, P::R2, 1, +1>(buf, LS, c, j, true, tw);
+      stage_smem<N, P::R1, P::R2, +1>(buf, LS, c, j, true, tw);
+    }
+    for (int idx = threadIdx.x; idx < 2 * Q * N; idx += NT) {
+      const int r = idx / N, y = idx - r * N;
+      reinterpret_cast<float*>(S + (size_t)(pass * 2 * Q + r) * NYC)[y] =
+          reinterpret_cast<const float*>(&buf[y * LS + (r >> 1)])[r & 1];
+    }
+    __syncthreads();
+  }
+  if (CL > 1) cluster.sync();
+
+  // ---------------- phase 4: subtract the pressure gradient ----------------
+  {
+    const float* pnext = reinterpret_cast<const float*>(Sr[(rank + 1) % CL]);      // row 0 of the next CTA = x-halo
+    for (int idx = threadIdx.x; idx < RPC * N; idx += NT) {
+      const int r = idx / N, y = idx - r * N;
+      const float* prow = reinterpret_cast<const float*>(S + (size_t)r * NYC);
+      const float p0 = prow[y];
+      const float pyp = prow[(y + 1) & (N - 1)];
+      const float pxp = (r + 1 < RPC) ? reinterpret_cast<const float*>(S + (size_t)(r + 1) * NYC)[y] : pnext[y];
+      const size_t off = (size_t)(row0 + r) * N + y;
+      gu[off] -= (pxp - p0) * p.inv_hx;
+      gv[off] -= (pyp - p0) * p.inv_hy;
+      if (pout) pout[img + off] = p0;
+    }
+  }
+  if (CL > 1) cluster.sync();          // nobody exits while a neighbour may still read its shared memory
+}
+
+template <int N, int CL>
+static int launch_project_cluster_t(float* u, float* v, float* pout, const float* inv_eig, const float2* tw,
+                                    const SolverParams& p, cudaStream_t st) {
+  using C = ProjCfg<N>;
+  const size_t smem = C::smem(CL);
+  static bool attr_done = false;
+  if (!attr_done) {
+    MLSIM_CUDA_CHECK(cudaFuncSetAttribute(k_project_cluster<N, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(p.batch * CL));
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MLSIM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_project_cluster<N, CL>, u, v, pout, inv_eig, tw, p));
+  return MLSIM_OK;
+}
+
+bool project_cluster_supported(const SolverParams& p) {
+  return p.nx == p.ny && (p.nx == 64 || p.nx == 128 || p.nx == 256);
+}
+
+int launch_project_cluster(float* u, float* v, float* pout, const float* inv_eig, const float2* tw,
+                           const SolverParams& p, cudaStream_t st) {
+  switch (p.nx) {
+    case 64:  return launch_project_cluster_t<64, 1>(u, v, pout, inv_eig, tw, p, st);
+    case 128: return launch_project_cluster_t<128, 1>(u, v, pout, inv_eig, tw, p, st);
+    case 256: return launch_project_cluster_t<256, 4>(u, v, pout, inv_eig, tw, p, st);
+    default: set_error("cluster projection: unsupported grid"); return MLSIM_EINVAL;
   }
 }
 

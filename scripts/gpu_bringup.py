@@ -108,10 +108,13 @@ def timing(nx, ny, batch):
     cfgj = json.load(open(os.path.join(ROOT, "tests/golden/MLACFD.json")))
     model = models.buildModel(cfgj)
     plan = Plan(PlanConfig(nx=nx, ny=ny, batch=batch)); model.attach(plan)
-    names = ["explicit", "div_rfft", "col_solve", "irfft_grad", "conv_first", "conv_mid", "conv_last"]
+    names = ["explicit", "div_rfft", "col_solve", "irfft_grad", "conv_first", "conv_mid", "conv_last", "proj_cluster"]
     cells = nx * ny * batch
     for w, nm in enumerate(names):
-        ms = plan.time_kernel(w, 3, 10)
+        try:
+            ms = plan.time_kernel(w, 3, 10)
+        except Exception as e:
+            print(f'   [{nx}x{ny} b{batch}] {nm:11s} n/a ({e})'); continue
         extra = ""
         if w == 5:
             extra = f" -> {2*9*64*64*cells/ms/1e9:.1f} TFLOP/s"

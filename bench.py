@@ -293,15 +293,126 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_slab(args):
+    """--workload slab: BASELINE.json configs[4] -- ONE nx x nx periodic grid (default 8192) decomposed into x-slabs over
+    the N GPUs (strong scaling: total work fixed), RK4 solver step + MLACFD correction CNN, halo exchange + spectral
+    all-to-all over NCCL every stage.  Prints one JSON line like the default workload."""
+    import torch
+    import torch.distributed as dist
+    from ml_accelerated_simulation_b200 import ensemble, models
+    from ml_accelerated_simulation_b200.slab import CudaSlabBackend, SlabComm, SlabGeometry, SlabStepper
+
+    rank, world, local = _dist()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    peaks = _peaks()
+    n = args.nx
+    cfgj, sd = _model_state()
+    model = models.buildModel(cfgj)
+    model.load_state_dict(sd)
+    geom = SlabGeometry(nx=n, ny=n, batch=1, rank=rank, world=world)
+    be = CudaSlabBackend(geom, device=local)
+    be.set_cnn(model.cnn.folded_layers())
+    stp = SlabStepper(be, SlabComm(geom))
+    # synthetic IC: band-limited random field built per slab (same generator family on every rank), made
+    # divergence-free by the slab projection itself and scaled to max speed 7 (reference src/inference.py:54-58,76-78)
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    xs = torch.arange(geom.nxl, device=dev, dtype=torch.float32)[:, None] + rank * geom.nxl
+    ys = torch.arange(n, device=dev, dtype=torch.float32)[None, :]
+    h = 2 * torch.pi / n
+    u0 = torch.zeros(1, geom.nxl, n, device=dev)
+    v0 = torch.zeros(1, geom.nxl, n, device=dev)
+    gc = torch.Generator().manual_seed(42)                       # same modes on every rank
+    for _ in range(16):
+        kx, ky = (int(t) for t in torch.randint(1, 7, (2,), generator=gc))
+        a, b, ph1, ph2 = (float(t) for t in torch.rand(4, generator=gc))
+        u0 += (a - 0.5) * torch.sin(kx * xs * h + ky * ys * h + 6.28 * ph1)
+        v0 += (b - 0.5) * torch.cos(kx * xs * h - ky * ys * h + 6.28 * ph2)
+    stp.set_local(u0, v0)
+    for _ in range(2):
+        stp.project()
+        ul, vl = stp.local()
+        smax = torch.sqrt(ul * ul + vl * vl).max()
+        if world > 1:
+            dist.all_reduce(smax, op=dist.ReduceOp.MAX)
+        ul.mul_(7.0 / smax); vl.mul_(7.0 / smax)
+    stp.project()
+    cells = n * n
+    K, W = args.steps, max(args.warmup, 3)
+
+    def timed(apply_cnn):
+        stp.step(W, apply_cnn=apply_cnn)
+        ensemble.barrier(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        stp.step(K, apply_cnn=apply_cnn)
+        e1.record()
+        ensemble.barrier(dev)
+        return ensemble.max_over_ranks(e0.elapsed_time(e1), dev) / K, t0, time.time()
+
+    solver_ms, _, _ = timed(False)
+    sampler = ClockSampler(local) if rank == 0 else None
+    be.plan.profile_enable(5, 5 * K + 8)
+    ms, t0, t1 = timed(True)
+    mid_ms, mid_n = be.plan.profile_read()
+    be.plan.profile_enable(-1, 0)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ul, vl = stp.local()
+    assert bool(torch.isfinite(ul).all()), "rollout diverged"
+    # per-kernel-class device time of the solver phases (CUDA events around every launch), solver-only steps
+    phase = {}
+    for cls, nm in ((0, "explicit"), (1, "div_rfft"), (2, "x_solve(3 kernels)"), (3, "irfft_grad")):
+        be.plan.profile_enable(cls, 64)
+        stp.step(2, apply_cnn=False)
+        tms, cnt = be.plan.profile_read()
+        phase[nm] = tms / max(cnt, 1)
+    be.plan.profile_enable(-1, 0)
+    if rank == 0:
+        rows = geom.nxl + (0 if world == 1 else (7 if rank in (0, world - 1) else 14))
+        mid_avg = mid_ms / max(mid_n, 1)
+        mid_tflops = MID_FLOP_PER_CELL * rows * n / (mid_avg * 1e-3) / 1e12
+        value = cells / (ms * 1e-3)
+        solver_rate = cells / (solver_ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 solver + bf16 conv (fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": f"single {n}x{n} periodic grid, batch 1, x-slab decomposition over {world} GPU(s) "
+                                   "(halo exchange + spectral all-to-all per RK stage over NCCL), RK4 solver step + MLACFD correction CNN",
+                       "l2": "fields 268 MB each at 8192^2 > 126 MB L2; no flush", "exchanges_per_step": 13},
+            "roofline": {"kernel": "k_conv_mid<64>", "bound": "tensor", "achieved": mid_tflops, "peak": peaks["tensor_tflops"],
+                         "unit": "TFLOP/s", "frac": mid_tflops / peaks["tensor_tflops"], "traffic": None,
+                         "avg_launch_ms": mid_avg, "launches_timed": mid_n, "peak_source": peaks["source"]},
+            "solver_roofline": {"bound": "hbm", "ms_per_step": solver_ms, "cell_steps_per_s": solver_rate,
+                                "achieved": SOLVER_BYTES_PER_CELL_STEP * solver_rate / world / 1e9, "peak": peaks["hbm_gbs"],
+                                "unit": "GB/s per GPU", "frac": SOLVER_BYTES_PER_CELL_STEP * solver_rate / world / 1e9 / peaks["hbm_gbs"],
+                                "phase_ms_per_launch": phase,
+                                "note": "312 B/cell-step algorithmic; includes the NCCL exchanges (4 halo + 8 all-to-all per step)"},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": (24 + 7) * K, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    be.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ensemble", choices=["ensemble", "slab"],
+                    help="ensemble: BASELINE configs[1] (default, the driver's line); slab: configs[4], one big grid over N GPUs")
+    ap.add_argument("--nx", type=int, default=8192, help="grid size of the slab workload")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "slab":
+        run_slab(args)
     else:
         run_ours(args)
 

@@ -38,7 +38,7 @@ typedef struct mlsim_plan mlsim_plan;
  * grids.Grid((nx,ny), domain=((0,lx),(0,ly))), stable_time_step(...) -> dt,
  * NavierStokes2DFVMProjection(viscosity, density, drag, forcing=KolmogorovForcing(wave_number, scale)). */
 typedef struct {
-  int32_t nx, ny, batch;          /* powers of two, 64 <= n <= 2048 (batch >= 1) */
+  int32_t nx, ny, batch;          /* powers of two, 64 <= n <= 8192 (batch >= 1); nx is the GLOBAL extent in slab mode */
   double  lx, ly;                 /* domain lengths (reference: 2*pi) */
   double  dt;                     /* full RK4 step */
   double  viscosity, density, drag;
@@ -47,6 +47,9 @@ typedef struct {
   int32_t advection;              /* MLSIM_ADV_* (reference: van Leer) */
   double  lw_dt_scale;            /* 1.0: Lax-Wendroff Courant number uses the full dt */
   int32_t device;                 /* CUDA device ordinal */
+  int32_t slab_rank, slab_world;  /* slab_world == 0: plain plan (whole grid on this device).  slab_world >= 1: this
+                                   * rank owns global rows [slab_rank*nx/slab_world, (slab_rank+1)*nx/slab_world) of one
+                                   * grid decomposed along x; only the mlsim_slab_* / mlsim_cnn_* entry points apply */
 } mlsim_config;
 
 int  mlsim_plan_create (const mlsim_config* cfg, mlsim_plan** out);
@@ -93,6 +96,25 @@ int  mlsim_cnn_forward(mlsim_plan* plan, const float* u, const float* v, float* 
                        double cnn_input_scale, void* stream);
 /* u += y[:,0]; v += y[:,1] with y = model(...) -- the fused correction-add of src/inference.py:102 */
 int  mlsim_cnn_correct(mlsim_plan* plan, float* u, float* v, double cnn_input_scale, void* stream);
+
+/* ---- slab decomposition along x: one large grid over several GPUs (BASELINE.json configs[4]; reference analogue:
+ * the same RKStepper.forward / model(v) calls of src/inference.py:100-102 on a grid that does not fit the per-step
+ * budget of one device).  The caller owns and exchanges the buffers (NCCL via torch.distributed in slab.py):
+ *   field pair   uv[2][batch][ext_rows][ny] fp32, local row i at ext row i + halo  (geometry: mlsim_slab_geometry)
+ *   fwd chunks   [world][batch][nxl  ][kywp] float2     bwd chunks  [world][batch][nxl+1][kywp] float2
+ * One RK stage = halo exchange of `us` (3 rows from below, 2 from above, periodic) -> mlsim_slab_stage_a (explicit
+ * terms + RK combine for rows [-1, nxl), divergence + row FFT -> fwd chunks) -> all-to-all -> mlsim_slab_stage_b
+ * (x-transform * inverse Laplacian spectrum * inverse x-transform on this rank's spectral columns -> bwd chunks) ->
+ * all-to-all -> mlsim_slab_stage_c (row inverse FFT + gradient subtraction, in place on `uv`).
+ * mlsim_slab_cnn_correct needs 7 current halo rows per interior side (zero padding at the global edges). */
+/* out8 = {nxl, halo, ext_rows, kyw, kywp, kyv (this rank's valid spectral columns), outer radix r0, cnn halo} */
+int  mlsim_slab_geometry(mlsim_plan* plan, int64_t* out8);
+int  mlsim_slab_stage_a(mlsim_plan* plan, int32_t stage, const float* us, const float* u0, float* acc, float* out,
+                        void* spec_send, void* stream);
+int  mlsim_slab_divergence_rfft(mlsim_plan* plan, const float* uv, void* spec_send, void* stream);   /* P alone: first half */
+int  mlsim_slab_stage_b(mlsim_plan* plan, const void* spec_recv, void* spec_send2, void* stream);
+int  mlsim_slab_stage_c(mlsim_plan* plan, const void* spec_recv2, float* uv, float* p_or_null, void* stream);
+int  mlsim_slab_cnn_correct(mlsim_plan* plan, float* uv, double cnn_input_scale, void* stream);
 
 /* ---- introspection ---- */
 /* number of kernel launches one mlsim_step(nsteps=1) issues (solver only, or solver + cnn) */

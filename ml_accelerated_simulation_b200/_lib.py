@@ -23,6 +23,7 @@ class MlsimConfig(C.Structure):
         ("forcing_wavenumber", C.c_int32), ("forcing_scale", C.c_double),
         ("advection", C.c_int32), ("lw_dt_scale", C.c_double),
         ("device", C.c_int32),
+        ("slab_rank", C.c_int32), ("slab_world", C.c_int32),
     ]
 
 
@@ -49,6 +50,12 @@ _SIGNATURES = {
     "mlsim_divergence": (C.c_int, [C.c_void_p] * 4 + [C.c_void_p]),
     "mlsim_cnn_forward": (C.c_int, [C.c_void_p] * 4 + [C.c_double, C.c_void_p]),
     "mlsim_cnn_correct": (C.c_int, [C.c_void_p] * 3 + [C.c_double, C.c_void_p]),
+    "mlsim_slab_geometry": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "mlsim_slab_stage_a": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 6),
+    "mlsim_slab_divergence_rfft": (C.c_int, [C.c_void_p] * 4),
+    "mlsim_slab_stage_b": (C.c_int, [C.c_void_p] * 4),
+    "mlsim_slab_stage_c": (C.c_int, [C.c_void_p] * 5),
+    "mlsim_slab_cnn_correct": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     "mlsim_launches_per_step": (C.c_int, [C.c_void_p, C.c_int32]),
     "mlsim_workspace_bytes": (C.c_int64, [C.c_void_p]),
     "mlsim_time_kernel": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_void_p]),

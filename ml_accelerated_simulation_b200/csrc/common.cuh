@@ -40,6 +40,11 @@ struct SolverParams {
   float dt_hx, dt_hy;         // lw_dt_scale*dt/h  (Courant factor)
   float drag;
   int advection;
+  long long img_stride;       // elements between consecutive images of a field (plain: nx*ny; slab: ext_rows*ny)
+  // slab decomposition along x (mlsim_config.slab_world >= 1): nx above is the LOCAL row count, field pointers
+  // address local row 0 of halo-extended buffers (rows [-halo, nx+halo) are valid memory, no periodic wrap in x)
+  int halo;
+  int kyw, kywp;              // spectral columns per rank chunk and its padded pitch (float2 units)
 };
 
 // Stage coefficients of the RK4-with-projection scheme.

@@ -79,8 +79,8 @@ k_conv_first(ConvFirstArgs a) {
     const int x = (tile / nyt) % a.nx;
     const int b = tile / (nyt * a.nx);
     const int y = yt * 128 + tid;
-    const float* __restrict__ gu = a.u + (size_t)b * a.nx * a.ny;
-    const float* __restrict__ gv = a.v + (size_t)b * a.nx * a.ny;
+    const float* __restrict__ gu = a.u + (size_t)b * a.img_stride;
+    const float* __restrict__ gv = a.v + (size_t)b * a.img_stride;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const int xx = x + i - 1;
@@ -400,7 +400,7 @@ k_conv_mid(ConvMidArgs a) {
         float u_old = 0.0f, v_old = 0.0f;
         if constexpr (LAST) {
           if (a.y_nchw == nullptr && y < a.ny) {
-            const size_t off0 = ((size_t)b * a.nx + x) * a.ny + y;
+            const size_t off0 = (size_t)b * a.img_stride + (size_t)x * a.ny + y;
             u_old = a.u[off0];
             v_old = a.v[off0];
           }
@@ -464,7 +464,7 @@ k_conv_mid(ConvMidArgs a) {
           tc_fence_before();
           if (lane == 0) mbar_arrive(&tempty[slot]);
           if (y < a.ny) {
-            const size_t off = ((size_t)b * a.nx + x) * a.ny + y;
+            const size_t off = (size_t)b * a.img_stride + (size_t)x * a.ny + y;
             if (a.y_nchw != nullptr) {
               const size_t img = (size_t)a.nx * a.ny;
 #pragma unroll

@@ -10,6 +10,7 @@ struct ConvFirstArgs {
   const uint8_t* wimg;                // packed weights (conv_first_wimg_bytes)
   float scale;                        // cnn_input_scale
   int nx, ny, batch;
+  long long img_stride;               // elements between consecutive images of u / v (nx*ny unless halo-extended)
   int reverse;                        // traverse tiles last-to-first (see ConvMidArgs::reverse)
 };
 
@@ -20,6 +21,7 @@ struct ConvMidArgs {
   float* y_nchw;                      // last layer, test hook output [batch][cout][nx][ny]
   const uint8_t* wimg;                // packed weights + bias
   int nx, ny, batch;
+  long long img_stride;               // elements between consecutive images of u / v (fused correction add)
   int rs;                             // output rows per work item (strip length)
   int cout;                           // real output channels of this layer
   int relu;

@@ -98,17 +98,29 @@ __device__ __forceinline__ int stage_out_base(int j) {
   return (j / NS) * NS * R + (j & (NS - 1));
 }
 
-// One complete shared-memory -> shared-memory stage for the thread's butterfly j (if j < N/R) on the
-// line at column offset `c` of a line-fastest buffer with line stride LS (float2 units).  Contains the
-// two __syncthreads() that make the in-place update safe; every thread of the block must call it.
-template <int N, int R, int NS, int SIGN>
-__device__ __forceinline__ void stage_smem(float2* buf, int LS, int c, int j, bool active,
-                                           const float2* __restrict__ tw) {
+// Shared-memory layout of a bundle of Q lines ("line-fastest": the Q lines' values of one point index are adjacent).
+//   Q >= 4: pitch Q+1 per point index (conflict-free for the Stockham stages and for row-major I/O);
+//   Q <= 2: long lines (N >= 4096): pitch Q with a skew of one point every 16 (a stride-8/16 first-stage store of a
+//           half warp then hits 16 distinct 8-byte bank pairs instead of 2).
+template <int Q>
+__host__ __device__ __forceinline__ constexpr int fidx(int idx, int c) {
+  return (Q >= 4) ? idx * (Q + 1) + c : (idx + (idx >> 4)) * Q + c;
+}
+template <int N, int Q>
+__host__ __device__ constexpr size_t fft_buf_elems() {
+  return (Q >= 4) ? (size_t)N * (Q + 1) : (size_t)(N + N / 16) * Q;
+}
+
+// One complete shared-memory -> shared-memory stage for the thread's butterfly j (if j < N/R) on line `c` of a
+// Q-line bundle.  Contains the two __syncthreads() that make the in-place update safe; every thread of the block
+// must call it.
+template <int N, int R, int NS, int SIGN, int Q>
+__device__ __forceinline__ void stage_smem(float2* buf, int c, int j, bool active, const float2* __restrict__ tw) {
   float2 v[R];
   const bool on = active && (j < N / R);
   if (on) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = buf[(j + r * (N / R)) * LS + c];
+    for (int r = 0; r < R; ++r) v[r] = buf[fidx<Q>(j + r * (N / R), c)];
   }
   __syncthreads();
   if (on) {
@@ -116,24 +128,54 @@ __device__ __forceinline__ void stage_smem(float2* buf, int LS, int c, int j, bo
     dft_regs<R, SIGN>(v);
     const int j0 = stage_out_base<R, NS>(j);
 #pragma unroll
-    for (int q = 0; q < R; ++q) buf[(j0 + q * NS) * LS + c] = v[q];
+    for (int q = 0; q < R; ++q) buf[fidx<Q>(j0 + q * NS, c)] = v[q];
   }
   __syncthreads();
 }
 
-// Radix plans per transform length (R3 == 1 means two stages).  R1*R2*R3 == N.
+// Radix plans per transform length (R3 == 1 / R4 == 1 mean fewer stages).  R1*R2*R3*R4 == N.
 template <int N> struct FftPlan;
-template <> struct FftPlan<64>   { static constexpr int R1 = 8,  R2 = 8,  R3 = 1; };
-template <> struct FftPlan<128>  { static constexpr int R1 = 8,  R2 = 16, R3 = 1; };
-template <> struct FftPlan<256>  { static constexpr int R1 = 16, R2 = 16, R3 = 1; };
-template <> struct FftPlan<512>  { static constexpr int R1 = 8,  R2 = 8,  R3 = 8; };
-template <> struct FftPlan<1024> { static constexpr int R1 = 8,  R2 = 8,  R3 = 16; };
-template <> struct FftPlan<2048> { static constexpr int R1 = 8,  R2 = 16, R3 = 16; };
+template <> struct FftPlan<64>   { static constexpr int R1 = 8,  R2 = 8,  R3 = 1,  R4 = 1; };
+template <> struct FftPlan<128>  { static constexpr int R1 = 8,  R2 = 16, R3 = 1,  R4 = 1; };
+template <> struct FftPlan<256>  { static constexpr int R1 = 16, R2 = 16, R3 = 1,  R4 = 1; };
+template <> struct FftPlan<512>  { static constexpr int R1 = 8,  R2 = 8,  R3 = 8,  R4 = 1; };
+template <> struct FftPlan<1024> { static constexpr int R1 = 8,  R2 = 8,  R3 = 16, R4 = 1; };
+template <> struct FftPlan<2048> { static constexpr int R1 = 8,  R2 = 16, R3 = 16, R4 = 1; };
+template <> struct FftPlan<4096> { static constexpr int R1 = 16, R2 = 16, R3 = 16, R4 = 1; };
+template <> struct FftPlan<8192> { static constexpr int R1 = 8,  R2 = 8,  R3 = 8,  R4 = 16; };
 
 template <int N> struct FftMinRadix {
   using P = FftPlan<N>;
   static constexpr int a = P::R1 < P::R2 ? P::R1 : P::R2;
-  static constexpr int value = (P::R3 > 1 && P::R3 < a) ? P::R3 : a;
+  static constexpr int b = (P::R3 > 1 && P::R3 < a) ? P::R3 : a;
+  static constexpr int value = (P::R4 > 1 && P::R4 < b) ? P::R4 : b;
 };
+
+// All forward stages (R1, R2, R3, R4) / all inverse stages (reversed radix order) of a Q-line bundle in shared memory.
+template <int N, int Q>
+__device__ __forceinline__ void fft_lines_forward(float2* buf, int c, int j, const float2* __restrict__ tw) {
+  using P = FftPlan<N>;
+  stage_smem<N, P::R1, 1, -1, Q>(buf, c, j, true, tw);
+  stage_smem<N, P::R2, P::R1, -1, Q>(buf, c, j, true, tw);
+  if constexpr (P::R3 > 1) stage_smem<N, P::R3, P::R1 * P::R2, -1, Q>(buf, c, j, true, tw);
+  if constexpr (P::R4 > 1) stage_smem<N, P::R4, P::R1 * P::R2 * P::R3, -1, Q>(buf, c, j, true, tw);
+}
+template <int N, int Q>
+__device__ __forceinline__ void fft_lines_inverse(float2* buf, int c, int j, const float2* __restrict__ tw) {
+  using P = FftPlan<N>;
+  if constexpr (P::R4 > 1) {
+    stage_smem<N, P::R4, 1, +1, Q>(buf, c, j, true, tw);
+    stage_smem<N, P::R3, P::R4, +1, Q>(buf, c, j, true, tw);
+    stage_smem<N, P::R2, P::R4 * P::R3, +1, Q>(buf, c, j, true, tw);
+    stage_smem<N, P::R1, P::R4 * P::R3 * P::R2, +1, Q>(buf, c, j, true, tw);
+  } else if constexpr (P::R3 > 1) {
+    stage_smem<N, P::R3, 1, +1, Q>(buf, c, j, true, tw);
+    stage_smem<N, P::R2, P::R3, +1, Q>(buf, c, j, true, tw);
+    stage_smem<N, P::R1, P::R3 * P::R2, +1, Q>(buf, c, j, true, tw);
+  } else {
+    stage_smem<N, P::R2, 1, +1, Q>(buf, c, j, true, tw);
+    stage_smem<N, P::R1, P::R2, +1, Q>(buf, c, j, true, tw);
+  }
+}
 
 }  // namespace mlsim

@@ -27,6 +27,11 @@ struct CnnLayer {
 
 using namespace mlsim;
 
+#define MLSIM_SLAB_HALO 8          /* halo rows on each side of the halo-extended field buffers */
+#define MLSIM_SLAB_CNN_HALO 7      /* rows of state the 7-layer 3x3 CNN needs from each neighbour (one per layer) */
+#define MLSIM_PLAIN_ONLY(pl) do { if ((pl)->slab) { set_error("this entry point needs a plain plan (slab_world == 0); use mlsim_slab_*"); return MLSIM_ESTATE; } } while (0)
+#define MLSIM_SLAB_ONLY(pl) do { if (!(pl)->slab) { set_error("this entry point needs a slab plan (slab_world >= 1)"); return MLSIM_ESTATE; } } while (0)
+
 struct mlsim_plan {
   mlsim_config cfg;
   SolverParams sp;
@@ -42,6 +47,12 @@ struct mlsim_plan {
   float* d_w2u = nullptr; float* d_w2v = nullptr;
   float* d_accu = nullptr; float* d_accv = nullptr;
   float2* d_spec = nullptr;
+  float2* d_tw_n2 = nullptr;            // twiddles of the in-smem column transform (length n2len; == d_twx when r0 == 1)
+  float2* d_split = nullptr;            // T buffer of the split x-transform (r0 > 1 or slab mode)
+  int r0 = 1, n2len = 0;                // nx(global) = r0 * n2len, n2len <= 2048
+  // slab decomposition (cfg.slab_world >= 1): this rank owns global rows [rank*nxl, (rank+1)*nxl)
+  bool slab = false;
+  int nxg = 0, nxl = 0, ext_rows = 0, kyw = 0, kywp = 0, kyv = 0, ky0 = 0;
   // cnn
   std::vector<CnnLayer> layers;
   bool cnn_ready = false;
@@ -87,7 +98,7 @@ uint16_t f32_to_bf16_rne(float f) {
 
 int build_tables(mlsim_plan* pl) {
   const mlsim_config& c = pl->cfg;
-  const int nx = c.nx, ny = c.ny, nyc = ny / 2 + 1;
+  const int nx = c.nx, ny = c.ny, nyc = ny / 2 + 1;      // nx = GLOBAL row count (also in slab mode)
   const double hx = c.lx / nx, hy = c.ly / ny;
   const double PI = 3.14159265358979323846;
   std::vector<float> forcing(ny);
@@ -95,29 +106,38 @@ int build_tables(mlsim_plan* pl) {
     forcing[j] = (float)(c.forcing_scale * sin(c.forcing_wavenumber * (j + 0.5) * hy) / c.density);
   // inverse spectrum of the periodic 5-point Laplacian, 1/(nx*ny) folded in.
   // cutoff 10*eps(float64): the reference solves in fp64, so only the (0,0) mode is removed.
-  std::vector<float> inv((size_t)nx * nyc);
+  // Table layout [k1 (r0)][k2 (n2len)][ky - ky0 (kyv)] with kx = k1 + r0*k2: the order in which the split
+  // x-transform produces the spectrum (r0 == 1: plain [kx][ky]); slab mode keeps only this rank's columns.
+  const int r0 = pl->r0, n2 = pl->n2len;
+  const int ky0 = pl->slab ? pl->ky0 : 0, kyv = pl->slab ? pl->kyv : nyc;
+  std::vector<float> inv((size_t)nx * kyv);
   const double cutoff = 10.0 * 2.220446049250313e-16;
-  for (int kx = 0; kx < nx; ++kx) {
-    const double lx = (2.0 * cos(2.0 * PI * kx / nx) - 2.0) / (hx * hx);
-    for (int ky = 0; ky < nyc; ++ky) {
-      const double ly = (2.0 * cos(2.0 * PI * ky / ny) - 2.0) / (hy * hy);
-      const double lam = lx + ly;
-      inv[(size_t)kx * nyc + ky] = (fabs(lam) > cutoff) ? (float)(1.0 / lam / ((double)nx * ny)) : 0.0f;
+  for (int k1 = 0; k1 < r0; ++k1)
+    for (int k2 = 0; k2 < n2; ++k2) {
+      const int kx = k1 + r0 * k2;
+      const double lx = (2.0 * cos(2.0 * PI * kx / nx) - 2.0) / (hx * hx);
+      for (int k = 0; k < kyv; ++k) {
+        const double ly = (2.0 * cos(2.0 * PI * (ky0 + k) / ny) - 2.0) / (hy * hy);
+        const double lam = lx + ly;
+        inv[((size_t)k1 * n2 + k2) * kyv + k] = (fabs(lam) > cutoff) ? (float)(1.0 / lam / ((double)nx * ny)) : 0.0f;
+      }
     }
-  }
-  std::vector<float2> twx(nx), twy(ny);
+  std::vector<float2> twx(nx), twy(ny), twn(n2);
   for (int m = 0; m < nx; ++m) twx[m] = make_float2((float)cos(2.0 * PI * m / nx), (float)(-sin(2.0 * PI * m / nx)));
   for (int m = 0; m < ny; ++m) twy[m] = make_float2((float)cos(2.0 * PI * m / ny), (float)(-sin(2.0 * PI * m / ny)));
+  for (int m = 0; m < n2; ++m) twn[m] = make_float2((float)cos(2.0 * PI * m / n2), (float)(-sin(2.0 * PI * m / n2)));
 
   int rc;
   if ((rc = dev_alloc(pl, &pl->d_forcing, ny))) return rc;
   if ((rc = dev_alloc(pl, &pl->d_inv_eig, inv.size()))) return rc;
   if ((rc = dev_alloc(pl, &pl->d_twx, nx))) return rc;
   if ((rc = dev_alloc(pl, &pl->d_twy, ny))) return rc;
+  if ((rc = dev_alloc(pl, &pl->d_tw_n2, n2))) return rc;
   MLSIM_CUDA_CHECK(cudaMemcpy(pl->d_forcing, forcing.data(), ny * sizeof(float), cudaMemcpyHostToDevice));
   MLSIM_CUDA_CHECK(cudaMemcpy(pl->d_inv_eig, inv.data(), inv.size() * sizeof(float), cudaMemcpyHostToDevice));
   MLSIM_CUDA_CHECK(cudaMemcpy(pl->d_twx, twx.data(), nx * sizeof(float2), cudaMemcpyHostToDevice));
   MLSIM_CUDA_CHECK(cudaMemcpy(pl->d_twy, twy.data(), ny * sizeof(float2), cudaMemcpyHostToDevice));
+  MLSIM_CUDA_CHECK(cudaMemcpy(pl->d_tw_n2, twn.data(), n2 * sizeof(float2), cudaMemcpyHostToDevice));
   return MLSIM_OK;
 }
 
@@ -163,7 +183,12 @@ int project(mlsim_plan* pl, float* u, float* v, float* p_or_null, cudaStream_t s
   }
   float2* spec = pl->d_spec + c.soff(pl);
   { ProfScope ps(pl, 1, st); if ((rc = launch_div_rfft(u, v, spec, pl->d_twy, sp, st))) return rc; }
-  { ProfScope ps(pl, 2, st); if ((rc = launch_col_solve(spec, pl->d_inv_eig, pl->d_twx, sp, st))) return rc; }
+  {
+    ProfScope ps(pl, 2, st);
+    if (pl->r0 == 1) rc = launch_col_solve(spec, pl->d_inv_eig, pl->d_twx, sp, sp.nx, sp.batch, 1, st);
+    else rc = launch_col_solve_split(spec, pl->d_split + c.soff(pl), pl->d_inv_eig, pl->d_twx, pl->d_tw_n2, sp, pl->r0, st);
+    if (rc) return rc;
+  }
   ProfScope ps(pl, 3, st);
   return launch_irfft_grad(spec, u, v, u, v, p_or_null, pl->d_twy, sp, st);
 }
@@ -217,7 +242,7 @@ int cnn_apply(mlsim_plan* pl, const float* u_in, const float* v_in, float* u, fl
   __nv_bfloat16* act[2] = {pl->d_act[0] + aoff, pl->d_act[1] + aoff};
   ConvFirstArgs f;
   f.u = u_in; f.v = v_in; f.out = act[0]; f.wimg = pl->layers[0].d_wimg; f.scale = (float)scale;
-  f.nx = c.nx; f.ny = c.ny; f.batch = ck.nb; f.reverse = 0;
+  f.nx = c.nx; f.ny = c.ny; f.batch = ck.nb; f.reverse = 0; f.img_stride = (long long)c.nx * c.ny;
   { ProfScope ps(pl, 4, st); if ((rc = launch_conv_first(f, pl->sm_count, st))) return rc; }
   int cur = 0;
   for (int l = 1; l < L; ++l) {
@@ -225,7 +250,7 @@ int cnn_apply(mlsim_plan* pl, const float* u_in, const float* v_in, float* u, fl
     m.in = act[cur]; m.out = act[cur ^ 1];
     m.u = u; m.v = v; m.y_nchw = y_nchw;
     m.wimg = pl->layers[l].d_wimg;
-    m.nx = c.nx; m.ny = c.ny; m.batch = ck.nb; m.rs = pl->rs;
+    m.nx = c.nx; m.ny = c.ny; m.batch = ck.nb; m.rs = pl->rs; m.img_stride = (long long)c.nx * c.ny;
     m.cout = pl->layers[l].cout; m.relu = pl->layers[l].relu; m.dbg = nullptr;
     m.reverse = l & 1;                  // layer 0 ascending, layer 1 descending, ...
     if (l < L - 1) {
@@ -262,11 +287,20 @@ const char* mlsim_version(void) { return "mlsim-b200 0.1 (sm_100a)"; }
 int mlsim_plan_create(const mlsim_config* cfg, mlsim_plan** out) {
   if (!cfg || !out) { set_error("null argument"); return MLSIM_EINVAL; }
   *out = nullptr;
-  MLSIM_REQUIRE(is_pow2(cfg->nx) && cfg->nx >= 64 && cfg->nx <= 2048, "nx must be a power of two in [64, 2048]");
-  MLSIM_REQUIRE(is_pow2(cfg->ny) && cfg->ny >= 64 && cfg->ny <= 2048, "ny must be a power of two in [64, 2048]");
+  MLSIM_REQUIRE(is_pow2(cfg->nx) && cfg->nx >= 64 && cfg->nx <= 8192, "nx must be a power of two in [64, 8192]");
+  MLSIM_REQUIRE(is_pow2(cfg->ny) && cfg->ny >= 64 && cfg->ny <= 8192, "ny must be a power of two in [64, 8192]");
   MLSIM_REQUIRE(cfg->batch >= 1 && cfg->batch <= 65535, "batch must be in [1, 65535]");
   MLSIM_REQUIRE(cfg->lx > 0 && cfg->ly > 0 && cfg->dt > 0 && cfg->density > 0, "lx, ly, dt, density must be positive");
   MLSIM_REQUIRE(cfg->advection >= 0 && cfg->advection <= 2, "unknown advection scheme");
+  MLSIM_REQUIRE((long)cfg->batch * (cfg->nx > 2048 ? cfg->nx / 2048 : 1) <= 65535, "batch * (nx/2048) must be <= 65535");
+  const bool slab = cfg->slab_world >= 1;
+  if (slab) {
+    const int W = cfg->slab_world;
+    MLSIM_REQUIRE(is_pow2(W) && W <= 64, "slab_world must be a power of two");
+    MLSIM_REQUIRE(cfg->slab_rank >= 0 && cfg->slab_rank < W, "slab_rank out of range");
+    MLSIM_REQUIRE(cfg->nx / W >= 32, "a slab needs at least 32 rows per rank");
+    MLSIM_REQUIRE(cfg->ny / 2 >= W * W, "ny too small for this many ranks (every rank needs spectral columns)");
+  }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -286,8 +320,22 @@ int mlsim_plan_create(const mlsim_config* cfg, mlsim_plan** out) {
   pl->sm_count = prop.multiProcessorCount;
   const double hx = cfg->lx / cfg->nx, hy = cfg->ly / cfg->ny;
   SolverParams& sp = pl->sp;
-  sp.nx = cfg->nx; sp.ny = cfg->ny; sp.batch = cfg->batch;
-  sp.nyc = cfg->ny / 2 + 1;
+  const int nyc = cfg->ny / 2 + 1;
+  pl->slab = slab;
+  pl->nxg = cfg->nx;
+  pl->r0 = cfg->nx > 2048 ? cfg->nx / 2048 : 1;
+  pl->n2len = cfg->nx / pl->r0;
+  if (slab) {
+    const int W = cfg->slab_world;
+    pl->nxl = cfg->nx / W;
+    pl->ext_rows = pl->nxl + 2 * MLSIM_SLAB_HALO;
+    pl->kyw = (nyc + W - 1) / W;
+    pl->kywp = (pl->kyw + 3) & ~3;
+    pl->ky0 = cfg->slab_rank * pl->kyw;
+    pl->kyv = nyc - pl->ky0 < pl->kyw ? nyc - pl->ky0 : pl->kyw;
+  }
+  sp.nx = slab ? pl->nxl : cfg->nx; sp.ny = cfg->ny; sp.batch = cfg->batch;
+  sp.nyc = nyc;
   sp.nycp = (sp.nyc + 3) & ~3;
   sp.inv_hx = (float)(1.0 / hx); sp.inv_hy = (float)(1.0 / hy);
   sp.nu_hx2 = (float)(cfg->viscosity / cfg->density / (hx * hx));
@@ -296,23 +344,45 @@ int mlsim_plan_create(const mlsim_config* cfg, mlsim_plan** out) {
   sp.dt_hy = (float)(cfg->lw_dt_scale * cfg->dt / hy);
   sp.drag = (float)cfg->drag;
   sp.advection = cfg->advection;
-  pl->field_elems = (size_t)cfg->batch * cfg->nx * cfg->ny;
-  // measured on B200 at 256^2 x 64: 0.0665 ms vs 0.0525 ms for K2+K3+K4 (the state is L2-resident, so saving the
-  // spectral round trip does not pay for the cluster barriers) -> opt-in only.
-  { const char* e = getenv("MLSIM_CLUSTER_PROJECTION"); pl->cluster_projection = project_cluster_supported(sp) && e != nullptr && e[0] == '1'; }
+  sp.img_stride = slab ? (long long)pl->ext_rows * cfg->ny : (long long)cfg->nx * cfg->ny;
+  sp.halo = slab ? MLSIM_SLAB_HALO : 0;
+  sp.kyw = pl->kyw; sp.kywp = pl->kywp;
+  pl->field_elems = (size_t)cfg->batch * sp.nx * cfg->ny;
+  // Single-kernel projection: measured on B200 -- 128^2 x 512: 0.103 ms vs 0.117 ms for K2+K3+K4 (one CTA per image,
+  // no cluster barrier); 256^2 x 64: 0.0665 ms vs 0.0525 ms (4-CTA cluster, DSMEM transposes; the L2-resident
+  // spectral round trip is cheaper than the cluster barriers).  Default: on for nx <= 128, off above;
+  // MLSIM_CLUSTER_PROJECTION=0/1 overrides.
+  {
+    const char* ev = getenv("MLSIM_CLUSTER_PROJECTION");
+    const bool want = ev ? (ev[0] == '1') : (cfg->nx <= 128);
+    pl->cluster_projection = !slab && project_cluster_supported(sp) && want;
+  }
 
   int rc = build_tables(pl);
   const size_t n = pl->field_elems;
-  if (!rc) rc = dev_alloc(pl, &pl->d_w1u, n);
-  if (!rc) rc = dev_alloc(pl, &pl->d_w1v, n);
-  if (!rc) rc = dev_alloc(pl, &pl->d_w2u, n);
-  if (!rc) rc = dev_alloc(pl, &pl->d_w2v, n);
-  if (!rc) rc = dev_alloc(pl, &pl->d_accu, n);
-  if (!rc) rc = dev_alloc(pl, &pl->d_accv, n);
-  if (!rc) rc = dev_alloc(pl, &pl->d_spec, (size_t)cfg->batch * cfg->nx * sp.nycp);
-  if (!rc) {
-    cudaError_t e2 = cudaMemset(pl->d_spec, 0, (size_t)cfg->batch * cfg->nx * sp.nycp * sizeof(float2));
-    if (e2 != cudaSuccess) { set_error(cudaGetErrorString(e2)); rc = MLSIM_ECUDA; }
+  if (!slab) {
+    // plain mode: the plan owns the RK workspaces and the spectral buffer(s); slab mode: the caller owns every
+    // exchanged buffer (halo-extended fields, spectral send/recv chunks), the plan only the split-transform buffer
+    if (!rc) rc = dev_alloc(pl, &pl->d_w1u, n);
+    if (!rc) rc = dev_alloc(pl, &pl->d_w1v, n);
+    if (!rc) rc = dev_alloc(pl, &pl->d_w2u, n);
+    if (!rc) rc = dev_alloc(pl, &pl->d_w2v, n);
+    if (!rc) rc = dev_alloc(pl, &pl->d_accu, n);
+    if (!rc) rc = dev_alloc(pl, &pl->d_accv, n);
+    const size_t ns = (size_t)cfg->batch * cfg->nx * sp.nycp;
+    if (!rc) rc = dev_alloc(pl, &pl->d_spec, ns);
+    if (!rc) {
+      cudaError_t e2 = cudaMemset(pl->d_spec, 0, ns * sizeof(float2));
+      if (e2 != cudaSuccess) { set_error(cudaGetErrorString(e2)); rc = MLSIM_ECUDA; }
+    }
+    if (!rc && pl->r0 > 1) rc = dev_alloc(pl, &pl->d_split, ns);
+  } else {
+    const size_t ns = (size_t)cfg->batch * cfg->nx * pl->kywp;
+    if (!rc) rc = dev_alloc(pl, &pl->d_split, ns);
+    if (!rc) {
+      cudaError_t e2 = cudaMemset(pl->d_split, 0, ns * sizeof(float2));
+      if (e2 != cudaSuccess) { set_error(cudaGetErrorString(e2)); rc = MLSIM_ECUDA; }
+    }
   }
   if (!rc) {
     cudaError_t e2 = cudaStreamCreateWithFlags(&pl->own_stream, cudaStreamNonBlocking);
@@ -328,7 +398,7 @@ int mlsim_plan_destroy(mlsim_plan* pl) {
   cudaSetDevice(pl->cfg.device);
   cudaDeviceSynchronize();
   void* ptrs[] = {pl->d_forcing, pl->d_inv_eig, pl->d_twx, pl->d_twy, pl->d_w1u, pl->d_w1v, pl->d_w2u, pl->d_w2v,
-                  pl->d_accu, pl->d_accv, pl->d_spec, pl->d_act[0], pl->d_act[1], pl->d_hu, pl->d_hv, pl->d_hp,
+                  pl->d_accu, pl->d_accv, pl->d_spec, pl->d_tw_n2, pl->d_split, pl->d_act[0], pl->d_act[1], pl->d_hu, pl->d_hv, pl->d_hp,
                   pl->d_tu, pl->d_tv, pl->d_dbg};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& l : pl->layers) if (l.d_wimg) cudaFree(l.d_wimg);
@@ -443,7 +513,8 @@ int mlsim_cnn_finalize(mlsim_plan* pl) {
   }
   if (!pl->d_act[0]) {
     const mlsim_config& c = pl->cfg;
-    pl->act_bytes = (size_t)c.batch * c.nx * 8 * (size_t)(c.ny + 2) * 16;
+    const int act_rows = pl->slab ? pl->nxl + 2 * MLSIM_SLAB_CNN_HALO : c.nx;
+    pl->act_bytes = (size_t)c.batch * act_rows * 8 * (size_t)(c.ny + 2) * 16;
     for (int i = 0; i < 2; ++i) {
       uint8_t* p = nullptr;
       int rc = dev_alloc(pl, &p, pl->act_bytes);
@@ -451,7 +522,7 @@ int mlsim_cnn_finalize(mlsim_plan* pl) {
       pl->d_act[i] = reinterpret_cast<__nv_bfloat16*>(p);
       MLSIM_CUDA_CHECK(cudaMemset(p, 0, pl->act_bytes));     // zero halo columns yp = 0 and yp = ny+1
     }
-    pl->rs = conv_pick_strip(c.nx, c.ny, c.batch, pl->sm_count);
+    pl->rs = conv_pick_strip(act_rows, c.ny, c.batch, pl->sm_count);
   }
   MLSIM_CUDA_CHECK(cudaDeviceSynchronize());
   pl->cnn_ready = true;
@@ -461,6 +532,7 @@ int mlsim_cnn_finalize(mlsim_plan* pl) {
 int mlsim_step(mlsim_plan* pl, float* u, float* v, float* p_or_null, int32_t nsteps, int32_t apply_cnn,
                double cnn_input_scale, void* stream) {
   if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_PLAIN_ONLY(pl);
   int rc;
   if ((rc = check_field(u, "u")) || (rc = check_field(v, "v"))) return rc;
   if (p_or_null && (rc = check_field(p_or_null, "p"))) return rc;
@@ -473,6 +545,7 @@ int mlsim_step(mlsim_plan* pl, float* u, float* v, float* p_or_null, int32_t nst
 int mlsim_rollout_host(mlsim_plan* pl, float* hu, float* hv, float* hp, int32_t nsteps, int32_t apply_cnn,
                        double cnn_input_scale) {
   if (!pl || !hu || !hv) { set_error("null argument"); return MLSIM_EINVAL; }
+  MLSIM_PLAIN_ONLY(pl);
   MLSIM_REQUIRE(nsteps >= 0, "nsteps must be >= 0");
   if (apply_cnn && !pl->cnn_ready) { set_error("apply_cnn set but the correction network is not finalised"); return MLSIM_ESTATE; }
   MLSIM_CUDA_CHECK(cudaSetDevice(pl->cfg.device));
@@ -516,6 +589,7 @@ int mlsim_rollout_host(mlsim_plan* pl, float* hu, float* hv, float* hp, int32_t 
 
 int mlsim_explicit_terms(mlsim_plan* pl, const float* u, const float* v, float* du, float* dv, void* stream) {
   if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_PLAIN_ONLY(pl);
   int rc;
   if ((rc = check_field(u, "u")) || (rc = check_field(v, "v")) || (rc = check_field(du, "du")) || (rc = check_field(dv, "dv"))) return rc;
   StageArgs a;
@@ -526,6 +600,7 @@ int mlsim_explicit_terms(mlsim_plan* pl, const float* u, const float* v, float* 
 
 int mlsim_project(mlsim_plan* pl, float* u, float* v, float* p_or_null, void* stream) {
   if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_PLAIN_ONLY(pl);
   int rc;
   if ((rc = check_field(u, "u")) || (rc = check_field(v, "v"))) return rc;
   return project(pl, u, v, p_or_null, reinterpret_cast<cudaStream_t>(stream), Chunk{0, pl->cfg.batch});
@@ -533,6 +608,7 @@ int mlsim_project(mlsim_plan* pl, float* u, float* v, float* p_or_null, void* st
 
 int mlsim_divergence(mlsim_plan* pl, const float* u, const float* v, float* d, void* stream) {
   if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_PLAIN_ONLY(pl);
   int rc;
   if ((rc = check_field(u, "u")) || (rc = check_field(v, "v")) || (rc = check_field(d, "div"))) return rc;
   return launch_divergence(u, v, d, pl->sp, reinterpret_cast<cudaStream_t>(stream));
@@ -540,6 +616,7 @@ int mlsim_divergence(mlsim_plan* pl, const float* u, const float* v, float* d, v
 
 int mlsim_cnn_forward(mlsim_plan* pl, const float* u, const float* v, float* y, double scale, void* stream) {
   if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_PLAIN_ONLY(pl);
   int rc;
   if ((rc = check_field(u, "u")) || (rc = check_field(v, "v")) || (rc = check_field(y, "y"))) return rc;
   return cnn_apply(pl, u, v, nullptr, nullptr, y, scale, reinterpret_cast<cudaStream_t>(stream), Chunk{0, pl->cfg.batch});
@@ -547,6 +624,7 @@ int mlsim_cnn_forward(mlsim_plan* pl, const float* u, const float* v, float* y, 
 
 int mlsim_cnn_correct(mlsim_plan* pl, float* u, float* v, double scale, void* stream) {
   if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_PLAIN_ONLY(pl);
   int rc;
   if ((rc = check_field(u, "u")) || (rc = check_field(v, "v"))) return rc;
   if (!pl->cnn_ready) { set_error("correction network not finalised"); return MLSIM_ESTATE; }
@@ -554,9 +632,134 @@ int mlsim_cnn_correct(mlsim_plan* pl, float* u, float* v, double scale, void* st
   return cnn_apply(pl, u, v, u, v, nullptr, scale, reinterpret_cast<cudaStream_t>(stream), Chunk{0, pl->cfg.batch});
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Slab decomposition along x (BASELINE config 5: one large grid over several GPUs).  The caller (one process per GPU)
+// owns every buffer that is exchanged and runs the exchanges itself (NCCL through torch.distributed, see slab.py):
+//   field pair  uv[2][batch][ext_rows][ny] fp32, ext_rows = nxl + 2*8: local row i lives at ext row i + 8
+//   forward  spectral chunks [world][batch][nxl  ][kywp] float2   (all-to-all: chunk r -> rank r)
+//   backward spectral chunks [world][batch][nxl+1][kywp] float2   (row nxl = x-halo of p-hat)
+// One RK stage =  halo exchange(us: 3 rows up, 2 rows down) -> stage_a -> all-to-all -> stage_b -> all-to-all -> stage_c.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct UV { float* u; float* v; };
+UV uv_origin(const mlsim_plan* pl, float* base) {
+  const size_t row0 = (size_t)MLSIM_SLAB_HALO * pl->cfg.ny;
+  return UV{base + row0, base + (size_t)pl->cfg.batch * pl->ext_rows * pl->cfg.ny + row0};
+}
+}  // namespace
+
+int mlsim_slab_geometry(mlsim_plan* pl, int64_t* out8) {
+  if (!pl || !out8) { set_error("null argument"); return MLSIM_EINVAL; }
+  MLSIM_SLAB_ONLY(pl);
+  out8[0] = pl->nxl; out8[1] = MLSIM_SLAB_HALO; out8[2] = pl->ext_rows; out8[3] = pl->kyw; out8[4] = pl->kywp;
+  out8[5] = pl->kyv; out8[6] = pl->r0; out8[7] = MLSIM_SLAB_CNN_HALO;
+  return MLSIM_OK;
+}
+
+int mlsim_slab_stage_a(mlsim_plan* pl, int32_t stage, const float* us, const float* u0, float* acc, float* out,
+                       void* spec_send, void* stream) {
+  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_SLAB_ONLY(pl);
+  MLSIM_REQUIRE(stage >= 0 && stage <= 3, "stage must be 0..3");
+  int rc;
+  if ((rc = check_field(us, "us")) || (rc = check_field(u0, "u0")) || (rc = check_field(acc, "acc")) ||
+      (rc = check_field(out, "out")) || (rc = check_field(spec_send, "spec_send"))) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const float dt = (float)pl->cfg.dt;
+  const UV s = uv_origin(pl, const_cast<float*>(us)), b = uv_origin(pl, const_cast<float*>(u0)), a = uv_origin(pl, acc),
+           o = uv_origin(pl, out);
+  StageArgs g;
+  g.us = s.u; g.vs = s.v; g.u0 = b.u; g.v0 = b.v; g.accu = a.u; g.accv = a.v; g.outu = o.u; g.outv = o.v;
+  switch (stage) {                                   // coefficients as in solver_step()
+    case 0: g.ca = dt / 6.0f; g.cs = 0.5f * dt; g.mode = 1; break;
+    case 1: g.ca = dt / 3.0f; g.cs = 0.5f * dt; g.mode = 2; break;
+    case 2: g.ca = dt / 3.0f; g.cs = dt; g.mode = 2; break;
+    default: g.ca = 0.0f; g.cs = dt / 6.0f; g.mode = 3; break;
+  }
+  { ProfScope ps(pl, 0, st); if ((rc = launch_explicit(g, pl->sp, pl->d_forcing, st))) return rc; }
+  ProfScope ps(pl, 1, st);
+  return launch_div_rfft(o.u, o.v, static_cast<float2*>(spec_send), pl->d_twy, pl->sp, st);
+}
+
+int mlsim_slab_divergence_rfft(mlsim_plan* pl, const float* uv, void* spec_send, void* stream) {
+  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_SLAB_ONLY(pl);
+  int rc;
+  if ((rc = check_field(uv, "uv")) || (rc = check_field(spec_send, "spec_send"))) return rc;
+  const UV o = uv_origin(pl, const_cast<float*>(uv));
+  return launch_div_rfft(o.u, o.v, static_cast<float2*>(spec_send), pl->d_twy, pl->sp, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mlsim_slab_stage_b(mlsim_plan* pl, const void* spec_recv, void* spec_send2, void* stream) {
+  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_SLAB_ONLY(pl);
+  int rc;
+  if ((rc = check_field(spec_recv, "spec_recv")) || (rc = check_field(spec_send2, "spec_send2"))) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ProfScope ps(pl, 2, st);
+  return launch_col_solve_slab(static_cast<const float2*>(spec_recv), static_cast<float2*>(spec_send2), pl->d_split,
+                               pl->d_inv_eig, pl->d_twx, pl->d_tw_n2, pl->sp, pl->nxg, pl->cfg.slab_world, pl->kyv,
+                               pl->r0, st);
+}
+
+int mlsim_slab_stage_c(mlsim_plan* pl, const void* spec_recv2, float* uv, float* p_or_null, void* stream) {
+  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_SLAB_ONLY(pl);
+  int rc;
+  if ((rc = check_field(spec_recv2, "spec_recv2")) || (rc = check_field(uv, "uv"))) return rc;
+  if (p_or_null && (rc = check_field(p_or_null, "p"))) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const UV o = uv_origin(pl, uv);
+  ProfScope ps(pl, 3, st);
+  return launch_irfft_grad(static_cast<const float2*>(spec_recv2), o.u, o.v, o.u, o.v, p_or_null, pl->d_twy, pl->sp, st);
+}
+
+// v += model(v) on the slab.  The CNN pads with ZEROS at the edges of the global grid (Conv2d padding=1, reference
+// src/models/tools.py), so it is not periodic: the 7 conv layers need 7 rows of state from each interior neighbour
+// (halo rows [-7, 0) and [nxl, nxl+7) must be current), the network runs on rows [lo, hi) = the slab plus those
+// halos (the outermost l rows of layer l's output are contaminated by the artificial edge and never reach local rows).
+int mlsim_slab_cnn_correct(mlsim_plan* pl, float* uv, double scale, void* stream) {
+  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_SLAB_ONLY(pl);
+  int rc;
+  if ((rc = check_field(uv, "uv"))) return rc;
+  if (!pl->cnn_ready) { set_error("correction network not finalised"); return MLSIM_ESTATE; }
+  MLSIM_REQUIRE(pl->layers.back().cout == 2, "the fused correction add needs a 2-channel output (u, v)");
+  MLSIM_REQUIRE((int)pl->layers.size() <= MLSIM_SLAB_CNN_HALO, "slab mode supports at most 7 conv layers (halo depth)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const mlsim_config& c = pl->cfg;
+  const int W = c.slab_world, r = c.slab_rank;
+  const int lo = (r == 0) ? 0 : -MLSIM_SLAB_CNN_HALO;
+  const int hi = pl->nxl + ((r == W - 1) ? 0 : MLSIM_SLAB_CNN_HALO);
+  const int rows = hi - lo;
+  const UV o = uv_origin(pl, uv);
+  float* u = o.u + (ptrdiff_t)lo * c.ny;
+  float* v = o.v + (ptrdiff_t)lo * c.ny;
+  const int L = (int)pl->layers.size();
+  ConvFirstArgs f;
+  f.u = u; f.v = v; f.out = pl->d_act[0]; f.wimg = pl->layers[0].d_wimg; f.scale = (float)scale;
+  f.nx = rows; f.ny = c.ny; f.batch = c.batch; f.reverse = 0; f.img_stride = pl->sp.img_stride;
+  { ProfScope ps(pl, 4, st); if ((rc = launch_conv_first(f, pl->sm_count, st))) return rc; }
+  int cur = 0;
+  for (int l = 1; l < L; ++l) {
+    ConvMidArgs m;
+    m.in = pl->d_act[cur]; m.out = pl->d_act[cur ^ 1];
+    m.u = u; m.v = v; m.y_nchw = nullptr;
+    m.wimg = pl->layers[l].d_wimg;
+    m.nx = rows; m.ny = c.ny; m.batch = c.batch; m.rs = pl->rs; m.img_stride = pl->sp.img_stride;
+    m.cout = pl->layers[l].cout; m.relu = pl->layers[l].relu; m.dbg = nullptr;
+    m.reverse = l & 1;
+    if (l < L - 1) { ProfScope ps(pl, 5, st); if ((rc = launch_conv_mid(m, pl->sm_count, st))) return rc; }
+    else { ProfScope ps(pl, 6, st); if ((rc = launch_conv_last(m, pl->sm_count, st))) return rc; }
+    cur ^= 1;
+  }
+  return MLSIM_OK;
+}
+
 int mlsim_launches_per_step(mlsim_plan* pl, int32_t apply_cnn) {
   if (!pl) return MLSIM_EINVAL;
   int n = pl->cluster_projection ? 8 : 16;   // 4 stages x (explicit + cluster projection | explicit, div+rfft, column solve, irfft+grad)
+  if (pl->slab || pl->r0 > 1) n = 4 * 6;     // split x-transform: explicit, div+rfft, pass A, column solve, pass C, irfft+grad
   if (apply_cnn && pl->cnn_ready) n += (int)pl->layers.size();
   return n;
 }
@@ -610,6 +813,7 @@ int mlsim_profile_read(mlsim_plan* pl, float* total_ms, int32_t* count) {
 
 int mlsim_time_kernel(mlsim_plan* pl, int32_t which, int32_t warmup, int32_t iters, float* ms_out, void* stream) {
   if (!pl || !ms_out) { set_error("null argument"); return MLSIM_EINVAL; }
+  MLSIM_PLAIN_ONLY(pl);
   MLSIM_REQUIRE(which >= 0 && which <= 7 && iters >= 1 && warmup >= 0, "bad arguments");
   if (which == 7 && !pl->cluster_projection) { set_error("cluster projection not available for this grid"); return MLSIM_EINVAL; }
   if (which >= 4 && !pl->cnn_ready) { set_error("correction network not finalised"); return MLSIM_ESTATE; }
@@ -634,12 +838,14 @@ int mlsim_time_kernel(mlsim_plan* pl, int32_t which, int32_t warmup, int32_t ite
       }
       case 7: return launch_project_cluster(pl->d_w1u, pl->d_w1v, nullptr, pl->d_inv_eig, pl->d_twy, pl->sp, st);
       case 1: return launch_div_rfft(pl->d_tu, pl->d_tv, pl->d_spec, pl->d_twy, pl->sp, st);
-      case 2: return launch_col_solve(pl->d_spec, pl->d_inv_eig, pl->d_twx, pl->sp, st);
+      case 2:
+        if (pl->r0 == 1) return launch_col_solve(pl->d_spec, pl->d_inv_eig, pl->d_twx, pl->sp, pl->sp.nx, pl->sp.batch, 1, st);
+        return launch_col_solve_split(pl->d_spec, pl->d_split, pl->d_inv_eig, pl->d_twx, pl->d_tw_n2, pl->sp, pl->r0, st);
       case 3: return launch_irfft_grad(pl->d_spec, pl->d_tu, pl->d_tv, pl->d_w1u, pl->d_w1v, nullptr, pl->d_twy, pl->sp, st);
       case 4: {
         ConvFirstArgs f;
         f.u = pl->d_tu; f.v = pl->d_tv; f.out = pl->d_act[0]; f.wimg = pl->layers[0].d_wimg; f.scale = 1.0f;
-        f.nx = c.nx; f.ny = c.ny; f.batch = c.batch; f.reverse = 0;
+        f.nx = c.nx; f.ny = c.ny; f.batch = c.batch; f.reverse = 0; f.img_stride = (long long)c.nx * c.ny;
         return launch_conv_first(f, pl->sm_count, st);
       }
       default: {
@@ -649,6 +855,7 @@ int mlsim_time_kernel(mlsim_plan* pl, int32_t which, int32_t warmup, int32_t ite
         ConvMidArgs m;
         m.in = pl->d_act[0]; m.out = pl->d_act[1]; m.u = pl->d_w1u; m.v = pl->d_w1v; m.y_nchw = nullptr;
         m.wimg = pl->layers[l].d_wimg; m.nx = c.nx; m.ny = c.ny; m.batch = c.batch; m.rs = pl->rs;
+        m.img_stride = (long long)c.nx * c.ny;
         m.cout = pl->layers[l].cout; m.relu = pl->layers[l].relu; m.dbg = pl->d_dbg; m.reverse = 0;
         return (which == 5) ? launch_conv_mid(m, pl->sm_count, st) : launch_conv_last(m, pl->sm_count, st);
       }

@@ -42,7 +42,10 @@ __device__ __forceinline__ float face_flux(float cl, float c, float cr, float cr
   return fmaf(t * phi, d, low) * w;
 }
 
-template <int TY, int ADV>
+// SLAB (x-slab decomposition): no periodic wrap in x; the tile rows come from the halo-extended buffers (row index
+// clamped to the valid rows [-halo, nx+halo)), and one extra leading tile (blockIdx.y == 0 <-> rows [-32, 0)) computes
+// output row -1 -- the x-halo of u* that the divergence of the local row 0 needs -- so no second exchange is required.
+template <int TY, int ADV, bool SLAB>
 __global__ void __launch_bounds__(K1_THREADS, 3)
 k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
   constexpr int NTY = TY / 4;                 // threads along y
@@ -55,9 +58,9 @@ k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
   float* sv = su + SH * SW;
 
   const int b = blockIdx.z;
-  const int i0 = blockIdx.y * K1_TX;
+  const int i0 = SLAB ? ((int)blockIdx.y - 1) * K1_TX : blockIdx.y * K1_TX;
   const int j0 = blockIdx.x * TY;
-  const size_t img = (size_t)b * p.nx * p.ny;
+  const ptrdiff_t img = (ptrdiff_t)b * p.img_stride;
   const float* __restrict__ gu = a.us + img;
   const float* __restrict__ gv = a.vs + img;
 
@@ -66,10 +69,10 @@ k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
   const int ny4 = p.ny >> 2;
   for (int idx = threadIdx.x; idx < SH * W4; idx += K1_THREADS) {
     const int r = idx / W4, c4 = idx - r * W4;
-    const int gi = (i0 - K1_HALO + r) & (p.nx - 1);
+    const int gi = SLAB ? max(-p.halo, min(i0 - K1_HALO + r, p.nx + p.halo - 1)) : ((i0 - K1_HALO + r) & (p.nx - 1));
     const int gc = ((j0 >> 2) - 1 + c4) & (ny4 - 1);
-    const float4 vu = __ldg(reinterpret_cast<const float4*>(gu + (size_t)gi * p.ny) + gc);
-    const float4 vv = __ldg(reinterpret_cast<const float4*>(gv + (size_t)gi * p.ny) + gc);
+    const float4 vu = __ldg(reinterpret_cast<const float4*>(gu + (ptrdiff_t)gi * p.ny) + gc);
+    const float4 vv = __ldg(reinterpret_cast<const float4*>(gv + (ptrdiff_t)gi * p.ny) + gc);
     reinterpret_cast<float4*>(su + r * SW)[c4] = vu;
     reinterpret_cast<float4*>(sv + r * SW)[c4] = vv;
   }
@@ -105,13 +108,14 @@ k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
   for (int rr = 0; rr < RPG; ++rr) {
     const int i = li0 + rr;
     // issue this row's RK operand loads first so their latency hides behind the flux arithmetic
-    const size_t off = img + (size_t)(i0 + (i - K1_HALO)) * p.ny + (j0 + 4 * ty);
+    const ptrdiff_t off = img + (ptrdiff_t)(i0 + (i - K1_HALO)) * p.ny + (j0 + 4 * ty);
+    const bool live = !SLAB || (i0 + (i - K1_HALO) >= -1);     // slab: the leading tile only produces row -1
     float4 bu = make_float4(0.f, 0.f, 0.f, 0.f), bv = bu, au = bu, av = bu;
-    if (a.mode == 2) {
+    if (live && a.mode == 2) {
       bu = __ldg(reinterpret_cast<const float4*>(a.u0 + off));
       bv = __ldg(reinterpret_cast<const float4*>(a.v0 + off));
     }
-    if (a.mode >= 2) {
+    if (live && a.mode >= 2) {
       au = *reinterpret_cast<const float4*>(a.accu + off);
       av = *reinterpret_cast<const float4*>(a.accv + off);
     }
@@ -148,6 +152,7 @@ k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
       fxu_prev[k] = fxu[k];
       fxv_prev[k] = fxv[k];
     }
+    if (!live) continue;
     // ---- RK combine + float4 I/O (the u0 / acc loads were issued at the top of the row) ----
     float4 ou, ov;
     if (a.mode == 0) {
@@ -177,25 +182,29 @@ k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
 #undef SV
 }
 
-template <int TY, int ADV>
+template <int TY, int ADV, bool SLAB>
 static int launch_explicit_ty(const StageArgs& a, const SolverParams& p, const float* forcing, cudaStream_t st) {
   constexpr int SW = TY + 8, SH = K1_TX + 2 * K1_HALO;
   const size_t smem = (size_t)2 * SH * SW * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
-    MLSIM_CUDA_CHECK(cudaFuncSetAttribute(k_explicit_rk<TY, ADV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MLSIM_CUDA_CHECK(cudaFuncSetAttribute(k_explicit_rk<TY, ADV, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  dim3 grid(p.ny / TY, p.nx / K1_TX, p.batch);
-  k_explicit_rk<TY, ADV><<<grid, K1_THREADS, smem, st>>>(a, p, forcing);
+  dim3 grid(p.ny / TY, p.nx / K1_TX + (SLAB ? 1 : 0), p.batch);
+  k_explicit_rk<TY, ADV, SLAB><<<grid, K1_THREADS, smem, st>>>(a, p, forcing);
   MLSIM_CUDA_CHECK(cudaGetLastError());
   return MLSIM_OK;
 }
 
 template <int ADV>
 static int launch_explicit_adv(const StageArgs& a, const SolverParams& p, const float* forcing, cudaStream_t st) {
-  if (p.ny >= 128) return launch_explicit_ty<128, ADV>(a, p, forcing, st);
-  return launch_explicit_ty<64, ADV>(a, p, forcing, st);
+  if (p.halo > 0) {
+    if (p.ny >= 128) return launch_explicit_ty<128, ADV, true>(a, p, forcing, st);
+    return launch_explicit_ty<64, ADV, true>(a, p, forcing, st);
+  }
+  if (p.ny >= 128) return launch_explicit_ty<128, ADV, false>(a, p, forcing, st);
+  return launch_explicit_ty<64, ADV, false>(a, p, forcing, st);
 }
 
 int launch_explicit(const StageArgs& a, const SolverParams& p, const float* forcing, cudaStream_t st) {
@@ -229,59 +238,73 @@ int launch_divergence(const float* u, const float* v, float* d, const SolverPara
 }
 
 // ---------------------------------------------------------------------------------------------
+// Spectral buffer addressing.
+//   plain:  S[b][x][nycp]                                   (x in [0, nx), all nyc columns)
+//   slab :  the half spectrum is cut into `world` column chunks of kyw columns (pitch kywp) so that one
+//           all-to-all moves chunk r to rank r:   S[r][b][x_local][kywp]  with `rows` = nxl (forward) or nxl+1
+//           (backward: local row nxl is the x-halo of p-hat, i.e. row 0 of the next rank's slab).
+// ---------------------------------------------------------------------------------------------
+template <bool SLAB>
+__device__ __forceinline__ size_t spec_off(const SolverParams& p, int b, int row, int k, int rows) {
+  if constexpr (!SLAB) {
+    return ((size_t)b * p.nx + row) * p.nycp + k;
+  } else {
+    const int r = k / p.kyw, kl = k - r * p.kyw;
+    return (((size_t)r * p.batch + b) * rows + row) * p.kywp + kl;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K2: divergence of (u*, v*) for 2Q rows, packed as Q complex lines (row 2q -> re, row 2q+1 -> im),
 // forward FFT along y in shared memory, untangle to the two half spectra, store nyc columns per row.
+// SLAB: fields are halo-extended (row -1 is the lower neighbour's last row, no wrap in x).
 // ---------------------------------------------------------------------------------------------
 template <int N> struct RowCfg {
   // lines per CTA such that Q*N/Rmin <= 1024 threads
   static constexpr int RMIN = FftMinRadix<N>::value;
-  static constexpr int Q = (N <= 256) ? 16 : (N <= 1024 ? 8 : 4);
+  static constexpr int Q = (N <= 256) ? 16 : (N <= 1024 ? 8 : (N <= 2048 ? 4 : (N <= 4096 ? 2 : 1)));
   static constexpr int THREADS = Q * N / RMIN;
-  static constexpr int LS = Q + 1;
-  static constexpr size_t SMEM = (size_t)N * LS * sizeof(float2);
+  static constexpr size_t SMEM = fft_buf_elems<N, Q>() * sizeof(float2);
 };
 
-template <int N>
+template <int N, bool SLAB>
 __global__ void __launch_bounds__(RowCfg<N>::THREADS)
 k_div_rfft(const float* __restrict__ u, const float* __restrict__ v, float2* __restrict__ S,
            const float2* __restrict__ tw, SolverParams p) {
-  using P = FftPlan<N>;
   using C = RowCfg<N>;
-  constexpr int Q = C::Q, LS = C::LS, NT = C::THREADS;
+  constexpr int Q = C::Q, NT = C::THREADS;
   extern __shared__ float4 smem4[];
   float2* buf = reinterpret_cast<float2*>(smem4);
 
   const int b = blockIdx.y;
   const int i0 = blockIdx.x * (2 * Q);
-  const size_t img = (size_t)b * p.nx * N;
-  const float* __restrict__ gu = u + img;
-  const float* __restrict__ gv = v + img;
+  const float* __restrict__ gu = u + (ptrdiff_t)b * p.img_stride;
+  const float* __restrict__ gv = v + (ptrdiff_t)b * p.img_stride;
 
   for (int idx = threadIdx.x; idx < 2 * Q * N; idx += NT) {
     const int r = idx / N, j = idx - r * N;
     const int i = i0 + r;
-    const int im = (i - 1) & (p.nx - 1), jm = (j - 1) & (N - 1);
-    const float d = (gu[(size_t)i * N + j] - gu[(size_t)im * N + j]) * p.inv_hx +
-                    (gv[(size_t)i * N + j] - gv[(size_t)i * N + jm]) * p.inv_hy;
-    reinterpret_cast<float*>(&buf[j * LS + (r >> 1)])[r & 1] = d;
+    const int im = SLAB ? (i - 1) : ((i - 1) & (p.nx - 1));
+    const int jm = (j - 1) & (N - 1);
+    const float d = (gu[(ptrdiff_t)i * N + j] - gu[(ptrdiff_t)im * N + j]) * p.inv_hx +
+                    (gv[(ptrdiff_t)i * N + j] - gv[(ptrdiff_t)i * N + jm]) * p.inv_hy;
+    reinterpret_cast<float*>(&buf[fidx<Q>(j, r >> 1)])[r & 1] = d;
   }
   __syncthreads();
 
   const int c = threadIdx.x % Q, j = threadIdx.x / Q;
-  stage_smem<N, P::R1, 1, -1>(buf, LS, c, j, true, tw);
-  stage_smem<N, P::R2, P::R1, -1>(buf, LS, c, j, true, tw);
-  if constexpr (P::R3 > 1) stage_smem<N, P::R3, P::R1 * P::R2, -1>(buf, LS, c, j, true, tw);
+  fft_lines_forward<N, Q>(buf, c, j, tw);
 
-  const int nyc = N / 2 + 1;
+  constexpr int nyc = N / 2 + 1;
   for (int idx = threadIdx.x; idx < Q * nyc; idx += NT) {
     const int q = idx / nyc, k = idx - q * nyc;
-    const float2 z = buf[k * LS + q];
-    const float2 zm = buf[((N - k) & (N - 1)) * LS + q];
+    const float2 z = buf[fidx<Q>(k, q)];
+    const float2 zm = buf[fidx<Q>((N - k) & (N - 1), q)];
     const float2 A = make_float2(0.5f * (z.x + zm.x), 0.5f * (z.y - zm.y));
     const float2 B = make_float2(0.5f * (z.y + zm.y), -0.5f * (z.x - zm.x));
-    const size_t row = (size_t)b * p.nx + i0 + 2 * q;
-    S[row * p.nycp + k] = A;
-    S[(row + 1) * p.nycp + k] = B;
+    const size_t o = spec_off<SLAB>(p, b, i0 + 2 * q, k, p.nx);
+    S[o] = A;
+    S[o + (SLAB ? p.kywp : p.nycp)] = B;
   }
 }
 
@@ -289,58 +312,52 @@ k_div_rfft(const float* __restrict__ u, const float* __restrict__ v, float2* __r
 // K4: rebuild Q complex lines from 2Q rows of p-hat, inverse FFT along y, then
 //     u -= d+x p, v -= d+y p  for the first 2Q-1 rows (the last row is the x-halo of p).
 // ---------------------------------------------------------------------------------------------
-template <int N>
+template <int N, bool SLAB>
 __global__ void __launch_bounds__(RowCfg<N>::THREADS)
 k_irfft_grad(const float2* __restrict__ S, const float* __restrict__ uin, const float* __restrict__ vin,
              float* __restrict__ uout, float* __restrict__ vout, float* __restrict__ pout,
              const float2* __restrict__ tw, SolverParams p) {
-  using P = FftPlan<N>;
   using C = RowCfg<N>;
-  constexpr int Q = C::Q, LS = C::LS, NT = C::THREADS;
+  constexpr int Q = C::Q, NT = C::THREADS;
   extern __shared__ float4 smem4[];
   float2* buf = reinterpret_cast<float2*>(smem4);
 
   const int b = blockIdx.y;
   const int i0 = blockIdx.x * (2 * Q - 1);
-  const int nyc = N / 2 + 1;
+  constexpr int nyc = N / 2 + 1;
 
   for (int idx = threadIdx.x; idx < Q * nyc; idx += NT) {
     const int q = idx / nyc, k = idx - q * nyc;
-    const int ia = (i0 + 2 * q) & (p.nx - 1), ib = (i0 + 2 * q + 1) & (p.nx - 1);
-    const float2 A = __ldg(&S[((size_t)b * p.nx + ia) * p.nycp + k]);
-    const float2 B = __ldg(&S[((size_t)b * p.nx + ib) * p.nycp + k]);
+    // plain: periodic wrap; slab: the spectral rows are [0, nx] (row nx = halo), rows past it are never used
+    const int ia = SLAB ? min(i0 + 2 * q, p.nx) : ((i0 + 2 * q) & (p.nx - 1));
+    const int ib = SLAB ? min(i0 + 2 * q + 1, p.nx) : ((i0 + 2 * q + 1) & (p.nx - 1));
+    const float2 A = __ldg(&S[spec_off<SLAB>(p, b, ia, k, p.nx + 1)]);
+    const float2 B = __ldg(&S[spec_off<SLAB>(p, b, ib, k, p.nx + 1)]);
     if (k == 0 || k == N / 2) {
-      buf[k * LS + q] = make_float2(A.x, B.x);          // c2r ignores Im of DC / Nyquist
+      buf[fidx<Q>(k, q)] = make_float2(A.x, B.x);          // c2r ignores Im of DC / Nyquist
     } else {
-      buf[k * LS + q] = make_float2(A.x - B.y, A.y + B.x);
-      buf[(N - k) * LS + q] = make_float2(A.x + B.y, B.x - A.y);
+      buf[fidx<Q>(k, q)] = make_float2(A.x - B.y, A.y + B.x);
+      buf[fidx<Q>(N - k, q)] = make_float2(A.x + B.y, B.x - A.y);
     }
   }
   __syncthreads();
 
   const int c = threadIdx.x % Q, j = threadIdx.x / Q;
-  // inverse radix order (R3,R2,R1) mirrors the column kernel; any order is valid
-  if constexpr (P::R3 > 1) {
-    stage_smem<N, P::R3, 1, +1>(buf, LS, c, j, true, tw);
-    stage_smem<N, P::R2, P::R3, +1>(buf, LS, c, j, true, tw);
-    stage_smem<N, P::R1, P::R3 * P::R2, +1>(buf, LS, c, j, true, tw);
-  } else {
-    stage_smem<N, P::R2, 1, +1>(buf, LS, c, j, true, tw);
-    stage_smem<N, P::R1, P::R2, +1>(buf, LS, c, j, true, tw);
-  }
+  fft_lines_inverse<N, Q>(buf, c, j, tw);
 
-  const size_t img = (size_t)b * p.nx * N;
-  for (int idx = threadIdx.x; idx < (2 * Q - 1) * N; idx += NT) {
+  const ptrdiff_t img = (ptrdiff_t)b * p.img_stride;
+  constexpr int NROWS = (2 * Q - 1 > 0) ? 2 * Q - 1 : 1;
+  for (int idx = threadIdx.x; idx < NROWS * N; idx += NT) {
     const int r = idx / N, y = idx - r * N;
     const int i = i0 + r;
     if (i >= p.nx) break;
-    const float p0 = reinterpret_cast<const float*>(&buf[y * LS + (r >> 1)])[r & 1];
-    const float pxp = reinterpret_cast<const float*>(&buf[y * LS + ((r + 1) >> 1)])[(r + 1) & 1];
-    const float pyp = reinterpret_cast<const float*>(&buf[((y + 1) & (N - 1)) * LS + (r >> 1)])[r & 1];
-    const size_t off = img + (size_t)i * N + y;
+    const float p0 = reinterpret_cast<const float*>(&buf[fidx<Q>(y, r >> 1)])[r & 1];
+    const float pxp = reinterpret_cast<const float*>(&buf[fidx<Q>(y, (r + 1) >> 1)])[(r + 1) & 1];
+    const float pyp = reinterpret_cast<const float*>(&buf[fidx<Q>((y + 1) & (N - 1), r >> 1)])[r & 1];
+    const ptrdiff_t off = img + (ptrdiff_t)i * N + y;
     uout[off] = uin[off] - (pxp - p0) * p.inv_hx;
     vout[off] = vin[off] - (pyp - p0) * p.inv_hy;
-    if (pout) pout[off] = p0;
+    if (pout) pout[((size_t)b * p.nx + i) * N + y] = p0;
   }
 }
 
@@ -348,24 +365,26 @@ k_irfft_grad(const float2* __restrict__ S, const float* __restrict__ uin, const 
 // K3: for C adjacent ky columns: FFT along x, multiply by inv_eig (includes 1/(nx*ny)), iFFT along x.
 // First stage loads straight from global, last stage stores straight to global, and the last forward
 // stage hands its registers to the first inverse stage (same thread owns the same points).
+// Works on a plain [image][N][nycp] buffer; image `img` uses table image img % eig_images (the split x-transform
+// of long / distributed grids runs R0 sub-transforms per image, each with its own slice of the spectrum).
 // ---------------------------------------------------------------------------------------------
 template <int N> struct ColCfg {
   static constexpr int RMIN = FftMinRadix<N>::value;
   static constexpr int C = (N <= 512) ? 16 : (N <= 1024 ? 8 : 4);
   static constexpr int THREADS = C * N / RMIN;
-  static constexpr int LS = C + 1;
-  static constexpr size_t SMEM = (size_t)N * LS * sizeof(float2);
+  static constexpr size_t SMEM = fft_buf_elems<N, C>() * sizeof(float2);
 };
 
 template <int N>
 __global__ void __launch_bounds__(ColCfg<N>::THREADS)
 k_col_solve(float2* __restrict__ S, const float* __restrict__ inv_eig, const float2* __restrict__ tw,
-            SolverParams p) {
+            SolverParams p, int eig_images) {
   using P = FftPlan<N>;
   using CC = ColCfg<N>;
-  constexpr int C = CC::C, LS = CC::LS;
+  constexpr int C = CC::C;
   constexpr int RL = (P::R3 > 1) ? P::R3 : P::R2;        // radix of the last forward stage
   constexpr int NSL = N / RL;                            // its Ns
+  static_assert(P::R4 == 1, "column transforms longer than 2048 go through the split passes");
   extern __shared__ float4 smem4[];
   float2* buf = reinterpret_cast<float2*>(smem4);
 
@@ -373,6 +392,7 @@ k_col_solve(float2* __restrict__ S, const float* __restrict__ inv_eig, const flo
   const int ky = blockIdx.x * C + c;
   const bool valid = ky < p.nyc;
   float2* base = S + (size_t)blockIdx.y * N * p.nycp + ky;
+  const float* __restrict__ eig = inv_eig + (size_t)(blockIdx.y % eig_images) * N * p.nyc;
 
   // forward stage 1: global -> registers -> smem
   {
@@ -384,11 +404,11 @@ k_col_solve(float2* __restrict__ S, const float* __restrict__ inv_eig, const flo
         v[r] = valid ? base[(size_t)(j + r * (N / R)) * p.nycp] : make_float2(0.f, 0.f);
       dft_regs<R, -1>(v);
 #pragma unroll
-      for (int q = 0; q < R; ++q) buf[(j * R + q) * LS + c] = v[q];
+      for (int q = 0; q < R; ++q) buf[fidx<C>(j * R + q, c)] = v[q];
     }
     __syncthreads();
   }
-  if constexpr (P::R3 > 1) stage_smem<N, P::R2, P::R1, -1>(buf, LS, c, j, true, tw);
+  if constexpr (P::R3 > 1) stage_smem<N, P::R2, P::R1, -1, C>(buf, c, j, true, tw);
 
   // last forward stage -> scale -> first inverse stage, all in registers
   {
@@ -396,7 +416,7 @@ k_col_solve(float2* __restrict__ S, const float* __restrict__ inv_eig, const flo
     const bool on = j < N / RL;
     if (on) {
 #pragma unroll
-      for (int r = 0; r < RL; ++r) v[r] = buf[(j + r * NSL) * LS + c];
+      for (int r = 0; r < RL; ++r) v[r] = buf[fidx<C>(j + r * NSL, c)];
     }
     __syncthreads();
     if (on) {
@@ -404,17 +424,17 @@ k_col_solve(float2* __restrict__ S, const float* __restrict__ inv_eig, const flo
       dft_regs<RL, -1>(v);                                // X[kx = j + q*NSL]
 #pragma unroll
       for (int q = 0; q < RL; ++q) {
-        const float s = valid ? __ldg(&inv_eig[(size_t)(j + q * NSL) * p.nyc + ky]) : 0.f;
+        const float s = valid ? __ldg(&eig[(size_t)(j + q * NSL) * p.nyc + ky]) : 0.f;
         v[q].x *= s;
         v[q].y *= s;
       }
       dft_regs<RL, +1>(v);                                // inverse stage 1: Ns = 1, no twiddle
 #pragma unroll
-      for (int q = 0; q < RL; ++q) buf[(j * RL + q) * LS + c] = v[q];
+      for (int q = 0; q < RL; ++q) buf[fidx<C>(j * RL + q, c)] = v[q];
     }
     __syncthreads();
   }
-  if constexpr (P::R3 > 1) stage_smem<N, P::R2, P::R3, +1>(buf, LS, c, j, true, tw);
+  if constexpr (P::R3 > 1) stage_smem<N, P::R2, P::R3, +1, C>(buf, c, j, true, tw);
 
   // last inverse stage: smem -> registers -> global
   {
@@ -423,13 +443,86 @@ k_col_solve(float2* __restrict__ S, const float* __restrict__ inv_eig, const flo
     if (j < N / R) {
       float2 v[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) v[r] = buf[(j + r * (N / R)) * LS + c];
+      for (int r = 0; r < R; ++r) v[r] = buf[fidx<C>(j + r * (N / R), c)];
       stage_twiddle<N, R, NS, +1>(v, j, tw);
       dft_regs<R, +1>(v);
       if (valid) {
 #pragma unroll
         for (int q = 0; q < R; ++q) base[(size_t)(j + q * NS) * p.nycp] = v[q];
       }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Split x-transform (four-step FFT with an outer radix R0 done through global memory) for grids whose x extent is
+// longer than one shared-memory column transform (nx > 2048) or distributed over ranks (slab decomposition):
+//   nx = R0 * N2,  x = N2*n1 + n2,  kx = k1 + R0*k2.
+//   pass A:  T[b][k1][n2][ky] = w^(n2*k1) * sum_n1 S[b][N2*n1 + n2][ky] e^{-2 pi i n1 k1 / R0},   w = e^{-2 pi i / nx}
+//   K3    :  length-N2 transform over n2 of every (b, k1) image, times inv_eig[k1 + R0*k2][ky], inverse transform
+//   pass C:  S'[b][N2*n1 + n2][ky] = sum_k1 conj(w)^(n2*k1) T[b][k1][n2][ky] e^{+2 pi i n1 k1 / R0}
+// Both passes are elementwise over (b, n2, ky), coalesced along ky.  With R0 == 1 they are plain re-layouts
+// (slab mode: gather the per-rank row chunks into T, scatter T into the backward chunks with the duplicated halo row).
+// ---------------------------------------------------------------------------------------------
+struct RowMap {          // element offset of (b, x, ky) = (x >> sh)*chunk_stride + b*img_stride + (x & mask)*pitch + ky
+  int sh, mask, pitch;
+  long long chunk_stride, img_stride;
+  int dup_row;           // >= 0: rows with (x & mask) == 0 are also stored at local row dup_row of the previous chunk
+  int nchunks;
+};
+__device__ __forceinline__ size_t rowmap_off(const RowMap& m, int b, int x, int ky) {
+  return (size_t)(x >> m.sh) * m.chunk_stride + (size_t)b * m.img_stride + (size_t)(x & m.mask) * m.pitch + ky;
+}
+
+template <int R0>
+__global__ void __launch_bounds__(128)
+k_xsplit_fwd(const float2* __restrict__ S, RowMap m, float2* __restrict__ T, const float2* __restrict__ twx, int n2len,
+             int pitch_t) {
+  const int ky = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ky >= pitch_t) return;
+  const int n2 = blockIdx.y, b = blockIdx.z;
+  float2 v[R0];
+#pragma unroll
+  for (int n1 = 0; n1 < R0; ++n1) v[n1] = __ldg(&S[rowmap_off(m, b, n1 * n2len + n2, ky)]);
+  if constexpr (R0 > 1) {
+    dft_regs<R0, -1>(v);
+#pragma unroll
+    for (int k1 = 1; k1 < R0; ++k1) {
+      const float2 w = __ldg(&twx[n2 * k1]);
+      const float2 x = v[k1];
+      v[k1] = make_float2(x.x * w.x - x.y * w.y, x.x * w.y + x.y * w.x);
+    }
+  }
+#pragma unroll
+  for (int k1 = 0; k1 < R0; ++k1) T[(((size_t)b * R0 + k1) * n2len + n2) * pitch_t + ky] = v[k1];
+}
+
+template <int R0>
+__global__ void __launch_bounds__(128)
+k_xsplit_inv(const float2* __restrict__ T, float2* __restrict__ S, RowMap m, const float2* __restrict__ twx, int n2len,
+             int pitch_t) {
+  const int ky = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ky >= pitch_t) return;
+  const int n2 = blockIdx.y, b = blockIdx.z;
+  float2 v[R0];
+#pragma unroll
+  for (int k1 = 0; k1 < R0; ++k1) v[k1] = __ldg(&T[(((size_t)b * R0 + k1) * n2len + n2) * pitch_t + ky]);
+  if constexpr (R0 > 1) {
+#pragma unroll
+    for (int k1 = 1; k1 < R0; ++k1) {
+      const float2 w = __ldg(&twx[n2 * k1]);               // conj(w)
+      const float2 x = v[k1];
+      v[k1] = make_float2(x.x * w.x + x.y * w.y, x.y * w.x - x.x * w.y);
+    }
+    dft_regs<R0, +1>(v);
+  }
+#pragma unroll
+  for (int n1 = 0; n1 < R0; ++n1) {
+    const int x = n1 * n2len + n2;
+    S[rowmap_off(m, b, x, ky)] = v[n1];
+    if (m.dup_row >= 0 && (x & m.mask) == 0) {
+      const int ch = ((x >> m.sh) + m.nchunks - 1) % m.nchunks;
+      S[(size_t)ch * m.chunk_stride + (size_t)b * m.img_stride + (size_t)m.dup_row * m.pitch + ky] = v[n1];
     }
   }
 }
@@ -490,9 +583,9 @@ k_project_cluster(float* __restrict__ u, float* __restrict__ v, float* __restric
       reinterpret_cast<float*>(&buf[y * LS + (r >> 1)])[r & 1] = d;
     }
     __syncthreads();
-    stage_smem<N, P::R1, 1, -1>(buf, LS, c, j, true, tw);
-    stage_smem<N, P::R2, P::R1, -1>(buf, LS, c, j, true, tw);
-    if constexpr (P::R3 > 1) stage_smem<N, P::R3, P::R1 * P::R2, -1>(buf, LS, c, j, true, tw);
+    stage_smem<N, P::R1, 1, -1, Q>(buf, c, j, true, tw);
+    stage_smem<N, P::R2, P::R1, -1, Q>(buf, c, j, true, tw);
+    if constexpr (P::R3 > 1) stage_smem<N, P::R3, P::R1 * P::R2, -1, Q>(buf, c, j, true, tw);
     for (int idx = threadIdx.x; idx < Q * NYC; idx += NT) {
       const int q = idx / NYC, k = idx - q * NYC;
       const float2 z = buf[k * LS + q];
@@ -529,7 +622,7 @@ k_project_cluster(float* __restrict__ u, float* __restrict__ v, float* __restric
         }
         __syncthreads();
       }
-      if constexpr (P::R3 > 1) stage_smem<N, P::R2, P::R1, -1>(buf, LS, c, j, true, tw);
+      if constexpr (P::R3 > 1) stage_smem<N, P::R2, P::R1, -1, Q>(buf, c, j, true, tw);
       {
         float2 w[RL];
         const bool on = j < N / RL;
@@ -553,7 +646,7 @@ k_project_cluster(float* __restrict__ u, float* __restrict__ v, float* __restric
         }
         __syncthreads();
       }
-      if constexpr (P::R3 > 1) stage_smem<N, P::R2, P::R3, +1>(buf, LS, c, j, true, tw);
+      if constexpr (P::R3 > 1) stage_smem<N, P::R2, P::R3, +1, Q>(buf, c, j, true, tw);
       {
         constexpr int R = P::R1;
         constexpr int NS = N / R;
@@ -592,12 +685,12 @@ k_project_cluster(float* __restrict__ u, float* __restrict__ v, float* __restric
     }
     __syncthreads();
     if constexpr (P::R3 > 1) {
-      stage_smem<N, P::R3, 1, +1>(buf, LS, c, j, true, tw);
-      stage_smem<N, P::R2, P::R3, +1>(buf, LS, c, j, true, tw);
-      stage_smem<N, P::R1, P::R3 * P::R2, +1>(buf, LS, c, j, true, tw);
+      stage_smem<N, P::R3, 1, +1, Q>(buf, c, j, true, tw);
+      stage_smem<N, P::R2, P::R3, +1, Q>(buf, c, j, true, tw);
+      stage_smem<N, P::R1, P::R3 * P::R2, +1, Q>(buf, c, j, true, tw);
     } else {
-      stage_smem<N, P::R2, 1, +1>(buf, LS, c, j, true, tw);
-      stage_smem<N, P::R1, P::R2, +1>(buf, LS, c, j, true, tw);
+      stage_smem<N, P::R2, 1, +1, Q>(buf, c, j, true, tw);
+      stage_smem<N, P::R1, P::R2, +1, Q>(buf, c, j, true, tw);
     }
     for (int idx = threadIdx.x; idx < 2 * Q * N; idx += NT) {
       const int r = idx / N, y = idx - r * N;
@@ -669,53 +762,53 @@ int launch_project_cluster(float* u, float* v, float* pout, const float* inv_eig
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-template <int N>
+template <int N, bool SLAB>
 static int launch_div_rfft_n(const float* u, const float* v, float2* S, const float2* tw, const SolverParams& p,
                              cudaStream_t st) {
   using C = RowCfg<N>;
   static bool attr_done = false;
   if (!attr_done) {
-    MLSIM_CUDA_CHECK(cudaFuncSetAttribute(k_div_rfft<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    MLSIM_CUDA_CHECK(cudaFuncSetAttribute(k_div_rfft<N, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     attr_done = true;
   }
   dim3 grid(p.nx / (2 * C::Q), p.batch);
-  k_div_rfft<N><<<grid, C::THREADS, C::SMEM, st>>>(u, v, S, tw, p);
+  k_div_rfft<N, SLAB><<<grid, C::THREADS, C::SMEM, st>>>(u, v, S, tw, p);
   MLSIM_CUDA_CHECK(cudaGetLastError());
   return MLSIM_OK;
 }
 
-template <int N>
+template <int N, bool SLAB>
 static int launch_irfft_grad_n(const float2* S, const float* uin, const float* vin, float* uout, float* vout,
                                float* pout, const float2* tw, const SolverParams& p, cudaStream_t st) {
   using C = RowCfg<N>;
   static bool attr_done = false;
   if (!attr_done) {
-    MLSIM_CUDA_CHECK(cudaFuncSetAttribute(k_irfft_grad<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    MLSIM_CUDA_CHECK(cudaFuncSetAttribute(k_irfft_grad<N, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     attr_done = true;
   }
   const int rows = 2 * C::Q - 1;
   dim3 grid((p.nx + rows - 1) / rows, p.batch);
-  k_irfft_grad<N><<<grid, C::THREADS, C::SMEM, st>>>(S, uin, vin, uout, vout, pout, tw, p);
+  k_irfft_grad<N, SLAB><<<grid, C::THREADS, C::SMEM, st>>>(S, uin, vin, uout, vout, pout, tw, p);
   MLSIM_CUDA_CHECK(cudaGetLastError());
   return MLSIM_OK;
 }
 
 template <int N>
-static int launch_col_solve_n(float2* S, const float* inv_eig, const float2* tw, const SolverParams& p,
-                              cudaStream_t st) {
+static int launch_col_solve_n(float2* S, const float* inv_eig, const float2* tw, const SolverParams& p, int images,
+                              int eig_images, cudaStream_t st) {
   using C = ColCfg<N>;
   static bool attr_done = false;
   if (!attr_done) {
     MLSIM_CUDA_CHECK(cudaFuncSetAttribute(k_col_solve<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     attr_done = true;
   }
-  dim3 grid((p.nyc + C::C - 1) / C::C, p.batch);
-  k_col_solve<N><<<grid, C::THREADS, C::SMEM, st>>>(S, inv_eig, tw, p);
+  dim3 grid((p.nyc + C::C - 1) / C::C, images);
+  k_col_solve<N><<<grid, C::THREADS, C::SMEM, st>>>(S, inv_eig, tw, p, eig_images);
   MLSIM_CUDA_CHECK(cudaGetLastError());
   return MLSIM_OK;
 }
 
-#define MLSIM_DISPATCH_N(n, CALL)                     \
+#define MLSIM_DISPATCH_ROW(n, CALL)                   \
   switch (n) {                                        \
     case 64:   { constexpr int N_ = 64;   return CALL; }   \
     case 128:  { constexpr int N_ = 128;  return CALL; }   \
@@ -723,19 +816,92 @@ static int launch_col_solve_n(float2* S, const float* inv_eig, const float2* tw,
     case 512:  { constexpr int N_ = 512;  return CALL; }   \
     case 1024: { constexpr int N_ = 1024; return CALL; }   \
     case 2048: { constexpr int N_ = 2048; return CALL; }   \
-    default: set_error("unsupported grid size (need power of two in [64, 2048])"); return MLSIM_EINVAL; \
+    case 4096: { constexpr int N_ = 4096; return CALL; }   \
+    case 8192: { constexpr int N_ = 8192; return CALL; }   \
+    default: set_error("unsupported ny (need a power of two in [64, 8192])"); return MLSIM_EINVAL; \
+  }
+#define MLSIM_DISPATCH_COL(n, CALL)                   \
+  switch (n) {                                        \
+    case 64:   { constexpr int N_ = 64;   return CALL; }   \
+    case 128:  { constexpr int N_ = 128;  return CALL; }   \
+    case 256:  { constexpr int N_ = 256;  return CALL; }   \
+    case 512:  { constexpr int N_ = 512;  return CALL; }   \
+    case 1024: { constexpr int N_ = 1024; return CALL; }   \
+    case 2048: { constexpr int N_ = 2048; return CALL; }   \
+    default: set_error("unsupported column transform length (need a power of two in [64, 2048])"); return MLSIM_EINVAL; \
   }
 
 int launch_div_rfft(const float* u, const float* v, float2* S, const float2* tw_y, const SolverParams& p,
                     cudaStream_t st) {
-  MLSIM_DISPATCH_N(p.ny, launch_div_rfft_n<N_>(u, v, S, tw_y, p, st));
+  if (p.halo > 0) { MLSIM_DISPATCH_ROW(p.ny, (launch_div_rfft_n<N_, true>(u, v, S, tw_y, p, st))); }
+  MLSIM_DISPATCH_ROW(p.ny, (launch_div_rfft_n<N_, false>(u, v, S, tw_y, p, st)));
 }
 int launch_irfft_grad(const float2* S, const float* uin, const float* vin, float* uout, float* vout, float* pout,
                       const float2* tw_y, const SolverParams& p, cudaStream_t st) {
-  MLSIM_DISPATCH_N(p.ny, launch_irfft_grad_n<N_>(S, uin, vin, uout, vout, pout, tw_y, p, st));
+  if (p.halo > 0) { MLSIM_DISPATCH_ROW(p.ny, (launch_irfft_grad_n<N_, true>(S, uin, vin, uout, vout, pout, tw_y, p, st))); }
+  MLSIM_DISPATCH_ROW(p.ny, (launch_irfft_grad_n<N_, false>(S, uin, vin, uout, vout, pout, tw_y, p, st)));
 }
-int launch_col_solve(float2* S, const float* inv_eig, const float2* tw_x, const SolverParams& p, cudaStream_t st) {
-  MLSIM_DISPATCH_N(p.nx, launch_col_solve_n<N_>(S, inv_eig, tw_x, p, st));
+// `n` rows per image, `images` images in the plain buffer S, image i scaled by table image i % eig_images
+int launch_col_solve(float2* S, const float* inv_eig, const float2* tw_x, const SolverParams& p, int n, int images,
+                     int eig_images, cudaStream_t st) {
+  MLSIM_DISPATCH_COL(n, (launch_col_solve_n<N_>(S, inv_eig, tw_x, p, images, eig_images, st)));
+}
+
+// Row maps of the three spectral buffer layouts the split passes read / write.
+static RowMap rowmap_plain(int nx, int pitch) {
+  RowMap m; m.sh = 31; m.mask = 0x7fffffff; m.pitch = pitch; m.chunk_stride = 0; m.img_stride = (long long)nx * pitch;
+  m.dup_row = -1; m.nchunks = 1; return m;
+}
+static RowMap rowmap_chunks(int nxl, int rows, int batch, int pitch, int world, bool dup) {
+  RowMap m; m.sh = ilog2(nxl); m.mask = nxl - 1; m.pitch = pitch; m.img_stride = (long long)rows * pitch;
+  m.chunk_stride = (long long)batch * rows * pitch; m.dup_row = dup ? nxl : -1; m.nchunks = world; return m;
+}
+
+template <int R0>
+static int launch_xsplit_r(bool fwd, float2* S, const RowMap& m, float2* T, const float2* twx, int n2len, int pitch_t,
+                           int batch, cudaStream_t st) {
+  dim3 grid((pitch_t + 127) / 128, n2len, batch);
+  if (fwd) k_xsplit_fwd<R0><<<grid, 128, 0, st>>>(S, m, T, twx, n2len, pitch_t);
+  else k_xsplit_inv<R0><<<grid, 128, 0, st>>>(T, S, m, twx, n2len, pitch_t);
+  MLSIM_CUDA_CHECK(cudaGetLastError());
+  return MLSIM_OK;
+}
+static int launch_xsplit(bool fwd, int r0, float2* S, const RowMap& m, float2* T, const float2* twx, int n2len,
+                         int pitch_t, int batch, cudaStream_t st) {
+  switch (r0) {
+    case 1: return launch_xsplit_r<1>(fwd, S, m, T, twx, n2len, pitch_t, batch, st);
+    case 2: return launch_xsplit_r<2>(fwd, S, m, T, twx, n2len, pitch_t, batch, st);
+    case 4: return launch_xsplit_r<4>(fwd, S, m, T, twx, n2len, pitch_t, batch, st);
+    case 8: return launch_xsplit_r<8>(fwd, S, m, T, twx, n2len, pitch_t, batch, st);
+    case 16: return launch_xsplit_r<16>(fwd, S, m, T, twx, n2len, pitch_t, batch, st);
+    default: set_error("unsupported outer radix of the split x-transform"); return MLSIM_EINVAL;
+  }
+}
+
+// x-direction solve of a plain buffer S[b][nx][nycp] with nx = r0 * n2len > 2048:  S -> T -> (K3 on T) -> S
+int launch_col_solve_split(float2* S, float2* T, const float* inv_eig_perm, const float2* twx_full, const float2* tw_n2,
+                           const SolverParams& p, int r0, cudaStream_t st) {
+  const int n2len = p.nx / r0;
+  const RowMap m = rowmap_plain(p.nx, p.nycp);
+  int rc;
+  if ((rc = launch_xsplit(true, r0, S, m, T, twx_full, n2len, p.nycp, p.batch, st))) return rc;
+  if ((rc = launch_col_solve(T, inv_eig_perm, tw_n2, p, n2len, p.batch * r0, r0, st))) return rc;
+  return launch_xsplit(false, r0, S, m, T, twx_full, n2len, p.nycp, p.batch, st);
+}
+
+// Slab decomposition, this rank's share of the spectrum (kyv valid columns, pitch kywp), all nxg rows:
+//   recv [world][b][nxl][kywp]  ->  T[b][r0][n2len][kywp]  -> K3 ->  send2 [world][b][nxl+1][kywp] (halo row duplicated)
+int launch_col_solve_slab(const float2* recv, float2* send2, float2* T, const float* inv_eig_perm, const float2* twx_full,
+                          const float2* tw_n2, const SolverParams& p, int nxg, int world, int kyv, int r0, cudaStream_t st) {
+  const int n2len = nxg / r0;
+  const RowMap min_ = rowmap_chunks(p.nx, p.nx, p.batch, p.kywp, world, false);
+  const RowMap mout = rowmap_chunks(p.nx, p.nx + 1, p.batch, p.kywp, world, true);
+  SolverParams q = p;
+  q.nyc = kyv; q.nycp = p.kywp;
+  int rc;
+  if ((rc = launch_xsplit(true, r0, const_cast<float2*>(recv), min_, T, twx_full, n2len, p.kywp, p.batch, st))) return rc;
+  if ((rc = launch_col_solve(T, inv_eig_perm, tw_n2, q, n2len, p.batch * r0, r0, st))) return rc;
+  return launch_xsplit(false, r0, send2, mout, T, twx_full, n2len, p.kywp, p.batch, st);
 }
 
 }  // namespace mlsim

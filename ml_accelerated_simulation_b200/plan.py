@@ -36,6 +36,8 @@ class PlanConfig:
     max_velocity: float = 7.0
     cfl: float = 0.5
     device: int = 0
+    slab_rank: int = 0                   # slab decomposition along x (see slab.py); slab_world == 0: plain plan
+    slab_world: int = 0
 
     def resolved_dt(self) -> float:
         if self.dt is not None:
@@ -58,7 +60,7 @@ class Plan:
         self.dt = cfg.resolved_dt()
         c = _lib.MlsimConfig(cfg.nx, cfg.ny, cfg.batch, cfg.lx, cfg.ly, self.dt, cfg.viscosity, cfg.density,
                              cfg.drag, cfg.forcing_wavenumber, cfg.forcing_scale, ADVECTION[cfg.advection],
-                             cfg.lw_dt_scale, cfg.device)
+                             cfg.lw_dt_scale, cfg.device, cfg.slab_rank, cfg.slab_world)
         h = C.c_void_p()
         _lib.check(self._lib.mlsim_plan_create(C.byref(c), C.byref(h)))
         self._h = h

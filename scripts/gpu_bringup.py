@@ -149,3 +149,6 @@ if __name__ == "__main__":
         section("timing")
         run("t256", lambda: timing(256, 256, 64))
         run("t1024", lambda: timing(1024, 1024, 16))
+    if "t128" in what:
+        section("timing 128^2 x 512 (config 4 share of one of 8 GPUs)")
+        run("t128", lambda: timing(128, 128, 512))

@@ -57,7 +57,7 @@ def test_plan_create_fails_loudly_without_a_gpu(built_lib):
 def test_plan_create_rejects_bad_geometry(built_lib):
     from ml_accelerated_simulation_b200 import _lib
     lib = _lib.load()
-    for nx, ny, batch in ((48, 64, 1), (64, 32, 1), (4096, 64, 1), (64, 64, 0)):
+    for nx, ny, batch in ((48, 64, 1), (64, 32, 1), (16384, 64, 1), (64, 64, 0)):
         cfg = _lib.MlsimConfig(nx, ny, batch, 6.28, 6.28, 1e-3, 1e-3, 1.0, 0.1, 4, 1.0, 0, 1.0, 0)
         h = C.c_void_p()
         assert lib.mlsim_plan_create(C.byref(cfg), C.byref(h)) == -1       # MLSIM_EINVAL, before any CUDA call

@@ -274,7 +274,7 @@ def run_ours(args):
         "roofline": {"kernel": "k_conv_mid<64> (3x3 conv 64->64, tcgen05 implicit GEMM)", "bound": "tensor",
                      "achieved": mid_tflops, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
                      "frac": mid_tflops / peaks["tensor_tflops"], "frac_of_burst": mid_tflops / peaks["tensor_tflops_burst"],
-                     "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_unit": "B/launch (ncu dram read+write, profiles/r01_ncu_summary.txt); algorithmic 1.074e9 B (541 MB bf16 activations in + out)", "launches_timed": mid_n, "avg_launch_ms": mid_avg_ms,
+                     "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if (NX, BATCH) == (256, 64) else None, "traffic_unit": "B/launch (ncu dram read+write, profiles/r01_ncu_summary.txt); algorithmic 1.074e9 B (541 MB bf16 activations in + out)", "launches_timed": mid_n, "avg_launch_ms": mid_avg_ms,
                      "share_of_step": mid_ms / ms_total, "peak_source": peaks["source"]},
         "solver_roofline": {"bound": "hbm", "ms_per_step": solver_ms, "cell_steps_per_s": solver_rate,
                             "achieved": SOLVER_BYTES_PER_CELL_STEP * solver_rate / 1e9, "peak": peaks["hbm_gbs"],
@@ -408,7 +408,14 @@ def main():
     ap.add_argument("--workload", default="ensemble", choices=["ensemble", "slab"],
                     help="ensemble: BASELINE configs[1] (default, the driver's line); slab: configs[4], one big grid over N GPUs")
     ap.add_argument("--nx", type=int, default=8192, help="grid size of the slab workload")
+    ap.add_argument("--grid", type=int, default=0, help="ensemble workload: grid size (default 256 = configs[1])")
+    ap.add_argument("--batch", type=int, default=0, help="ensemble workload: trajectories per GPU (default 64)")
     args = ap.parse_args()
+    if args.grid or args.batch:          # other BASELINE configs through the same code path (e.g. configs[3]: --grid 128 --batch 512 at 8 GPUs)
+        global NX, NY, BATCH, WORKLOAD
+        NX = NY = args.grid or NX
+        BATCH = args.batch or BATCH
+        WORKLOAD = f"{NX}x{NY} grid, batch {BATCH} trajectories per GPU, RK4 solver step + MLACFD correction CNN"
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "slab":

@@ -61,6 +61,33 @@ struct StageArgs {
   int mode;
 };
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the step is launched with the "programmatic stream serialization"
+// attribute, releases its dependents at once (pdl_launch_dependents) and waits for the complete, flushed result of
+// its predecessor (pdl_wait) before touching any buffer the step writes.  The next kernel's CTAs are therefore
+// already resident (prologue done: indices, barrier init, TMEM allocation, weight image load) when the previous
+// grid drains, instead of paying drain + launch latency between each of the 23 dependent kernels of a step.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 static inline int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
 static inline bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 

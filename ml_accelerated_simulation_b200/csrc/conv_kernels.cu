@@ -61,10 +61,12 @@ k_conv_first(ConvFirstArgs a) {
     tmem_alloc(&tmem_slot, 128);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                       // everything above (weights, barriers, TMEM) is independent of the previous kernel
   const uint32_t tmem = tmem_slot;
   const uint32_t idesc = umma_idesc_bf16(64);
 
@@ -242,10 +244,23 @@ k_conv_mid(ConvMidArgs a) {
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // the weight image does not depend on the previous kernel: start its bulk copy before waiting for that kernel
+  if (tid == 0) {
+    mbar_arrive_expect_tx(wbar, (uint32_t)(L::WBYTES + NB * 4));
+    uint32_t off = 0;
+    const uint32_t total = L::WBYTES + NB * 4;
+    while (off < total) {                       // weight image + bias, in pieces of at most 32 KB
+      const uint32_t n = (total - off) > 32768u ? 32768u : (total - off);
+      bulk_g2s(sW + off, a.wimg + off, n, wbar);
+      off += n;
+    }
+  }
+  pdl_wait();
 
   const int nyt = (a.ny + 127) >> 7;
   const int nstrips = (a.nx + a.rs - 1) / a.rs;
@@ -266,16 +281,6 @@ k_conv_mid(ConvMidArgs a) {
     // (tempty[q] phase u = ring position q ready for its u-th use, phase 0 = initial zero fill).  The MMA warp
     // then has a single barrier to wait for per input row (full[stage]), keeping its inter-row gap short.
     if (lane == 0) {
-      mbar_arrive_expect_tx(wbar, (uint32_t)(L::WBYTES + NB * 4));
-      {
-        uint32_t off = 0;
-        const uint32_t total = L::WBYTES + NB * 4;
-        while (off < total) {                       // weight image + bias, in pieces of at most 32 KB
-          const uint32_t n = (total - off) > 32768u ? 32768u : (total - off);
-          bulk_g2s(sW + off, a.wimg + off, n, wbar);
-          off += n;
-        }
-      }
       uint32_t stage = 0, empty_parity = 1;          // fresh barrier: waiting on parity 1 passes immediately
       uint32_t qn = 0, ready_par = 0;
       for (int it_ = blockIdx.x; it_ < nitems; it_ += gridDim.x) {
@@ -504,8 +509,7 @@ int launch_conv_first(const ConvFirstArgs& a, int sm_count, cudaStream_t st) {
   const long ntiles = (long)a.batch * a.nx * nyt;
   const long resident = (long)sm_count * 4;      // 4 CTAs/SM: 2 x 64 TMEM columns each, ~110 registers/thread
   int grid = (int)(ntiles < resident ? ntiles : resident);
-  k_conv_first<<<grid, CF_THREADS, 0, st>>>(a);
-  MLSIM_CUDA_CHECK(cudaGetLastError());
+  MLSIM_CUDA_CHECK(launch_pdl(k_conv_first, dim3(grid), dim3(CF_THREADS), 0, st, a));
   return MLSIM_OK;
 }
 
@@ -529,8 +533,7 @@ static int launch_conv_mid_t(const ConvMidArgs& a, int sm_count, cudaStream_t st
   const long nitems = (long)a.batch * nstrips * nyt;
   const long resident = (long)sm_count * (LAST ? 2 : 1);
   const int grid = (int)(nitems < resident ? nitems : resident);
-  k_conv_mid<NB, LAST><<<grid, LAST ? CM_THREADS_LAST : CM_THREADS_MID, L::TOTAL, st>>>(a);
-  MLSIM_CUDA_CHECK(cudaGetLastError());
+  MLSIM_CUDA_CHECK(launch_pdl(k_conv_mid<NB, LAST>, dim3(grid), dim3(LAST ? CM_THREADS_LAST : CM_THREADS_MID), (size_t)L::TOTAL, st, a));
   return MLSIM_OK;
 }
 

@@ -23,23 +23,30 @@ constexpr int K1_TX = 32;
 constexpr int K1_HALO = 2;
 constexpr int K1_THREADS = 256;
 
+__device__ __forceinline__ float rcp_approx(float x) {        // bare MUFU.RCP (no range fix-up code around it)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 template <int ADV>
-__device__ __forceinline__ float face_flux(float cl, float c, float cr, float crr, float w, float cfl) {
-  // TVD face value times face velocity (App. A.3.2):  face = low - (low - high) * phi.
-  // With t = +-0.5*(1 -+ C) and d = cr - c:  high = low + t*d, so  face = low + (t*phi)*d.
-  // phi(r) = 2r/(1+r), r = num/d, is evaluated as 2*num/(d+num): identical for r > 0, one division, and
-  // free of the inf/inf hazard when d is tiny.  __fdividef: <= 2 ulp, |d+num| >= |num| so no overflow.
-  const bool pos = w > 0.0f;
+__device__ __forceinline__ float face_flux(float cl, float c, float cr, float crr, float w2, float hq) {
+  // TWICE the TVD face flux (App. A.3.2):  face = low - (low - high) * phi,  flux = face * w.
+  // w2 = sum of the two velocities whose mean is the face velocity (w = w2/2; the caller folds the 1/2 into 1/h);
+  // hq = 0.5*dt/h, so the Courant number is C = hq*w2.  With d = cr - c and t2 = +-1 - C:  high = low + (t2/2)*d.
+  // van Leer: phi(r) = 2r/(1+r), r = num/d  =>  (t2/2)*phi*d = t2 * (num*d)/(d+num): one product e = num*d whose
+  // sign is also the "r > 0" test, one reciprocal (MUFU.RCP, <= 2 ulp; e > 0 implies |d+num| > 0), all selects --
+  // no divergent branches.  (If e underflows, both differences are < 1e-19 and the dropped correction < 1e-38.)
+  const bool pos = w2 > 0.0f;
   const float low = pos ? c : cr;
-  if (ADV == MLSIM_ADV_UPWIND) return low * w;
+  if (ADV == MLSIM_ADV_UPWIND) return low * w2;
   const float d = cr - c;
-  const float hc = 0.5f * cfl * w;                          // half the Courant number
-  const float t = pos ? (0.5f - hc) : (-0.5f - hc);
-  if (ADV == MLSIM_ADV_LAX_WENDROFF) return fmaf(t, d, low) * w;
+  const float t2 = fmaf(-hq, w2, pos ? 1.0f : -1.0f);
+  if (ADV == MLSIM_ADV_LAX_WENDROFF) return fmaf(t2, 0.5f * d, low) * w2;
   const float num = pos ? (c - cl) : (crr - cr);
-  const bool same = (num > 0.0f && d > 0.0f) || (num < 0.0f && d < 0.0f);
-  const float phi = same ? __fdividef(2.0f * num, d + num) : 0.0f;
-  return fmaf(t * phi, d, low) * w;
+  const float e = num * d;
+  const float g = e * rcp_approx(d + num);
+  return fmaf(t2, (e > 0.0f) ? g : 0.0f, low) * w2;
 }
 
 // SLAB (x-slab decomposition): no periodic wrap in x; the tile rows come from the halo-extended buffers (row index
@@ -57,6 +64,8 @@ k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
   float* su = reinterpret_cast<float*>(smem4);
   float* sv = su + SH * SW;
 
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.z;
   const int i0 = SLAB ? ((int)blockIdx.y - 1) * K1_TX : blockIdx.y * K1_TX;
   const int j0 = blockIdx.x * TY;
@@ -86,6 +95,8 @@ k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
 #define SU(i, j) su[(i) * SW + (j)]
 #define SV(i, j) sv[(i) * SW + (j)]
 
+  const float hcx = 0.5f * p.dt_hx, hcy = 0.5f * p.dt_hy;     // hq of face_flux
+  const float hix = 0.5f * p.inv_hx, hiy = 0.5f * p.inv_hy;    // fluxes carry a factor 2
   // x-face fluxes at face (li0-1) for the 4 columns: carried along the march
   float fxu_prev[4], fxv_prev[4];
   {
@@ -93,10 +104,10 @@ k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int j = lj + k;
-      const float wxu = 0.5f * (SU(i, j) + SU(i + 1, j));
-      fxu_prev[k] = face_flux<ADV>(SU(i - 1, j), SU(i, j), SU(i + 1, j), SU(i + 2, j), wxu, p.dt_hx);
-      const float wxv = 0.5f * (SU(i, j) + SU(i, j + 1));
-      fxv_prev[k] = face_flux<ADV>(SV(i - 1, j), SV(i, j), SV(i + 1, j), SV(i + 2, j), wxv, p.dt_hx);
+      const float wxu = SU(i, j) + SU(i + 1, j);
+      fxu_prev[k] = face_flux<ADV>(SU(i - 1, j), SU(i, j), SU(i + 1, j), SU(i + 2, j), wxu, hcx);
+      const float wxv = SU(i, j) + SU(i, j + 1);
+      fxv_prev[k] = face_flux<ADV>(SV(i - 1, j), SV(i, j), SV(i + 1, j), SV(i + 2, j), wxv, hcx);
     }
   }
 
@@ -123,26 +134,26 @@ k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int j = lj + k;
-      const float wxu = 0.5f * (SU(i, j) + SU(i + 1, j));
-      fxu[k] = face_flux<ADV>(SU(i - 1, j), SU(i, j), SU(i + 1, j), SU(i + 2, j), wxu, p.dt_hx);
-      const float wxv = 0.5f * (SU(i, j) + SU(i, j + 1));
-      fxv[k] = face_flux<ADV>(SV(i - 1, j), SV(i, j), SV(i + 1, j), SV(i + 2, j), wxv, p.dt_hx);
+      const float wxu = SU(i, j) + SU(i + 1, j);
+      fxu[k] = face_flux<ADV>(SU(i - 1, j), SU(i, j), SU(i + 1, j), SU(i + 2, j), wxu, hcx);
+      const float wxv = SU(i, j) + SU(i, j + 1);
+      fxv[k] = face_flux<ADV>(SV(i - 1, j), SV(i, j), SV(i + 1, j), SV(i + 2, j), wxv, hcx);
     }
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
       const int j = lj - 1 + k;               // y-face between columns j and j+1
-      const float wyu = 0.5f * (SV(i, j) + SV(i + 1, j));
-      fyu[k] = face_flux<ADV>(SU(i, j - 1), SU(i, j), SU(i, j + 1), SU(i, j + 2), wyu, p.dt_hy);
-      const float wyv = 0.5f * (SV(i, j) + SV(i, j + 1));
-      fyv[k] = face_flux<ADV>(SV(i, j - 1), SV(i, j), SV(i, j + 1), SV(i, j + 2), wyv, p.dt_hy);
+      const float wyu = SV(i, j) + SV(i + 1, j);
+      fyu[k] = face_flux<ADV>(SU(i, j - 1), SU(i, j), SU(i, j + 1), SU(i, j + 2), wyu, hcy);
+      const float wyv = SV(i, j) + SV(i, j + 1);
+      fyv[k] = face_flux<ADV>(SV(i, j - 1), SV(i, j), SV(i, j + 1), SV(i, j + 2), wyv, hcy);
     }
     float ku[4], kv[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int j = lj + k;
       const float cu = SU(i, j), cv = SV(i, j);
-      const float advu = -((fxu[k] - fxu_prev[k]) * p.inv_hx + (fyu[k + 1] - fyu[k]) * p.inv_hy);
-      const float advv = -((fxv[k] - fxv_prev[k]) * p.inv_hx + (fyv[k + 1] - fyv[k]) * p.inv_hy);
+      const float advu = -((fxu[k] - fxu_prev[k]) * hix + (fyu[k + 1] - fyu[k]) * hiy);
+      const float advv = -((fxv[k] - fxv_prev[k]) * hix + (fyv[k + 1] - fyv[k]) * hiy);
       const float lapu = (SU(i - 1, j) + SU(i + 1, j) - 2.0f * cu) * p.nu_hx2 +
                          (SU(i, j - 1) + SU(i, j + 1) - 2.0f * cu) * p.nu_hy2;
       const float lapv = (SV(i - 1, j) + SV(i + 1, j) - 2.0f * cv) * p.nu_hx2 +
@@ -192,8 +203,7 @@ static int launch_explicit_ty(const StageArgs& a, const SolverParams& p, const f
     attr_done = true;
   }
   dim3 grid(p.ny / TY, p.nx / K1_TX + (SLAB ? 1 : 0), p.batch);
-  k_explicit_rk<TY, ADV, SLAB><<<grid, K1_THREADS, smem, st>>>(a, p, forcing);
-  MLSIM_CUDA_CHECK(cudaGetLastError());
+  MLSIM_CUDA_CHECK(launch_pdl(k_explicit_rk<TY, ADV, SLAB>, grid, dim3(K1_THREADS), smem, st, a, p, forcing));
   return MLSIM_OK;
 }
 
@@ -276,6 +286,8 @@ k_div_rfft(const float* __restrict__ u, const float* __restrict__ v, float2* __r
   extern __shared__ float4 smem4[];
   float2* buf = reinterpret_cast<float2*>(smem4);
 
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const int i0 = blockIdx.x * (2 * Q);
   const float* __restrict__ gu = u + (ptrdiff_t)b * p.img_stride;
@@ -322,6 +334,8 @@ k_irfft_grad(const float2* __restrict__ S, const float* __restrict__ uin, const 
   extern __shared__ float4 smem4[];
   float2* buf = reinterpret_cast<float2*>(smem4);
 
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const int i0 = blockIdx.x * (2 * Q - 1);
   constexpr int nyc = N / 2 + 1;
@@ -388,6 +402,8 @@ k_col_solve(float2* __restrict__ S, const float* __restrict__ inv_eig, const flo
   extern __shared__ float4 smem4[];
   float2* buf = reinterpret_cast<float2*>(smem4);
 
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = threadIdx.x % C, j = threadIdx.x / C;
   const int ky = blockIdx.x * C + c;
   const bool valid = ky < p.nyc;
@@ -478,6 +494,8 @@ template <int R0>
 __global__ void __launch_bounds__(128)
 k_xsplit_fwd(const float2* __restrict__ S, RowMap m, float2* __restrict__ T, const float2* __restrict__ twx, int n2len,
              int pitch_t) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int ky = blockIdx.x * blockDim.x + threadIdx.x;
   if (ky >= pitch_t) return;
   const int n2 = blockIdx.y, b = blockIdx.z;
@@ -501,6 +519,8 @@ template <int R0>
 __global__ void __launch_bounds__(128)
 k_xsplit_inv(const float2* __restrict__ T, float2* __restrict__ S, RowMap m, const float2* __restrict__ twx, int n2len,
              int pitch_t) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int ky = blockIdx.x * blockDim.x + threadIdx.x;
   if (ky >= pitch_t) return;
   const int n2 = blockIdx.y, b = blockIdx.z;
@@ -558,6 +578,8 @@ k_project_cluster(float* __restrict__ u, float* __restrict__ v, float* __restric
   float2* S = reinterpret_cast<float2*>(smem4);            // [RPC][NYC] half spectrum of the CTA's rows, later p rows
   float2* buf = S + (size_t)RPC * NYC;                     // [N][LS] FFT work buffer (line-fastest)
 
+  pdl_launch_dependents();
+  pdl_wait();
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (CL == 1) ? 0 : (int)cluster.block_rank();
   const int b = blockIdx.x / CL;
@@ -734,13 +756,15 @@ static int launch_project_cluster_t(float* u, float* v, float* pout, const float
   cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   MLSIM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_project_cluster<N, CL>, u, v, pout, inv_eig, tw, p));
   return MLSIM_OK;
 }
@@ -772,8 +796,7 @@ static int launch_div_rfft_n(const float* u, const float* v, float2* S, const fl
     attr_done = true;
   }
   dim3 grid(p.nx / (2 * C::Q), p.batch);
-  k_div_rfft<N, SLAB><<<grid, C::THREADS, C::SMEM, st>>>(u, v, S, tw, p);
-  MLSIM_CUDA_CHECK(cudaGetLastError());
+  MLSIM_CUDA_CHECK(launch_pdl(k_div_rfft<N, SLAB>, grid, dim3(C::THREADS), C::SMEM, st, u, v, S, tw, p));
   return MLSIM_OK;
 }
 
@@ -788,8 +811,7 @@ static int launch_irfft_grad_n(const float2* S, const float* uin, const float* v
   }
   const int rows = 2 * C::Q - 1;
   dim3 grid((p.nx + rows - 1) / rows, p.batch);
-  k_irfft_grad<N, SLAB><<<grid, C::THREADS, C::SMEM, st>>>(S, uin, vin, uout, vout, pout, tw, p);
-  MLSIM_CUDA_CHECK(cudaGetLastError());
+  MLSIM_CUDA_CHECK(launch_pdl(k_irfft_grad<N, SLAB>, grid, dim3(C::THREADS), C::SMEM, st, S, uin, vin, uout, vout, pout, tw, p));
   return MLSIM_OK;
 }
 
@@ -803,8 +825,7 @@ static int launch_col_solve_n(float2* S, const float* inv_eig, const float2* tw,
     attr_done = true;
   }
   dim3 grid((p.nyc + C::C - 1) / C::C, images);
-  k_col_solve<N><<<grid, C::THREADS, C::SMEM, st>>>(S, inv_eig, tw, p, eig_images);
-  MLSIM_CUDA_CHECK(cudaGetLastError());
+  MLSIM_CUDA_CHECK(launch_pdl(k_col_solve<N>, grid, dim3(C::THREADS), C::SMEM, st, S, inv_eig, tw, p, eig_images));
   return MLSIM_OK;
 }
 
@@ -861,9 +882,8 @@ template <int R0>
 static int launch_xsplit_r(bool fwd, float2* S, const RowMap& m, float2* T, const float2* twx, int n2len, int pitch_t,
                            int batch, cudaStream_t st) {
   dim3 grid((pitch_t + 127) / 128, n2len, batch);
-  if (fwd) k_xsplit_fwd<R0><<<grid, 128, 0, st>>>(S, m, T, twx, n2len, pitch_t);
-  else k_xsplit_inv<R0><<<grid, 128, 0, st>>>(T, S, m, twx, n2len, pitch_t);
-  MLSIM_CUDA_CHECK(cudaGetLastError());
+  if (fwd) MLSIM_CUDA_CHECK(launch_pdl(k_xsplit_fwd<R0>, grid, dim3(128), 0, st, S, m, T, twx, n2len, pitch_t));
+  else MLSIM_CUDA_CHECK(launch_pdl(k_xsplit_inv<R0>, grid, dim3(128), 0, st, T, S, m, twx, n2len, pitch_t));
   return MLSIM_OK;
 }
 static int launch_xsplit(bool fwd, int r0, float2* S, const RowMap& m, float2* T, const float2* twx, int n2len,

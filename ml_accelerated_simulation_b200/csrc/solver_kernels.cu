@@ -10,6 +10,7 @@
 #include "solver_kernels.h"
 
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace mlsim {
 
@@ -52,8 +53,8 @@ __device__ __forceinline__ float face_flux(float cl, float c, float cr, float cr
 // SLAB (x-slab decomposition): no periodic wrap in x; the tile rows come from the halo-extended buffers (row index
 // clamped to the valid rows [-halo, nx+halo)), and one extra leading tile (blockIdx.y == 0 <-> rows [-32, 0)) computes
 // output row -1 -- the x-halo of u* that the divergence of the local row 0 needs -- so no second exchange is required.
-template <int TY, int ADV, bool SLAB>
-__global__ void __launch_bounds__(K1_THREADS, 3)
+template <int TY, int ADV, bool SLAB, int MINB>
+__global__ void __launch_bounds__(K1_THREADS, MINB)
 k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
   constexpr int NTY = TY / 4;                 // threads along y
   constexpr int NG = K1_THREADS / NTY;        // row groups
@@ -193,18 +194,24 @@ k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
 #undef SV
 }
 
-template <int TY, int ADV, bool SLAB>
-static int launch_explicit_ty(const StageArgs& a, const SolverParams& p, const float* forcing, cudaStream_t st) {
+template <int TY, int ADV, bool SLAB, int MINB>
+static int launch_explicit_mb(const StageArgs& a, const SolverParams& p, const float* forcing, cudaStream_t st) {
   constexpr int SW = TY + 8, SH = K1_TX + 2 * K1_HALO;
   const size_t smem = (size_t)2 * SH * SW * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
-    MLSIM_CUDA_CHECK(cudaFuncSetAttribute(k_explicit_rk<TY, ADV, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MLSIM_CUDA_CHECK(cudaFuncSetAttribute(k_explicit_rk<TY, ADV, SLAB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   dim3 grid(p.ny / TY, p.nx / K1_TX + (SLAB ? 1 : 0), p.batch);
-  MLSIM_CUDA_CHECK(launch_pdl(k_explicit_rk<TY, ADV, SLAB>, grid, dim3(K1_THREADS), smem, st, a, p, forcing));
+  MLSIM_CUDA_CHECK(launch_pdl(k_explicit_rk<TY, ADV, SLAB, MINB>, grid, dim3(K1_THREADS), smem, st, a, p, forcing));
   return MLSIM_OK;
+}
+template <int TY, int ADV, bool SLAB>
+static int launch_explicit_ty(const StageArgs& a, const SolverParams& p, const float* forcing, cudaStream_t st) {
+  static const int minb = [] { const char* e = getenv("MLSIM_K1_MINB"); return e ? atoi(e) : 3; }();
+  if (ADV == MLSIM_ADV_VAN_LEER && minb == 4) return launch_explicit_mb<TY, ADV, SLAB, 4>(a, p, forcing, st);
+  return launch_explicit_mb<TY, ADV, SLAB, 3>(a, p, forcing, st);
 }
 
 template <int ADV>
@@ -293,14 +300,19 @@ k_div_rfft(const float* __restrict__ u, const float* __restrict__ v, float2* __r
   const float* __restrict__ gu = u + (ptrdiff_t)b * p.img_stride;
   const float* __restrict__ gv = v + (ptrdiff_t)b * p.img_stride;
 
-  for (int idx = threadIdx.x; idx < 2 * Q * N; idx += NT) {
-    const int r = idx / N, j = idx - r * N;
-    const int i = i0 + r;
+  // divergence: a thread owns one y and two consecutive rows (= the two halves of one float2 of the line-fastest
+  // layout): coalesced 128-byte row loads, one conflict-free 64-bit shared store
+  for (int g = threadIdx.x; g < Q * N; g += NT) {
+    const int q = g / N, j = g - q * N;
+    const int i = i0 + 2 * q;
     const int im = SLAB ? (i - 1) : ((i - 1) & (p.nx - 1));
     const int jm = (j - 1) & (N - 1);
-    const float d = (gu[(ptrdiff_t)i * N + j] - gu[(ptrdiff_t)im * N + j]) * p.inv_hx +
-                    (gv[(ptrdiff_t)i * N + j] - gv[(ptrdiff_t)i * N + jm]) * p.inv_hy;
-    reinterpret_cast<float*>(&buf[fidx<Q>(j, r >> 1)])[r & 1] = d;
+    const float um = gu[(ptrdiff_t)im * N + j];
+    const float ua = gu[(ptrdiff_t)i * N + j], ub = gu[(ptrdiff_t)(i + 1) * N + j];
+    const float va = gv[(ptrdiff_t)i * N + j], vb = gv[(ptrdiff_t)(i + 1) * N + j];
+    const float vam = gv[(ptrdiff_t)i * N + jm], vbm = gv[(ptrdiff_t)(i + 1) * N + jm];
+    buf[fidx<Q>(j, q)] = make_float2((ua - um) * p.inv_hx + (va - vam) * p.inv_hy,
+                                     (ub - ua) * p.inv_hx + (vb - vbm) * p.inv_hy);
   }
   __syncthreads();
 
@@ -359,19 +371,43 @@ k_irfft_grad(const float2* __restrict__ S, const float* __restrict__ uin, const 
   const int c = threadIdx.x % Q, j = threadIdx.x / Q;
   fft_lines_inverse<N, Q>(buf, c, j, tw);
 
+  // Gradient subtraction.  A thread owns one y and a block of 4 consecutive rows: in the line-fastest layout the rows
+  // 2q, 2q+1 of one y are the two halves of one float2, so its pressure values are 3 + 2 conflict-free 64-bit
+  // shared loads (consecutive lanes <-> consecutive y: pitch Q+1 float2), and its global accesses are coalesced
+  // 128-byte rows.  All loads of an item are issued before its first store.
   const ptrdiff_t img = (ptrdiff_t)b * p.img_stride;
   constexpr int NROWS = (2 * Q - 1 > 0) ? 2 * Q - 1 : 1;
-  for (int idx = threadIdx.x; idx < NROWS * N; idx += NT) {
-    const int r = idx / N, y = idx - r * N;
-    const int i = i0 + r;
-    if (i >= p.nx) break;
-    const float p0 = reinterpret_cast<const float*>(&buf[fidx<Q>(y, r >> 1)])[r & 1];
-    const float pxp = reinterpret_cast<const float*>(&buf[fidx<Q>(y, (r + 1) >> 1)])[(r + 1) & 1];
-    const float pyp = reinterpret_cast<const float*>(&buf[fidx<Q>((y + 1) & (N - 1), r >> 1)])[r & 1];
-    const ptrdiff_t off = img + (ptrdiff_t)i * N + y;
-    uout[off] = uin[off] - (pxp - p0) * p.inv_hx;
-    vout[off] = vin[off] - (pyp - p0) * p.inv_hy;
-    if (pout) pout[((size_t)b * p.nx + i) * N + y] = p0;
+  constexpr int NRG = (NROWS + 3) / 4;
+  for (int g = threadIdx.x; g < NRG * N; g += NT) {
+    const int rg = g / N, y = g - rg * N;
+    const int r0 = 4 * rg, q0 = 2 * rg;
+    float uo[4], vo[4];
+    bool on[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      on[k] = (r0 + k < NROWS) && (i0 + r0 + k < p.nx);
+      if (on[k]) {
+        const ptrdiff_t off = img + (ptrdiff_t)(i0 + r0 + k) * N + y;
+        uo[k] = uin[off];
+        vo[k] = vin[off];
+      }
+    }
+    const int yn = (y + 1) & (N - 1);
+    const float2 A0 = buf[fidx<Q>(y, q0)];
+    const float2 A1 = (q0 + 1 < Q) ? buf[fidx<Q>(y, q0 + 1)] : make_float2(0.f, 0.f);
+    const float2 A2 = (q0 + 2 < Q) ? buf[fidx<Q>(y, q0 + 2)] : make_float2(0.f, 0.f);
+    const float2 B0 = buf[fidx<Q>(yn, q0)];
+    const float2 B1 = (q0 + 1 < Q) ? buf[fidx<Q>(yn, q0 + 1)] : make_float2(0.f, 0.f);
+    const float pr[5] = {A0.x, A0.y, A1.x, A1.y, A2.x};
+    const float py[4] = {B0.x, B0.y, B1.x, B1.y};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!on[k]) continue;
+      const ptrdiff_t off = img + (ptrdiff_t)(i0 + r0 + k) * N + y;
+      uout[off] = uo[k] - (pr[k + 1] - pr[k]) * p.inv_hx;
+      vout[off] = vo[k] - (py[k] - pr[k]) * p.inv_hy;
+      if (pout) pout[((size_t)b * p.nx + i0 + r0 + k) * N + y] = pr[k];
+    }
   }
 }
 

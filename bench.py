@@ -399,19 +399,54 @@ def run_slab(args):
         dist.destroy_process_group()
 
 
+def run_datagen(args):
+    """--workload datagen: SURVEY.md 8f row f1 -- the reference's data-generation loop (src/data_generation.py:203-213)
+    at its own sizes (fine 1024^2, coarse 64^2, batch 64): K fine steps + downsample + 16 fine steps + 1 coarse step as
+    one device pipeline; reports fine-grid cell-steps/s and the HBM fraction of the solver (312 - 16 = 296 B/cell-step)."""
+    import torch
+    from ml_accelerated_simulation_b200.data_generation import PairGenerator
+    peaks = _peaks()
+    gen = PairGenerator(high_res=args.grid or 1024, low_res=64, batch_size=args.batch or 64)
+    gen.reset(42, iterations=4)
+    K = args.steps
+    gen.next_pair(steps_between=max(args.warmup, 3))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    (uf, vf), (uc, vc) = gen.next_pair(steps_between=K)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    assert bool(torch.isfinite(uf).all()) and bool(torch.isfinite(uc).all())
+    n = gen.high_res
+    steps = K + gen.inner_step
+    rate = gen.batch * n * n * steps / (ms * 1e-3)
+    print(json.dumps({
+        "metric": "grid cell-steps/sec (data generation: fine solver steps, pair pipeline)", "value": rate, "unit": UNIT,
+        "n_gpus": 1, "steps": steps, "ms_per_step": ms / steps, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"data generation pair: {n}x{n} fine grid, batch {gen.batch}, {K}+{gen.inner_step} fine steps, "
+                               "downsample x16, 1 coarse 64x64 step (reference src/data_generation.py:203-213)"},
+        "roofline": {"bound": "hbm", "achieved": 296 * rate / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": 296 * rate / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                     "note": "algorithmic 296 B/cell-step (74 fp32 words, SURVEY.md 8d); fields 268 MB each > L2"},
+        "full_pair_seconds_at_reference_settings": (gen.steps_between + gen.inner_step) * ms / steps * 1e-3,
+    }), flush=True)
+    gen.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ensemble", choices=["ensemble", "slab"],
+    ap.add_argument("--workload", default="ensemble", choices=["ensemble", "slab", "datagen"],
                     help="ensemble: BASELINE configs[1] (default, the driver's line); slab: configs[4], one big grid over N GPUs")
     ap.add_argument("--nx", type=int, default=8192, help="grid size of the slab workload")
     ap.add_argument("--grid", type=int, default=0, help="ensemble workload: grid size (default 256 = configs[1])")
     ap.add_argument("--batch", type=int, default=0, help="ensemble workload: trajectories per GPU (default 64)")
     args = ap.parse_args()
-    if args.grid or args.batch:          # other BASELINE configs through the same code path (e.g. configs[3]: --grid 128 --batch 512 at 8 GPUs)
+    if args.workload == "ensemble" and (args.grid or args.batch):          # other BASELINE configs through the same code path (e.g. configs[3]: --grid 128 --batch 512 at 8 GPUs)
         global NX, NY, BATCH, WORKLOAD
         NX = NY = args.grid or NX
         BATCH = args.batch or BATCH
@@ -420,6 +455,8 @@ def main():
         run_reference(args)
     elif args.workload == "slab":
         run_slab(args)
+    elif args.workload == "datagen":
+        run_datagen(args)
     else:
         run_ours(args)
 

@@ -116,6 +116,19 @@ int  mlsim_slab_stage_b(mlsim_plan* plan, const void* spec_recv, void* spec_send
 int  mlsim_slab_stage_c(mlsim_plan* plan, const void* spec_recv2, float* uv, float* p_or_null, void* stream);
 int  mlsim_slab_cnn_correct(mlsim_plan* plan, float* uv, double cnn_input_scale, void* stream);
 
+/* ---- data generation, reference src/data_generation.py:91-111,193-213 ----
+ * mlsim_downsample_staggered: downsample_staggered_velocity(fine_grid, coarse_grid, (u, v)) -- u keeps the faces
+ * factor-1::factor along x and is block-averaged over y, v the faces along y averaged over x.  Inputs
+ * [batch][nx][ny], outputs [batch][nx/factor][ny/factor], fp32 device pointers; needs no plan.
+ * mlsim_datagen_pair: one stored training pair, entirely on the device and stream-ordered:
+ *   n_between fine steps (:205-206); (cu, cv) = downsample(u, v) (:209); n_inner fine steps (:210-211);
+ *   one coarse step of (cu, cv) with the coarse plan's dt (:212).  On return (u, v) is the `_f` entry and
+ *   (cu, cv) the `_c` entry of the sample (:219-220). */
+int  mlsim_downsample_staggered(const float* u, const float* v, float* cu, float* cv, int32_t batch, int32_t nx,
+                                int32_t ny, int32_t factor, void* stream);
+int  mlsim_datagen_pair(mlsim_plan* fine, mlsim_plan* coarse, float* u, float* v, float* cu, float* cv,
+                        int32_t n_between, int32_t n_inner, void* stream);
+
 /* ---- introspection ---- */
 /* number of kernel launches one mlsim_step(nsteps=1) issues (solver only, or solver + cnn) */
 int  mlsim_launches_per_step(mlsim_plan* plan, int32_t apply_cnn);

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmlsim_b200.so")
-SOURCES = ["plan.cu", "solver_kernels.cu", "conv_kernels.cu"]
+SOURCES = ["plan.cu", "solver_kernels.cu", "conv_kernels.cu", "datagen_kernels.cu"]
 HEADERS = ["common.cuh", "fft.cuh", "tc05.cuh", "solver_kernels.h", "conv_kernels.h", os.path.join("..", "..", "include", "mlsim.h")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-cudart", "static"]

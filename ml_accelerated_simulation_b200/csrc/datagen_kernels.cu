@@ -1,0 +1,60 @@
+// Data-generation side of the rollout path: the staggered-velocity downsampler that sits
+// between the fine rollout and the paired coarse step in reference src/data_generation.py:91-111,208-212.
+//
+//   downsample_staggered_velocity_component(u, direction, factor):
+//     w   = u sliced along `direction` at indices factor-1, 2*factor-1, ...      (the face that coincides with a coarse face)
+//     out = block mean of w over blocks of `factor` along the OTHER axis
+//   u (offset (1, 1/2)) uses direction 0 (x = array axis 0), v (offset (1/2, 1)) direction 1 (y, contiguous).
+//
+// HBM-bound byte shuffling: u reads 1/factor of its rows (full, coalesced float4), v reads one float per `factor`
+// columns of every row (one 32-byte sector per value: inherent to the layout); outputs are 1/factor^2 of the input.
+#include "common.cuh"
+
+namespace mlsim {
+
+// cu[b][I][J] = mean_{j in [J f, (J+1) f)} u[b][I f + f - 1][j]        one thread per output, f contiguous floats
+// cv[b][I][J] = mean_{i in [I f, (I+1) f)} v[b][i][J f + f - 1]        one thread per output, f rows strided
+__global__ void __launch_bounds__(256)
+k_downsample_staggered(const float* __restrict__ u, const float* __restrict__ v, float* __restrict__ cu,
+                       float* __restrict__ cv, int batch, int nx, int ny, int f) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int cnx = nx / f, cny = ny / f;
+  const size_t nout = (size_t)batch * cnx * cny;
+  const float inv = 1.0f / (float)f;
+  for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < 2 * nout; o += (size_t)gridDim.x * blockDim.x) {
+    const bool is_v = o >= nout;
+    const size_t e = is_v ? o - nout : o;
+    const int J = (int)(e % cny);
+    const int I = (int)((e / cny) % cnx);
+    const size_t b = e / ((size_t)cny * cnx);
+    float s = 0.0f;
+    if (!is_v) {
+      const float* row = u + (b * nx + (size_t)I * f + f - 1) * ny + (size_t)J * f;
+      if ((f & 3) == 0) {
+        for (int k = 0; k < f; k += 4) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(row + k));
+          s += (q.x + q.y) + (q.z + q.w);
+        }
+      } else {
+        for (int k = 0; k < f; ++k) s += __ldg(row + k);
+      }
+      cu[e] = s * inv;
+    } else {
+      const float* col = v + (b * nx + (size_t)I * f) * ny + (size_t)J * f + f - 1;
+      for (int k = 0; k < f; ++k) s += __ldg(col + (size_t)k * ny);
+      cv[e] = s * inv;
+    }
+  }
+}
+
+int launch_downsample_staggered(const float* u, const float* v, float* cu, float* cv, int batch, int nx, int ny, int f,
+                                cudaStream_t st) {
+  const size_t nout = 2 * (size_t)batch * (nx / f) * (ny / f);
+  size_t blocks = (nout + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  MLSIM_CUDA_CHECK(launch_pdl(k_downsample_staggered, dim3((unsigned)blocks), dim3(256), 0, st, u, v, cu, cv, batch, nx, ny, f));
+  return MLSIM_OK;
+}
+
+}  // namespace mlsim

@@ -756,6 +756,41 @@ int mlsim_slab_cnn_correct(mlsim_plan* pl, float* uv, double scale, void* stream
   return MLSIM_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Data generation (reference src/data_generation.py:193-213): one stored pair =
+//   n_between fine steps; coarse_t = downsample(fine); n_inner fine steps; one coarse step of coarse_t
+// all stream-ordered on the device, nothing returns to the host between the pieces.
+// ---------------------------------------------------------------------------------------------------------------
+int mlsim_downsample_staggered(const float* u, const float* v, float* cu, float* cv, int32_t batch, int32_t nx,
+                               int32_t ny, int32_t factor, void* stream) {
+  int rc;
+  if ((rc = check_field(u, "u")) || (rc = check_field(v, "v")) || (rc = check_field(cu, "cu")) || (rc = check_field(cv, "cv"))) return rc;
+  MLSIM_REQUIRE(batch >= 1 && nx >= 1 && ny >= 1 && factor >= 1, "bad shape");
+  MLSIM_REQUIRE(nx % factor == 0 && ny % factor == 0, "`factor` must divide the grid (block_reduce of the reference raises)");
+  MLSIM_REQUIRE(factor == 1 || ((ny % 4) == 0), "ny must be a multiple of 4");
+  return launch_downsample_staggered(u, v, cu, cv, batch, nx, ny, factor, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mlsim_datagen_pair(mlsim_plan* fine, mlsim_plan* coarse, float* u, float* v, float* cu, float* cv,
+                       int32_t n_between, int32_t n_inner, void* stream) {
+  if (!fine || !coarse) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_PLAIN_ONLY(fine);
+  MLSIM_PLAIN_ONLY(coarse);
+  int rc;
+  if ((rc = check_field(u, "u")) || (rc = check_field(v, "v")) || (rc = check_field(cu, "cu")) || (rc = check_field(cv, "cv"))) return rc;
+  const mlsim_config& f = fine->cfg;
+  const mlsim_config& c = coarse->cfg;
+  MLSIM_REQUIRE(n_between >= 0 && n_inner >= 0, "step counts must be >= 0");
+  MLSIM_REQUIRE(f.batch == c.batch && f.device == c.device, "fine and coarse plans must share batch and device");
+  MLSIM_REQUIRE(f.nx % c.nx == 0 && f.ny % c.ny == 0 && f.nx / c.nx == f.ny / c.ny, "coarse grid must divide the fine grid isotropically");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const Chunk fc{0, f.batch}, cc{0, c.batch};
+  if ((rc = run_steps(fine, u, v, nullptr, n_between, 0, 1.0, st, fc))) return rc;
+  if ((rc = launch_downsample_staggered(u, v, cu, cv, f.batch, f.nx, f.ny, f.nx / c.nx, st))) return rc;
+  if ((rc = run_steps(fine, u, v, nullptr, n_inner, 0, 1.0, st, fc))) return rc;
+  return run_steps(coarse, cu, cv, nullptr, 1, 0, 1.0, st, cc);
+}
+
 int mlsim_launches_per_step(mlsim_plan* pl, int32_t apply_cnn) {
   if (!pl) return MLSIM_EINVAL;
   int n = pl->cluster_projection ? 8 : 16;   // 4 stages x (explicit + cluster projection | explicit, div+rfft, column solve, irfft+grad)

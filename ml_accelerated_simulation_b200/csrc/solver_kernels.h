@@ -19,4 +19,7 @@ int launch_irfft_grad(const float2* S, const float* uin, const float* vin, float
 bool project_cluster_supported(const SolverParams& p);
 int launch_project_cluster(float* u, float* v, float* pout, const float* inv_eig, const float2* tw,
                            const SolverParams& p, cudaStream_t st);
+// datagen_kernels.cu
+int launch_downsample_staggered(const float* u, const float* v, float* cu, float* cv, int batch, int nx, int ny, int f,
+                                cudaStream_t st);
 }  // namespace mlsim

@@ -149,3 +149,57 @@ def test_slab_nccl_matches_single_gpu(built_lib, world, tmp_path):
     assert res["cnn_vs_bf16_oracle_u"] <= 4 * res["o32_vs_oracle_u"] + 1e-6, res
     assert res["cnn_vs_bf16_oracle_v"] <= 4 * res["o32_vs_oracle_v"] + 1e-6, res
     assert res["vs_plain_plan_u"] <= 1e-6 and res["vs_plain_plan_v"] <= 1e-6, res
+
+
+# ------------------------------------------------------------------------------------------ data generation (8f)
+def test_downsample_kernel_matches_reference_golden(mlsim, golden_dir):
+    """bit-level: the fp32 kernel against the reference's own functions (golden fp64 vectors rounded to fp32 inputs)."""
+    from ml_accelerated_simulation_b200.data_generation import downsample_fields
+    from oracle import datagen as D
+    gold = st.load_file(os.path.join(golden_dir, "datagen_golden.safetensors"))
+    for name in ("a", "b", "c"):
+        f = int(gold[f"{name}_factor"][0])
+        u32, v32 = gold[f"{name}_u"].float(), gold[f"{name}_v"].float()
+        cu, cv = downsample_fields(u32.to(DEV), v32.to(DEV), f)
+        ou, ov = D.downsample_staggered_velocity(u32.double(), v32.double(), f)
+        assert (cu.double().cpu() - ou).abs().max().item() <= 4e-7 * ou.abs().max().item() + 1e-7
+        assert (cv.double().cpu() - ov).abs().max().item() <= 4e-7 * ov.abs().max().item() + 1e-7
+        # fp64 golden from the reference itself: only the fp32 input rounding separates them
+        assert rel(cu, gold[f"{name}_cu"]) < 2e-7 and rel(cv, gold[f"{name}_cv"]) < 2e-7
+
+
+def test_downsample_api_and_errors(mlsim):
+    from ml_accelerated_simulation_b200 import grids
+    from ml_accelerated_simulation_b200.data_generation import downsample_staggered_velocity
+    fine = grids.Grid((64, 64), domain=((0, 6.28), (0, 6.28)))
+    coarse = grids.Grid((16, 16), domain=((0, 6.28), (0, 6.28)))
+    u = torch.arange(64, dtype=torch.float64, device=DEV)[None, :, None].expand(2, 64, 64).contiguous()
+    v = torch.arange(64, dtype=torch.float64, device=DEV)[None, None, :].expand(2, 64, 64).contiguous()
+    vec = grids.GridVariableVector((grids.GridVariable(u, (1.0, 0.5), fine), grids.GridVariable(v, (0.5, 1.0), fine)))
+    out = downsample_staggered_velocity(fine, coarse, vec)
+    assert out[0].data.dtype == torch.float64 and out[0].data.shape == (2, 16, 16) and out[0].grid is coarse
+    assert torch.equal(out[0].data[0, :, 0].cpu(), torch.arange(3, 64, 4, dtype=torch.float64))      # faces f-1::f along x
+    assert torch.equal(out[1].data[1, 0, :].cpu(), torch.arange(3, 64, 4, dtype=torch.float64))      # faces f-1::f along y
+    bad = grids.Grid((24, 24), domain=((0, 6.28), (0, 6.28)))
+    with pytest.raises(ValueError):
+        downsample_staggered_velocity(fine, bad, vec)
+
+
+def test_datagen_pair_matches_oracle(mlsim):
+    """One stored pair (fine steps, downsample, fine steps, coarse step) as ONE device pipeline vs the oracle's loop."""
+    from ml_accelerated_simulation_b200.data_generation import PairGenerator, pairs_to_dataset
+    from oracle import datagen as D
+    gen = PairGenerator(high_res=256, low_res=64, batch_size=2)
+    fine_cfg, coarse_cfg = S.SolverConfig(nx=256, ny=256), S.SolverConfig(nx=64, ny=64)
+    assert gen.inner_step == 4 and abs(gen.dt - fine_cfg.dt) < 1e-15 and abs(gen.delta_t - coarse_cfg.dt) < 1e-15
+    u64, v64 = S.filtered_velocity_field(fine_cfg, 2, seed=9, iterations=4)
+    gen.u, gen.v = u64.float().to(DEV), v64.float().to(DEV)
+    (uf, vf), (uc, vc) = gen.next_pair(steps_between=3)
+    (ou, ov), (ocu, ocv) = D.datagen_pair(u64, v64, fine_cfg, coarse_cfg, 3, gen.inner_step)
+    (qu, qv), (qcu, qcv) = D.datagen_pair(u64.float(), v64.float(), fine_cfg, coarse_cfg, 3, gen.inner_step)
+    assert rel(uf, ou) <= 4 * rel(qu, ou) + 2e-7 and rel(vf, ov) <= 4 * rel(qv, ov) + 2e-7
+    assert rel(uc, ocu) <= 4 * rel(qcu, ocu) + 2e-7 and rel(vc, ocv) <= 4 * rel(qcv, ocv) + 2e-7
+    ds = pairs_to_dataset([((uf, vf), (uc, vc))], first_index=10)
+    assert sorted(ds) == ["10_c", "10_f", "11_c", "11_f"]
+    assert ds["10_f"].shape == (2, 256, 256) and ds["11_c"].shape == (2, 64, 64) and ds["10_f"].dtype == torch.float64
+    gen.close()

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmlsim_b200.so")
+LIB_PATH = os.environ.get("MLSIM_LIB") or os.path.join(HERE, "libmlsim_b200.so")     # MLSIM_LIB: developer override (tuning variants)
 
 MLSIM_OK = 0
 

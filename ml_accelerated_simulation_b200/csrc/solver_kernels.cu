@@ -279,7 +279,18 @@ __device__ __forceinline__ size_t spec_off(const SolverParams& p, int b, int row
 template <int N> struct RowCfg {
   // lines per CTA such that Q*N/Rmin <= 1024 threads
   static constexpr int RMIN = FftMinRadix<N>::value;
-  static constexpr int Q = (N <= 256) ? 16 : (N <= 1024 ? 8 : (N <= 2048 ? 4 : (N <= 4096 ? 2 : 1)));
+#ifndef MLSIM_Q512
+// lines per CTA for the long row transforms (measured on B200, scripts/gpu_bringup.py t=N,N,B with the variants built by
+// -DMLSIM_Q..=..): 1024: Q=4 beats Q=8 (irfft_grad 0.110 -> 0.085 ms at 1024^2 x 16; 512 threads, 2 CTAs/SM instead of one
+// 1024-thread CTA whose load / transform / store phases cannot overlap); 2048: Q=2 (step 2.06 -> 1.91 ms at 2048^2 x 4)
+#define MLSIM_Q512 8
+#define MLSIM_Q1024 4
+#define MLSIM_Q2048 2
+#define MLSIM_C512 16
+#define MLSIM_C1024 8
+#define MLSIM_C2048 4
+#endif
+  static constexpr int Q = (N <= 256) ? 16 : (N == 512 ? MLSIM_Q512 : (N == 1024 ? MLSIM_Q1024 : (N == 2048 ? MLSIM_Q2048 : (N <= 4096 ? 2 : 1))));
   static constexpr int THREADS = Q * N / RMIN;
   static constexpr size_t SMEM = fft_buf_elems<N, Q>() * sizeof(float2);
 };
@@ -420,7 +431,7 @@ k_irfft_grad(const float2* __restrict__ S, const float* __restrict__ uin, const 
 // ---------------------------------------------------------------------------------------------
 template <int N> struct ColCfg {
   static constexpr int RMIN = FftMinRadix<N>::value;
-  static constexpr int C = (N <= 512) ? 16 : (N <= 1024 ? 8 : 4);
+  static constexpr int C = (N <= 256) ? 16 : (N == 512 ? MLSIM_C512 : (N == 1024 ? MLSIM_C1024 : MLSIM_C2048));
   static constexpr int THREADS = C * N / RMIN;
   static constexpr size_t SMEM = fft_buf_elems<N, C>() * sizeof(float2);
 };

@@ -149,6 +149,10 @@ if __name__ == "__main__":
         section("timing")
         run("t256", lambda: timing(256, 256, 64))
         run("t1024", lambda: timing(1024, 1024, 16))
+    for w in what:
+        if w.startswith("t="):
+            nx_, ny_, b_ = (int(x) for x in w[2:].split(","))
+            run(w, lambda: timing(nx_, ny_, b_))
     if "t128" in what:
         section("timing 128^2 x 512 (config 4 share of one of 8 GPUs)")
         run("t128", lambda: timing(128, 128, 512))

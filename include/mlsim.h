@@ -64,6 +64,15 @@ int  mlsim_plan_destroy(mlsim_plan* plan);
 int  mlsim_cnn_begin    (mlsim_plan* plan, int32_t nlayers);
 int  mlsim_cnn_set_layer(mlsim_plan* plan, int32_t layer, int32_t cin, int32_t cout, int32_t ksize,
                          const void* w_oihw, const void* bias, int32_t src_dtype, int32_t relu_after);
+/* ResNet shortcut (reference src/models/ResNet.py:42-50, ``act(x + y)``): after convolution `layer` and before its
+ * activation add the block input x = output of layer `src_layer` (-1: the 2-channel network input).
+ *   w1x1 == NULL : identity shortcut (hidden layer, same channel count)
+ *   w1x1 != NULL : x passes through the block's 1x1 convolution ``conv1`` first: weights [cout][cin_src], bias [cout];
+ *                  supported for the network input feeding a hidden layer and for an activation feeding the last
+ *                  layer (cout <= 4) -- the two places configs/fullmodels/basicResnet1.json uses it.
+ * With relu_after = 1 on that layer the activation is applied to the sum, as the reference does. */
+int  mlsim_cnn_set_shortcut(mlsim_plan* plan, int32_t layer, int32_t src_layer, const void* w1x1, const void* b1x1,
+                            int32_t src_dtype);
 int  mlsim_cnn_finalize (mlsim_plan* plan);
 
 /* Host-only helper (no CUDA call): pack one layer into the bf16 shared-memory operand image the kernels

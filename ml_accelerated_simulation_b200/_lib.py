@@ -39,6 +39,7 @@ _SIGNATURES = {
     "mlsim_cnn_begin": (C.c_int, [C.c_void_p, C.c_int32]),
     "mlsim_cnn_set_layer": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_int32, C.c_int32]),
+    "mlsim_cnn_set_shortcut": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
     "mlsim_cnn_finalize": (C.c_int, [C.c_void_p]),
     "mlsim_cnn_pack_host": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "mlsim_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double,

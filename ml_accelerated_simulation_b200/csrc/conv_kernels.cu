@@ -207,7 +207,10 @@ template <int NB> struct ConvMidSmem {
   static constexpr int WDY = 8 * LBO_B;
   static constexpr int WBYTES = 3 * WDY;
   static constexpr int BIAS_OFF = WBYTES;
-  static constexpr int STAGE_OFF = ((WBYTES + NB * 4 + 127) / 128) * 128;
+  static constexpr int EXTRA_OFF = WBYTES + NB * 4;                   // 1x1 shortcut weights (fp32)
+  static constexpr int EXTRA_BYTES = (NB == 64) ? 64 * 2 * 4 : 16 * 64 * 4;
+  static constexpr int IMG_BYTES = EXTRA_OFF + EXTRA_BYTES;           // what the host packs and the CTA bulk-copies
+  static constexpr int STAGE_OFF = ((IMG_BYTES + 127) / 128) * 128;
   static constexpr int BAR_OFF = STAGE_OFF + CM_STAGES * CM_STAGE_BYTES;
   static constexpr int NBARS = 2 * CM_STAGES + 2 * CM_SLOTS + 1;
   static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
@@ -222,6 +225,7 @@ k_conv_mid(ConvMidArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sW = smem;
   const float* sBias = reinterpret_cast<const float*>(smem + L::BIAS_OFF);
+  const float* sExtra = reinterpret_cast<const float*>(smem + L::EXTRA_OFF);
   uint8_t* sStage = smem + L::STAGE_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* full = bars;
@@ -251,9 +255,9 @@ k_conv_mid(ConvMidArgs a) {
   const uint32_t tmem = *tmem_slot;
   // the weight image does not depend on the previous kernel: start its bulk copy before waiting for that kernel
   if (tid == 0) {
-    mbar_arrive_expect_tx(wbar, (uint32_t)(L::WBYTES + NB * 4));
+    mbar_arrive_expect_tx(wbar, (uint32_t)L::IMG_BYTES);
     uint32_t off = 0;
-    const uint32_t total = L::WBYTES + NB * 4;
+    const uint32_t total = L::IMG_BYTES;
     while (off < total) {                       // weight image + bias, in pieces of at most 32 KB
       const uint32_t n = (total - off) > 32768u ? 32768u : (total - off);
       bulk_g2s(sW + off, a.wimg + off, n, wbar);
@@ -403,11 +407,29 @@ k_conv_mid(ConvMidArgs a) {
         // last layer: fetch the state this row's correction is added to BEFORE waiting for the accumulator, so the
         // global-load latency hides behind the wait instead of serialising the epilogue
         float u_old = 0.0f, v_old = 0.0f;
+        uint4 rres[LAST ? 8 : 4];                         // shortcut operand, fetched before the accumulator wait
         if constexpr (LAST) {
           if (a.y_nchw == nullptr && y < a.ny) {
             const size_t off0 = (size_t)b * a.img_stride + (size_t)x * a.ny + y;
             u_old = a.u[off0];
             v_old = a.v[off0];
+          }
+          if (a.res_mode == 3 && y < a.ny) {
+            const uint8_t* rrow = reinterpret_cast<const uint8_t*>(a.res) + ((((size_t)b * a.nx + x) * 8) * plane + (size_t)(y + 1)) * 16;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) rres[c] = __ldg(reinterpret_cast<const uint4*>(rrow + (size_t)c * plane * 16));
+          }
+        } else {
+          if (a.res_mode == 1 && y < a.ny) {
+            const uint8_t* rrow = reinterpret_cast<const uint8_t*>(a.res) +
+                                  ((((size_t)b * a.nx + x) * 8 + (size_t)(half * 4)) * plane + (size_t)(y + 1)) * 16;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) rres[c] = __ldg(reinterpret_cast<const uint4*>(rrow + (size_t)c * plane * 16));
+          } else if (a.res_mode == 2 && y < a.ny) {
+            const size_t off0 = (size_t)b * a.img_stride + (size_t)x * a.ny + y;
+            // the network input as the first layer sees it: (u, v) * scale rounded to bf16
+            u_old = __bfloat162float(__float2bfloat16_rn(a.u[off0] * a.sscale));
+            v_old = __bfloat162float(__float2bfloat16_rn(a.v[off0] * a.sscale));
           }
         }
         // ring position `slot` (q); q < 2 also owns mirror slot 6+q
@@ -442,9 +464,24 @@ k_conv_mid(ConvMidArgs a) {
             for (int c = 0; c < 4; ++c) {
               float f[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                f[e] = __uint_as_float(r[c * 8 + e]) + sBias[half * 32 + c * 8 + e];
-                if (a.relu) f[e] = fmaxf(f[e], 0.0f);
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[c * 8 + e]) + sBias[half * 32 + c * 8 + e];
+              if (a.res_mode == 1) {
+                const uint32_t w[4] = {rres[c].x, rres[c].y, rres[c].z, rres[c].w};
+#pragma unroll
+                for (int e2 = 0; e2 < 4; ++e2) {
+                  f[2 * e2] += __uint_as_float(w[e2] << 16);              // bf16 -> f32: low half = even channel
+                  f[2 * e2 + 1] += __uint_as_float(w[e2] & 0xffff0000u);
+                }
+              } else if (a.res_mode == 2) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const int ch = half * 32 + c * 8 + e;
+                  f[e] = fmaf(sExtra[2 * ch], u_old, fmaf(sExtra[2 * ch + 1], v_old, f[e]));
+                }
+              }
+              if (a.relu) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
               }
               uint4 o;
               o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
@@ -470,16 +507,36 @@ k_conv_mid(ConvMidArgs a) {
           if (lane == 0) mbar_arrive(&tempty[slot]);
           if (y < a.ny) {
             const size_t off = (size_t)b * a.img_stride + (size_t)x * a.ny + y;
+            float o[16];
+#pragma unroll
+            for (int co = 0; co < 16; ++co) o[co] = __uint_as_float(r[co]) + sBias[co];
+            if (a.res_mode == 3) {                        // 1x1 shortcut of the block input (64 channels of this pixel)
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const uint32_t w[4] = {rres[c].x, rres[c].y, rres[c].z, rres[c].w};
+#pragma unroll
+                for (int e2 = 0; e2 < 4; ++e2) {
+                  const float x0 = __uint_as_float(w[e2] << 16), x1 = __uint_as_float(w[e2] & 0xffff0000u);
+                  const int ci = c * 8 + 2 * e2;
+#pragma unroll
+                  for (int co = 0; co < 4; ++co)          // the shortcut feeds at most 4 output channels (u, v correction: 2)
+                    if (co < a.cout) o[co] = fmaf(sExtra[co * 64 + ci], x0, fmaf(sExtra[co * 64 + ci + 1], x1, o[co]));
+                }
+              }
+            }
+            if (a.relu) {
+#pragma unroll
+              for (int co = 0; co < 16; ++co) o[co] = fmaxf(o[co], 0.0f);
+            }
             if (a.y_nchw != nullptr) {
               const size_t img = (size_t)a.nx * a.ny;
 #pragma unroll
               for (int co = 0; co < 16; ++co)
-                if (co < a.cout)
-                  a.y_nchw[((size_t)b * a.cout + co) * img + (size_t)x * a.ny + y] = __uint_as_float(r[co]) + sBias[co];
+                if (co < a.cout) a.y_nchw[((size_t)b * a.cout + co) * img + (size_t)x * a.ny + y] = o[co];
             } else {
               // fused correction add (reference src/inference.py:102): v += model(v)
-              a.u[off] = u_old + (__uint_as_float(r[0]) + sBias[0]);
-              a.v[off] = v_old + (__uint_as_float(r[1]) + sBias[1]);
+              a.u[off] = u_old + o[0];
+              a.v[off] = v_old + o[1];
             }
           }
         }
@@ -545,7 +602,9 @@ int launch_conv_last(const ConvMidArgs& a, int sm_count, cudaStream_t st) {
 }
 
 int conv_first_wimg_bytes() { return CF_WBYTES + 64 * 4; }
-int conv_mid_wimg_bytes() { return ConvMidSmem<64>::WBYTES + 64 * 4; }
-int conv_last_wimg_bytes() { return ConvMidSmem<16>::WBYTES + 16 * 4; }
+int conv_mid_wimg_bytes() { return ConvMidSmem<64>::IMG_BYTES; }
+int conv_last_wimg_bytes() { return ConvMidSmem<16>::IMG_BYTES; }
+int conv_mid_extra_off() { return ConvMidSmem<64>::EXTRA_OFF; }
+int conv_last_extra_off() { return ConvMidSmem<16>::EXTRA_OFF; }
 
 }  // namespace mlsim

@@ -28,6 +28,14 @@ struct ConvMidArgs {
   int reverse;                        // traverse work items last-to-first: consecutive layers alternate direction so
                                       // each layer starts on the activations its predecessor wrote last (still in L2)
   unsigned long long* dbg;            // optional [grid][8] cycle counters (nullptr = off): see mlsim_conv_debug
+  // shortcut added before the activation (ResNet blocks, reference src/models/ResNet.py:42-50: act(x + y)):
+  //   0 none
+  //   1 mid layers: identity, `res` = block input in the activation layout
+  //   2 mid layers: 1x1 convolution of the 2-channel network input (u, v) * sscale; weights [64][2] fp32 after the bias
+  //   3 last layer: 1x1 convolution (64 -> cout) of the block input `res`; weights [16][64] fp32 after the bias
+  int res_mode;
+  const __nv_bfloat16* res;
+  float sscale;
 };
 
 int launch_conv_first(const ConvFirstArgs& a, int sm_count, cudaStream_t st);
@@ -35,7 +43,9 @@ int launch_conv_mid(const ConvMidArgs& a, int sm_count, cudaStream_t st);
 int launch_conv_last(const ConvMidArgs& a, int sm_count, cudaStream_t st);
 int conv_pick_strip(int nx, int ny, int batch, int sm_count);
 int conv_first_wimg_bytes();
-int conv_mid_wimg_bytes();
-int conv_last_wimg_bytes();
+int conv_mid_wimg_bytes();        // [operand image][bias 64 f32][1x1 shortcut weights 64x2 f32]
+int conv_last_wimg_bytes();       // [operand image][bias 16 f32][1x1 shortcut weights 16x64 f32]
+int conv_mid_extra_off();         // byte offset of the shortcut weights inside the image
+int conv_last_extra_off();
 
 }  // namespace mlsim

@@ -21,6 +21,11 @@ struct CnnLayer {
   std::vector<double> w, b;   // OIHW, bias
   bool set = false;
   uint8_t* d_wimg = nullptr;
+  // shortcut added before the activation (ResNet blocks): 0 none, 1 identity, 2 1x1 conv of the network input,
+  // 3 1x1 conv of an activation (last layer); src = layer whose output is the block input (-1: network input)
+  int res_mode = 0, res_src = -1;
+  std::vector<double> sw, sb; // 1x1 weights [cout][cin_src], bias [cout]
+  int in_buf = 0, out_buf = 0, res_buf = 0;   // activation buffer assignment (finalize)
 };
 
 }  // namespace mlsim
@@ -56,7 +61,8 @@ struct mlsim_plan {
   // cnn
   std::vector<CnnLayer> layers;
   bool cnn_ready = false;
-  __nv_bfloat16* d_act[2] = {nullptr, nullptr};
+  __nv_bfloat16* d_act[3] = {nullptr, nullptr, nullptr};
+  int nact = 2;
   size_t act_bytes = 0;
   int rs = 32;
   bool cluster_projection = false;      // single-kernel projection (thread-block cluster per image)
@@ -228,6 +234,40 @@ int solver_step(mlsim_plan* pl, float* u, float* v, float* p_or_null, cudaStream
   return project(pl, u, v, p_or_null, st, c);
 }
 
+// The layer chain on `rows` x ny images: first conv from the fp32 state, hidden convs between the activation buffers
+// (with the ResNet shortcuts fused into their epilogues), last conv + shortcut + correction add (or y_nchw).
+int run_cnn_layers(mlsim_plan* pl, const float* u_in, const float* v_in, float* u, float* v, float* y_nchw, double scale,
+                   int rows, int batch, long long img_stride, size_t aoff, cudaStream_t st) {
+  const mlsim_config& c = pl->cfg;
+  const int L = (int)pl->layers.size();
+  int rc;
+  __nv_bfloat16* act[3] = {pl->d_act[0] + aoff, pl->d_act[1] + aoff, pl->d_act[2] ? pl->d_act[2] + aoff : nullptr};
+  ConvFirstArgs f;
+  f.u = u_in; f.v = v_in; f.out = act[pl->layers[0].out_buf]; f.wimg = pl->layers[0].d_wimg; f.scale = (float)scale;
+  f.nx = rows; f.ny = c.ny; f.batch = batch; f.reverse = 0; f.img_stride = img_stride;
+  { ProfScope ps(pl, 4, st); if ((rc = launch_conv_first(f, pl->sm_count, st))) return rc; }
+  for (int l = 1; l < L; ++l) {
+    const CnnLayer& ly = pl->layers[l];
+    ConvMidArgs m;
+    m.in = act[ly.in_buf]; m.out = (l < L - 1) ? act[ly.out_buf] : nullptr;
+    m.u = u; m.v = v; m.y_nchw = y_nchw;
+    m.wimg = ly.d_wimg;
+    m.nx = rows; m.ny = c.ny; m.batch = batch; m.rs = pl->rs; m.img_stride = img_stride;
+    m.cout = ly.cout; m.relu = ly.relu; m.dbg = nullptr;
+    m.reverse = l & 1;                  // layer 0 ascending, layer 1 descending, ...
+    m.res_mode = ly.res_mode; m.res = ly.res_buf >= 0 ? act[ly.res_buf] : nullptr; m.sscale = (float)scale;
+    if (ly.res_mode == 2) { m.u = const_cast<float*>(u_in); m.v = const_cast<float*>(v_in); }   // read-only here
+    if (l < L - 1) {
+      ProfScope ps(pl, 5, st);
+      if ((rc = launch_conv_mid(m, pl->sm_count, st))) return rc;
+    } else {
+      ProfScope ps(pl, 6, st);
+      if ((rc = launch_conv_last(m, pl->sm_count, st))) return rc;
+    }
+  }
+  return MLSIM_OK;
+}
+
 // y = model(stack((u,v),1)*scale); either y_nchw (test hook) or fused u += y0, v += y1.
 int cnn_apply(mlsim_plan* pl, const float* u_in, const float* v_in, float* u, float* v, float* y_nchw, double scale,
               cudaStream_t st, Chunk ck) {
@@ -236,33 +276,8 @@ int cnn_apply(mlsim_plan* pl, const float* u_in, const float* v_in, float* u, fl
     return MLSIM_ESTATE;
   }
   const mlsim_config& c = pl->cfg;
-  const int L = (int)pl->layers.size();
-  int rc;
   const size_t aoff = (size_t)ck.b0 * c.nx * 8 * (size_t)(c.ny + 2) * 8;      // bf16 elements per image block
-  __nv_bfloat16* act[2] = {pl->d_act[0] + aoff, pl->d_act[1] + aoff};
-  ConvFirstArgs f;
-  f.u = u_in; f.v = v_in; f.out = act[0]; f.wimg = pl->layers[0].d_wimg; f.scale = (float)scale;
-  f.nx = c.nx; f.ny = c.ny; f.batch = ck.nb; f.reverse = 0; f.img_stride = (long long)c.nx * c.ny;
-  { ProfScope ps(pl, 4, st); if ((rc = launch_conv_first(f, pl->sm_count, st))) return rc; }
-  int cur = 0;
-  for (int l = 1; l < L; ++l) {
-    ConvMidArgs m;
-    m.in = act[cur]; m.out = act[cur ^ 1];
-    m.u = u; m.v = v; m.y_nchw = y_nchw;
-    m.wimg = pl->layers[l].d_wimg;
-    m.nx = c.nx; m.ny = c.ny; m.batch = ck.nb; m.rs = pl->rs; m.img_stride = (long long)c.nx * c.ny;
-    m.cout = pl->layers[l].cout; m.relu = pl->layers[l].relu; m.dbg = nullptr;
-    m.reverse = l & 1;                  // layer 0 ascending, layer 1 descending, ...
-    if (l < L - 1) {
-      ProfScope ps(pl, 5, st);
-      if ((rc = launch_conv_mid(m, pl->sm_count, st))) return rc;
-    } else {
-      ProfScope ps(pl, 6, st);
-      if ((rc = launch_conv_last(m, pl->sm_count, st))) return rc;
-    }
-    cur ^= 1;
-  }
-  return MLSIM_OK;
+  return run_cnn_layers(pl, u_in, v_in, u, v, y_nchw, scale, c.nx, ck.nb, (long long)c.nx * c.ny, aoff, st);
 }
 
 // nsteps of {solver step; optional correction} on one block of the batch (pointers already offset to it)
@@ -398,7 +413,7 @@ int mlsim_plan_destroy(mlsim_plan* pl) {
   cudaSetDevice(pl->cfg.device);
   cudaDeviceSynchronize();
   void* ptrs[] = {pl->d_forcing, pl->d_inv_eig, pl->d_twx, pl->d_twy, pl->d_w1u, pl->d_w1v, pl->d_w2u, pl->d_w2v,
-                  pl->d_accu, pl->d_accv, pl->d_spec, pl->d_tw_n2, pl->d_split, pl->d_act[0], pl->d_act[1], pl->d_hu, pl->d_hv, pl->d_hp,
+                  pl->d_accu, pl->d_accv, pl->d_spec, pl->d_tw_n2, pl->d_split, pl->d_act[0], pl->d_act[1], pl->d_act[2], pl->d_hu, pl->d_hv, pl->d_hp,
                   pl->d_tu, pl->d_tv, pl->d_dbg};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& l : pl->layers) if (l.d_wimg) cudaFree(l.d_wimg);
@@ -451,7 +466,8 @@ int64_t mlsim_cnn_pack_host(int32_t kind, int32_t cin, int32_t cout, const doubl
           }
     nbias = NB;
   }
-  float* bq = reinterpret_cast<float*>(img + need - (int64_t)nbias * 4);
+  const int64_t bias_off = (kind == 0) ? need - (int64_t)nbias * 4 : (kind == 1 ? conv_mid_extra_off() : conv_last_extra_off()) - (int64_t)nbias * 4;
+  float* bq = reinterpret_cast<float*>(img + bias_off);
   for (int i = 0; i < nbias; ++i) bq[i] = (i < cout) ? (float)bias[i] : 0.0f;
   return need;
 }
@@ -475,7 +491,7 @@ int mlsim_cnn_set_layer(mlsim_plan* pl, int32_t layer, int32_t cin, int32_t cout
   if (layer == 0) MLSIM_REQUIRE(cin == 2 && cout >= 1 && cout <= 64, "first layer must be 2 -> (1..64) channels");
   else if (layer == L - 1) MLSIM_REQUIRE(cin >= 1 && cin <= 64 && cout >= 1 && cout <= 16, "last layer must be (1..64) -> (1..16) channels");
   else MLSIM_REQUIRE(cin >= 1 && cin <= 64 && cout >= 1 && cout <= 64, "hidden layers must be (1..64) -> (1..64) channels");
-  MLSIM_REQUIRE((relu_after != 0) == (layer != L - 1), "ReLU after every layer but the last (reference CNN.forward)");
+  if (layer != L - 1) MLSIM_REQUIRE(relu_after != 0, "ReLU after every hidden layer (reference CNN.forward / ResNetBlock.forward)");
   CnnLayer& l = pl->layers[layer];
   l.cin = cin; l.cout = cout; l.relu = relu_after ? 1 : 0;
   const size_t nw = (size_t)cout * cin * 9;
@@ -488,6 +504,34 @@ int mlsim_cnn_set_layer(mlsim_plan* pl, int32_t layer, int32_t cin, int32_t cout
     for (int i = 0; i < cout; ++i) l.b[i] = ((const float*)bias)[i];
   }
   l.set = true;
+  l.res_mode = 0; l.res_src = -1; l.sw.clear(); l.sb.clear();
+  pl->cnn_ready = false;
+  return MLSIM_OK;
+}
+
+int mlsim_cnn_set_shortcut(mlsim_plan* pl, int32_t layer, int32_t src_layer, const void* w1x1, const void* b1x1,
+                           int32_t src_dtype) {
+  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  const int L = (int)pl->layers.size();
+  MLSIM_REQUIRE(layer >= 1 && layer < L && pl->layers[layer].set, "set the layer before its shortcut (layer >= 1)");
+  MLSIM_REQUIRE(src_layer >= -1 && src_layer < layer - 1, "the shortcut source must be an earlier layer's output (-1: network input)");
+  MLSIM_REQUIRE(src_dtype == 0 || src_dtype == 1, "src_dtype: 0 = f32, 1 = f64");
+  CnnLayer& l = pl->layers[layer];
+  const int cs = (src_layer < 0) ? 2 : pl->layers[src_layer].cout;
+  if (w1x1 == nullptr) {
+    MLSIM_REQUIRE(src_layer >= 0 && layer < L - 1 && cs == l.cout, "identity shortcut: hidden layer, source with the same channel count");
+    l.res_mode = 1;
+  } else {
+    MLSIM_REQUIRE(b1x1 != nullptr, "1x1 shortcut needs a bias");
+    if (src_layer < 0) MLSIM_REQUIRE(layer < L - 1, "1x1 shortcut of the network input is supported on hidden layers");
+    else MLSIM_REQUIRE(layer == L - 1 && l.cout <= 4, "1x1 shortcut of an activation is supported on the last layer (<= 4 output channels)");
+    l.res_mode = (src_layer < 0) ? 2 : 3;
+    const size_t nw = (size_t)l.cout * cs;
+    l.sw.resize(nw); l.sb.resize(l.cout);
+    for (size_t i = 0; i < nw; ++i) l.sw[i] = src_dtype == 1 ? ((const double*)w1x1)[i] : (double)((const float*)w1x1)[i];
+    for (int i = 0; i < l.cout; ++i) l.sb[i] = src_dtype == 1 ? ((const double*)b1x1)[i] : (double)((const float*)b1x1)[i];
+  }
+  l.res_src = src_layer;
   pl->cnn_ready = false;
   return MLSIM_OK;
 }
@@ -505,17 +549,59 @@ int mlsim_cnn_finalize(mlsim_plan* pl) {
     CnnLayer& l = pl->layers[li];
     const int kind = (li == 0) ? 0 : (li == L - 1 ? 2 : 1);
     std::vector<uint8_t> img((size_t)mlsim_cnn_pack_host(kind, l.cin, l.cout, nullptr, nullptr, nullptr, 0));
-    if (mlsim_cnn_pack_host(kind, l.cin, l.cout, l.w.data(), l.b.data(), img.data(), (int64_t)img.size()) < 0) return MLSIM_EINVAL;
+    std::vector<double> bias = l.b;
+    if (l.res_mode >= 2) for (int i = 0; i < l.cout; ++i) bias[i] += l.sb[i];     // the shortcut's bias rides on the layer's
+    if (mlsim_cnn_pack_host(kind, l.cin, l.cout, l.w.data(), bias.data(), img.data(), (int64_t)img.size()) < 0) return MLSIM_EINVAL;
+    if (l.res_mode >= 2) {
+      // 1x1 weights, rounded to bf16 like every other conv weight (kept as fp32 in the image: CUDA-core epilogue math)
+      float* ex = reinterpret_cast<float*>(img.data() + (kind == 1 ? conv_mid_extra_off() : conv_last_extra_off()));
+      const int cs = (l.res_src < 0) ? 2 : pl->layers[l.res_src].cout;
+      for (int co = 0; co < l.cout; ++co)
+        for (int ci = 0; ci < cs; ++ci) {
+          const uint16_t h = f32_to_bf16_rne((float)l.sw[(size_t)co * cs + ci]);
+          const uint32_t bits = (uint32_t)h << 16;
+          float f; memcpy(&f, &bits, 4);
+          ex[(size_t)co * (kind == 1 ? 2 : 64) + ci] = f;
+        }
+    }
     if (l.d_wimg) { cudaFree(l.d_wimg); l.d_wimg = nullptr; }
     int rc = dev_alloc(pl, &l.d_wimg, img.size());
     if (rc) return rc;
     MLSIM_CUDA_CHECK(cudaMemcpy(l.d_wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
   }
+  // activation buffer assignment: the output of a layer must not overwrite its input nor a block input that a later
+  // shortcut still needs (two buffers for a plain chain, three with shortcuts)
+  {
+    int need = 2;
+    for (auto& l : pl->layers) if (l.res_mode == 1 || l.res_mode == 3) need = 3;
+    std::vector<int> buf_of(L, -1);
+    for (int li = 0; li < L; ++li) {
+      CnnLayer& l = pl->layers[li];
+      l.in_buf = li > 0 ? buf_of[li - 1] : -1;
+      l.res_buf = (l.res_mode == 1 || l.res_mode == 3) ? buf_of[l.res_src] : -1;
+      int pick = -1;
+      for (int b = 0; b < need && pick < 0; ++b) {
+        bool busy = (b == l.in_buf);
+        for (int m = li; m < L && !busy; ++m) {           // block inputs still to be consumed (including by this layer)
+          const CnnLayer& q = pl->layers[m];
+          if ((q.res_mode == 1 || q.res_mode == 3) && q.res_src < li && buf_of[q.res_src] == b) busy = true;
+        }
+        if (!busy) pick = b;
+      }
+      MLSIM_REQUIRE(pick >= 0 || li == L - 1, "more than one outstanding shortcut source: not supported");
+      l.out_buf = pick;
+      buf_of[li] = pick;
+    }
+    if (need > pl->nact && pl->d_act[0]) {       // re-finalised with a deeper buffer requirement: reallocate
+      for (int i = 0; i < 3; ++i) if (pl->d_act[i]) { cudaFree(pl->d_act[i]); pl->d_act[i] = nullptr; }
+    }
+    pl->nact = need;
+  }
   if (!pl->d_act[0]) {
     const mlsim_config& c = pl->cfg;
     const int act_rows = pl->slab ? pl->nxl + 2 * MLSIM_SLAB_CNN_HALO : c.nx;
     pl->act_bytes = (size_t)c.batch * act_rows * 8 * (size_t)(c.ny + 2) * 16;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < pl->nact; ++i) {
       uint8_t* p = nullptr;
       int rc = dev_alloc(pl, &p, pl->act_bytes);
       if (rc) return rc;
@@ -735,25 +821,7 @@ int mlsim_slab_cnn_correct(mlsim_plan* pl, float* uv, double scale, void* stream
   const UV o = uv_origin(pl, uv);
   float* u = o.u + (ptrdiff_t)lo * c.ny;
   float* v = o.v + (ptrdiff_t)lo * c.ny;
-  const int L = (int)pl->layers.size();
-  ConvFirstArgs f;
-  f.u = u; f.v = v; f.out = pl->d_act[0]; f.wimg = pl->layers[0].d_wimg; f.scale = (float)scale;
-  f.nx = rows; f.ny = c.ny; f.batch = c.batch; f.reverse = 0; f.img_stride = pl->sp.img_stride;
-  { ProfScope ps(pl, 4, st); if ((rc = launch_conv_first(f, pl->sm_count, st))) return rc; }
-  int cur = 0;
-  for (int l = 1; l < L; ++l) {
-    ConvMidArgs m;
-    m.in = pl->d_act[cur]; m.out = pl->d_act[cur ^ 1];
-    m.u = u; m.v = v; m.y_nchw = nullptr;
-    m.wimg = pl->layers[l].d_wimg;
-    m.nx = rows; m.ny = c.ny; m.batch = c.batch; m.rs = pl->rs; m.img_stride = pl->sp.img_stride;
-    m.cout = pl->layers[l].cout; m.relu = pl->layers[l].relu; m.dbg = nullptr;
-    m.reverse = l & 1;
-    if (l < L - 1) { ProfScope ps(pl, 5, st); if ((rc = launch_conv_mid(m, pl->sm_count, st))) return rc; }
-    else { ProfScope ps(pl, 6, st); if ((rc = launch_conv_last(m, pl->sm_count, st))) return rc; }
-    cur ^= 1;
-  }
-  return MLSIM_OK;
+  return run_cnn_layers(pl, u, v, u, v, nullptr, scale, rows, c.batch, pl->sp.img_stride, 0, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -890,7 +958,7 @@ int mlsim_time_kernel(mlsim_plan* pl, int32_t which, int32_t warmup, int32_t ite
         ConvMidArgs m;
         m.in = pl->d_act[0]; m.out = pl->d_act[1]; m.u = pl->d_w1u; m.v = pl->d_w1v; m.y_nchw = nullptr;
         m.wimg = pl->layers[l].d_wimg; m.nx = c.nx; m.ny = c.ny; m.batch = c.batch; m.rs = pl->rs;
-        m.img_stride = (long long)c.nx * c.ny;
+        m.img_stride = (long long)c.nx * c.ny; m.res_mode = 0; m.res = nullptr; m.sscale = 1.0f;
         m.cout = pl->layers[l].cout; m.relu = pl->layers[l].relu; m.dbg = pl->d_dbg; m.reverse = 0;
         return (which == 5) ? launch_conv_mid(m, pl->sm_count, st) : launch_conv_last(m, pl->sm_count, st);
       }

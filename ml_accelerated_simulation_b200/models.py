@@ -86,26 +86,101 @@ class CNN(nn.Module):
         return tuple(int(p._version) for p in list(self.parameters()) + list(self.buffers()))
 
 
+_RESNET_NAMES = ("RESNETBLOCK", "RESNETBASICBLOCK", "RESNETBOTTLENECKBLOCK")     # reference src/models/tools.py:93-95
+
+
+class ResNetBlock(nn.Module):
+    """Parameter container with the reference ResNetBlock's layout (src/models/ResNet.py:26-39): every layer is
+    ``Sequential(Conv2d, BatchNorm2d)``, optional 1x1 ``conv1`` on the block input; forward = ``act(x + y)`` (:41-50).
+    Only the basic-block shape is on the B200 path: 3x3 / stride 1 / padding 1 / groups 1, ReLU, two or more layers."""
+
+    def __init__(self, config: dict):
+        super().__init__()
+        chans = _channels(config["structures"])
+        n = len(chans) - 1
+        ks = _as_list(config["kernel_sizes"], n, "kernel_sizes")
+        st = _as_list(config["strides"], n, "strides")
+        pd = _as_list(config["paddings"], n, "paddings")
+        gr = _as_list(config["group"], n, "group")
+        self.dropouts = _as_list(config["dropouts"], n, "dropouts")
+        if str(config["activation_func"]).lower() != "relu":
+            raise NotImplementedError("only ReLU ResNet blocks are on the B200 hot path")
+        if any(k != 3 for k in ks) or any(s != 1 for s in st) or any(p != 1 for p in pd) or any(g != 1 for g in gr):
+            raise NotImplementedError("only 3x3 / stride 1 / padding 1 / groups 1 convolutions are on the B200 hot path")
+        if n < 2:
+            raise NotImplementedError("ResNet blocks on the B200 path need at least two conv layers")
+        self.channels = chans
+        self.layers = nn.ModuleList([nn.Sequential(nn.Conv2d(chans[i], chans[i + 1], 3, 1, 1),
+                                                   nn.BatchNorm2d(chans[i + 1])) for i in range(n)])
+        self.conv1 = nn.Conv2d(chans[0], chans[-1], kernel_size=1) if config.get("1x1_conv", False) else None
+        if self.conv1 is None and chans[0] != chans[-1]:
+            raise ValueError("identity shortcut needs in_channels == out_channels (the reference would fail to add)")
+
+    def folded_layers(self) -> List[Tuple[torch.Tensor, torch.Tensor]]:
+        out = []
+        for layer in self.layers:
+            conv, bn = layer[0], layer[1]
+            w = conv.weight.detach().double().cpu()
+            b = conv.bias.detach().double().cpu()
+            scale = bn.weight.detach().double().cpu() / torch.sqrt(bn.running_var.detach().double().cpu() + bn.eps)
+            out.append(((w * scale[:, None, None, None]).contiguous(),
+                        ((b - bn.running_mean.detach().double().cpu()) * scale + bn.bias.detach().double().cpu()).contiguous()))
+        return out
+
+
 class buildModel(nn.Module):
-    """Drop-in for the reference's ``buildModel(configs)`` restricted to a single CNN block."""
+    """Drop-in for the reference's ``buildModel(configs)`` (src/models/modelbuilder.py:5-31) for the conv families on the
+    B200 path: one CNN block (e.g. baselines/MLACFD.json) or a chain of ResNet basic blocks (e.g. basicResnet1.json)."""
 
     def __init__(self, configs: Sequence[dict]):
         super().__init__()
-        if len(configs) != 1 or str(configs[0]["name"]).upper() != "CNN":
-            raise NotImplementedError("the B200 hot path covers buildModel([CNN block]) (e.g. MLACFD.json)")
+        names = [str(c["name"]).upper() for c in configs]
+        if len(configs) == 1 and names[0] == "CNN":
+            self.family = "cnn"
+            self.models = nn.ModuleList([CNN(configs[0])])
+        elif configs and all(nm in _RESNET_NAMES for nm in names):
+            self.family = "resnet"
+            configs = [dict(c) for c in configs]
+            for i in range(len(configs) - 1):             # the reference corrects mismatching channel counts (:12-15)
+                configs[i + 1]["structures"] = dict(configs[i + 1]["structures"])
+                configs[i + 1]["structures"]["in_channels"] = configs[i]["structures"]["out_channels"]
+            self.models = nn.ModuleList([ResNetBlock(c) for c in configs])
+            ch = [b.channels for b in self.models]
+            if ch[0][0] != 2 or ch[-1][-1] > 4 or any(c > 64 for b in ch for c in b[1:-1]) or any(b[-1] > 64 for b in ch[:-1]):
+                raise NotImplementedError("supported ResNet shapes: 2 -> (<=64)* -> (<=4) channels")
+        else:
+            raise NotImplementedError("the B200 hot path covers buildModel([CNN block]) and chains of ResNet basic blocks")
         self.models_name = [c["name"] for c in configs]
-        self.models = nn.ModuleList([CNN(configs[0])])
         self.input_scale = 1.0
         self._plans: Dict[tuple, Tuple[Plan, tuple]] = {}
         self.eval()
 
     @property
-    def cnn(self) -> CNN:
+    def cnn(self):
         return self.models[0]
 
-    def attach(self, plan: Plan) -> None:
+    def param_version(self) -> tuple:
+        return tuple(int(p._version) for p in list(self.parameters()) + list(self.buffers()))
+
+    def flat_layers(self):
+        """(layers, shortcuts, final_relu) in the form Plan.set_cnn takes."""
+        if self.family == "cnn":
+            return self.cnn.folded_layers(), None, False
+        layers, shortcuts = [], {}
+        for blk in self.models:
+            start = len(layers)
+            layers += blk.folded_layers()
+            end = len(layers) - 1
+            if blk.conv1 is None:
+                shortcuts[end] = (start - 1, None, None)
+            else:
+                shortcuts[end] = (start - 1, blk.conv1.weight.detach().double().cpu(), blk.conv1.bias.detach().double().cpu())
+        return layers, shortcuts, True
+
+    def attach(self, plan) -> None:
         """Upload (BN-folded, bf16-packed) weights into ``plan`` so plan.step(..., apply_cnn=True) can run."""
-        plan.set_cnn(self.cnn.folded_layers())
+        layers, shortcuts, final_relu = self.flat_layers()
+        plan.set_cnn(layers, shortcuts, final_relu)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.training:
@@ -116,7 +191,7 @@ class buildModel(nn.Module):
             raise ValueError("expected input [batch, 2, nx, ny]")
         b, _, nx, ny = x.shape
         key = (b, nx, ny, x.device.index)
-        ver = self.cnn.param_version()
+        ver = self.param_version()
         entry = self._plans.get(key)
         if entry is None or entry[1] != ver:
             plan = entry[0] if entry is not None else Plan(PlanConfig(nx=nx, ny=ny, batch=b, dt=1.0,

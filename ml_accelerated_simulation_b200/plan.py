@@ -96,8 +96,10 @@ class Plan:
         return torch.cuda.current_stream().cuda_stream
 
     # ------------------------------------------------------------------ correction network
-    def set_cnn(self, layers: Sequence[Tuple[torch.Tensor, torch.Tensor]]):
-        """layers: [(weight[cout,cin,3,3], bias[cout]), ...] on the host, any float dtype (BN already folded)."""
+    def set_cnn(self, layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], shortcuts=None, final_relu: bool = False):
+        """layers: [(weight[cout,cin,3,3], bias[cout]), ...] on the host, any float dtype (BN already folded).
+        shortcuts: {layer: (src_layer, w1x1 | None, b1x1 | None)} -- ResNet ``act(x + y)`` (mlsim_cnn_set_shortcut);
+        final_relu: activation after the last layer too (ResNet blocks end with one, CNN blocks do not)."""
         n = len(layers)
         _lib.check(self._lib.mlsim_cnn_begin(self._h, n))
         for i, (w, b) in enumerate(layers):
@@ -107,7 +109,14 @@ class Plan:
             if kh != 3 or kw != 3:
                 raise ValueError("only 3x3 convolutions are on the hot path")
             _lib.check(self._lib.mlsim_cnn_set_layer(self._h, i, cin, cout, 3, w64.data_ptr(), b64.data_ptr(), 1,
-                                                      1 if i < n - 1 else 0))
+                                                      1 if (i < n - 1 or final_relu) else 0))
+        for layer, (src, w1, b1) in sorted((shortcuts or {}).items()):
+            if w1 is None:
+                _lib.check(self._lib.mlsim_cnn_set_shortcut(self._h, layer, src, None, None, 1))
+            else:
+                w64 = w1.detach().to("cpu", torch.float64).reshape(w1.shape[0], -1).contiguous()
+                b64 = b1.detach().to("cpu", torch.float64).contiguous()
+                _lib.check(self._lib.mlsim_cnn_set_shortcut(self._h, layer, src, w64.data_ptr(), b64.data_ptr(), 1))
         _lib.check(self._lib.mlsim_cnn_finalize(self._h))
         self.cnn_out_channels = int(layers[-1][0].shape[0])
         self.has_cnn = True

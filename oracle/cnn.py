@@ -90,13 +90,57 @@ def cnn_block_forward(x: torch.Tensor, config: dict, sd: Dict[str, torch.Tensor]
     return x
 
 
+def resnet_block_forward(x: torch.Tensor, config: dict, sd: Dict[str, torch.Tensor], prefix: str,
+                         round_bf16: bool = False, last_block: bool = False) -> torch.Tensor:
+    """Eval-mode forward of one ``ResNetBlock`` (src/models/ResNet.py:26-50): every layer is Conv2d + BatchNorm2d
+    (:31), activation after every layer but the last (:44-46), optional 1x1 ``conv1`` on the block input (:33-39,
+    :48-49), output ``act(x + y)`` (:50).
+
+    ``round_bf16`` as in cnn_block_forward: conv weights (3x3 and 1x1) and every stored activation -- including each
+    block's output, except the network's final output (``last_block``) -- are rounded to bf16; ``x`` must already be
+    rounded by the caller (it is the previous block's stored output or the rounded network input)."""
+    chans = structure_to_list(config["structures"])
+    n = len(chans) - 1
+    ks = param_to_list(config["kernel_sizes"], n)
+    st = param_to_list(config["strides"], n)
+    pd = param_to_list(config["paddings"], n)
+    gr = param_to_list(config["group"], n)
+    act = _act(config["activation_func"])
+
+    def q(t):
+        return t.to(torch.bfloat16).to(t.dtype) if round_bf16 else t
+
+    y = x
+    for i in range(n):
+        cp, bp = f"{prefix}layers.{i}.0.", f"{prefix}layers.{i}.1."
+        w, b = sd[cp + "weight"].to(x.dtype), sd[cp + "bias"].to(x.dtype)
+        g, beta = sd[bp + "weight"].to(x.dtype), sd[bp + "bias"].to(x.dtype)
+        mean, var = sd[bp + "running_mean"].to(x.dtype), sd[bp + "running_var"].to(x.dtype)
+        scale = g / torch.sqrt(var + 1e-5)
+        w = w * scale[:, None, None, None]
+        b = (b - mean) * scale + beta
+        y = F.conv2d(y, q(w), b, stride=st[i], padding=pd[i], groups=gr[i])
+        if i < n - 1:
+            y = q(act(y))
+    if config.get("1x1_conv", False):
+        x = F.conv2d(x, q(sd[prefix + "conv1.weight"].to(x.dtype)), sd[prefix + "conv1.bias"].to(x.dtype))
+    out = act(x + y)
+    return out if last_block else q(out)
+
+
 def model_forward(x: torch.Tensor, configs: Sequence[dict], sd: Dict[str, torch.Tensor],
                   round_bf16: bool = False) -> torch.Tensor:
-    """buildModel.forward for a list of CNN blocks (src/models/modelbuilder.py:21-31)."""
+    """buildModel.forward for a list of CNN / ResNet blocks (src/models/modelbuilder.py:21-31)."""
     for m, config in enumerate(configs):
-        if config["name"].upper() != "CNN":
-            raise ValueError(f"oracle covers only CNN blocks, got {config['name']}")
-        x = cnn_block_forward(x, config, sd, f"models.{m}.", round_bf16)
+        name = config["name"].upper()
+        if name == "CNN":
+            x = cnn_block_forward(x, config, sd, f"models.{m}.", round_bf16)
+        elif name in ("RESNETBLOCK", "RESNETBASICBLOCK", "RESNETBOTTLENECKBLOCK"):        # src/models/tools.py:93-95
+            if m == 0 and round_bf16:
+                x = x.to(torch.bfloat16).to(x.dtype)
+            x = resnet_block_forward(x, config, sd, f"models.{m}.", round_bf16, last_block=(m == len(configs) - 1))
+        else:
+            raise ValueError(f"oracle covers only CNN and ResNet blocks, got {config['name']}")
     return x
 
 

@@ -68,13 +68,13 @@ def test_pack_host_sizes_and_bias(built_lib):
     from ml_accelerated_simulation_b200 import _lib
     lib = _lib.load()
     assert lib.mlsim_cnn_pack_host(0, 2, 64, None, None, None, 0) == 4 * 64 * 16 + 256
-    assert lib.mlsim_cnn_pack_host(1, 64, 64, None, None, None, 0) == 9 * 64 * 64 * 2 + 256
-    assert lib.mlsim_cnn_pack_host(2, 64, 2, None, None, None, 0) == 3 * 8 * 48 * 16 + 64
+    assert lib.mlsim_cnn_pack_host(1, 64, 64, None, None, None, 0) == 9 * 64 * 64 * 2 + 256 + 64 * 2 * 4     # + bias + 1x1 shortcut slot
+    assert lib.mlsim_cnn_pack_host(2, 64, 2, None, None, None, 0) == 3 * 8 * 48 * 16 + 64 + 16 * 64 * 4
     w = np.arange(2 * 64 * 9, dtype=np.float64).reshape(2, 64, 3, 3) / 1000.0
     b = np.array([0.25, -1.5])
     n = lib.mlsim_cnn_pack_host(2, 64, 2, None, None, None, 0)
     out = np.zeros(n, dtype=np.uint8)
     assert lib.mlsim_cnn_pack_host(2, 64, 2, w.ctypes.data, b.ctypes.data, out.ctypes.data, n) == n
-    bias = out[-64:].view(np.float32)
+    bias = out[3 * 8 * 48 * 16:3 * 8 * 48 * 16 + 64].view(np.float32)
     assert bias[0] == 0.25 and bias[1] == -1.5 and not bias[2:].any()
     assert lib.mlsim_cnn_pack_host(2, 64, 2, w.ctypes.data, b.ctypes.data, out.ctypes.data, 8) < 0

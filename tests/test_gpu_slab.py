@@ -203,3 +203,57 @@ def test_datagen_pair_matches_oracle(mlsim):
     assert sorted(ds) == ["10_c", "10_f", "11_c", "11_f"]
     assert ds["10_f"].shape == (2, 256, 256) and ds["11_c"].shape == (2, 64, 64) and ds["10_f"].dtype == torch.float64
     gen.close()
+
+
+# ------------------------------------------------------------------------------------------ ResNet correction net (8f f4)
+@pytest.fixture(scope="module")
+def resnet(golden_dir):
+    cfg = json.load(open(os.path.join(golden_dir, "basicResnet1.json")))
+    sd = st.load_file(os.path.join(golden_dir, "resnet_weights.safetensors"))
+    return cfg, sd
+
+
+def test_resnet_forward_matches_reference_golden(mlsim, resnet, golden_dir):
+    """buildModel(basicResnet1.json)(x) on the tcgen05 kernels (BN folded, shortcuts fused in the epilogues) against the
+    reference's own fp64 forward.  Tolerance (self-calibrating, as for the solver): through 12 layers with shortcuts the
+    bf16 rounding decisions of an fp32-accumulating evaluation flip against the fp64-accumulating emulation, so
+    relL2(K, E64) <= 2 * relL2(E32, E64) + 2e-4, where E32 is the SAME bf16-emulating oracle run in fp32 on the CPU
+    (measured: K 1.6e-3, E32 2.5e-3; two CPU fp32 evaluations with different summation orders differ by 1.1e-3)."""
+    from ml_accelerated_simulation_b200 import models
+    cfg, sd = resnet
+    g = st.load_file(os.path.join(golden_dir, "resnet_golden.safetensors"))
+    model = models.buildModel(cfg)
+    model.load_state_dict(sd)
+    y = model(g["x"].to(DEV))
+    emu = OC.model_forward(g["x"], cfg, sd, round_bf16=True)
+    sd32 = {k: (t.float() if t.dtype.is_floating_point else t) for k, t in sd.items()}
+    emu32 = OC.model_forward(g["x"].float(), cfg, sd32, round_bf16=True)
+    assert y.shape == g["y"].shape
+    assert rel(y, emu) <= 2 * rel(emu32, emu) + 2e-4, (rel(y, emu), rel(emu32, emu), rel(emu, g["y"]))
+    assert rel(y, g["y"]) <= 2 * rel(emu, g["y"]) + 1e-3
+
+
+@pytest.mark.parametrize("nx,ny,batch", [(64, 64, 2), (128, 256, 1)])
+def test_resnet_rollout_matches_oracle(mlsim, resnet, nx, ny, batch):
+    from ml_accelerated_simulation_b200 import models
+    cfg, sd = resnet
+    scfg = S.SolverConfig(nx=nx, ny=ny)
+    u64, v64 = S.filtered_velocity_field(scfg, batch, seed=21, iterations=4)
+    model = models.buildModel(cfg)
+    model.load_state_dict(sd)
+    plan = mlsim.Plan(mlsim.PlanConfig(nx=nx, ny=ny, batch=batch))
+    model.attach(plan)
+    u, v = u64.float().to(DEV), v64.float().to(DEV)
+    # one correction alone, then a short rollout (the untrained net adds O(0.5) per step; 2 steps stay finite)
+    y = plan.cnn_forward(u, v, 1.0)
+    x = torch.stack((u64, v64), 1)
+    emu = OC.model_forward(x.float().double(), cfg, sd, round_bf16=True)
+    sd32 = {k: (t.float() if t.dtype.is_floating_point else t) for k, t in sd.items()}
+    emu32 = OC.model_forward(x.float(), cfg, sd32, round_bf16=True)
+    assert rel(y, emu) <= 2 * rel(emu32, emu) + 2e-4, (rel(y, emu), rel(emu32, emu))
+    plan.step(u, v, nsteps=2, apply_cnn=True, input_scale=1.0 / 7.0)
+    eu, ev, _ = OC.rollout(u64, v64, scfg, 2, cfg, sd, 1.0 / 7.0, round_bf16=True)
+    qu, qv, _ = OC.rollout(u64.float(), v64.float(), scfg, 2, cfg, sd32, 1.0 / 7.0, round_bf16=True)
+    assert torch.isfinite(u).all()
+    assert rel(u, eu) <= 4 * rel(qu, eu) + 1e-5 and rel(v, ev) <= 4 * rel(qv, ev) + 1e-5, (rel(u, eu), rel(qu, eu))
+    plan.close()

@@ -63,3 +63,44 @@ def test_config_helpers_follow_reference_semantics():
     with pytest.raises(TypeError):
         OC.param_to_list("3", 3)
     assert OC.structure_to_list({"in_channels": 2, "hidden_channels": [4, 5], "out_channels": 2}) == [2, 4, 5, 2]
+
+
+def test_resnet_oracle_matches_reference_golden(golden_dir):
+    """ResNet basic-block chain (reference configs/fullmodels/basicResnet1.json, src/models/ResNet.py:26-50): oracle vs
+    the reference's own forward (tests/golden/make_golden_resnet.py), fp64."""
+    import json
+    import os
+    import safetensors.torch as st
+    from oracle import cnn as OC
+    cfg = json.load(open(os.path.join(golden_dir, "basicResnet1.json")))
+    sd = st.load_file(os.path.join(golden_dir, "resnet_weights.safetensors"))
+    g = st.load_file(os.path.join(golden_dir, "resnet_golden.safetensors"))
+    y = OC.model_forward(g["x"], cfg, sd)
+    assert (y - g["y"]).abs().max().item() <= 1e-14
+    assert (g["y"] >= 0).all()                       # every block ends with act(x + y)
+    yb = OC.model_forward(g["x"], cfg, sd, round_bf16=True)
+    assert 1e-4 < ((yb - g["y"]).norm() / g["y"].norm()).item() < 3e-2       # the stated bf16 storage error
+
+
+def test_resnet_module_tree_loads_reference_checkpoint(golden_dir, built_lib):
+    """models.buildModel(basicResnet1.json) has the reference's parameter names and folds BN like the oracle."""
+    import json
+    import os
+    import safetensors.torch as st
+    import torch
+    from ml_accelerated_simulation_b200 import models
+    cfg = json.load(open(os.path.join(golden_dir, "basicResnet1.json")))
+    sd = st.load_file(os.path.join(golden_dir, "resnet_weights.safetensors"))
+    model = models.buildModel(cfg)
+    missing, unexpected = model.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    layers, shortcuts, final_relu = model.flat_layers()
+    assert len(layers) == 12 and final_relu
+    assert sorted(shortcuts) == [1, 3, 5, 7, 9, 11]
+    assert shortcuts[1][0] == -1 and shortcuts[1][1].shape == (64, 2, 1, 1)          # 1x1 conv of the network input
+    assert shortcuts[3] == (1, None, None)                                             # identity
+    assert shortcuts[11][0] == 9 and shortcuts[11][1].shape == (2, 64, 1, 1)         # 1x1 conv of the block input
+    w, b = layers[0]
+    bn = "models.0.layers.0.1."
+    scale = sd[bn + "weight"].double() / torch.sqrt(sd[bn + "running_var"].double() + 1e-5)
+    assert torch.allclose(w, sd["models.0.layers.0.0.weight"].double() * scale[:, None, None, None], atol=1e-15)

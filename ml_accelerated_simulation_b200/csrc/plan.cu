@@ -625,7 +625,19 @@ int mlsim_step(mlsim_plan* pl, float* u, float* v, float* p_or_null, int32_t nst
   MLSIM_REQUIRE(nsteps >= 0, "nsteps must be >= 0");
   if (apply_cnn && !pl->cnn_ready) { set_error("apply_cnn set but the correction network is not finalised"); return MLSIM_ESTATE; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return run_steps(pl, u, v, p_or_null, nsteps, apply_cnn, cnn_input_scale, st, Chunk{0, pl->cfg.batch});
+  // experiment hook: run the batch in independent blocks, block after block (smaller per-launch working set)
+  static const int nchunks_env = [] { const char* e = getenv("MLSIM_STEP_CHUNKS"); return e ? atoi(e) : 1; }();
+  const int B = pl->cfg.batch;
+  const int nchunks = (nchunks_env >= 1 && nchunks_env <= B) ? nchunks_env : 1;
+  if (nchunks == 1) return run_steps(pl, u, v, p_or_null, nsteps, apply_cnn, cnn_input_scale, st, Chunk{0, B});
+  const size_t img = (size_t)pl->cfg.nx * pl->cfg.ny;
+  for (int k = 0; k < nchunks; ++k) {
+    const int b0 = (int)((long)B * k / nchunks), b1 = (int)((long)B * (k + 1) / nchunks);
+    const size_t off = (size_t)b0 * img;
+    if ((rc = run_steps(pl, u + off, v + off, p_or_null ? p_or_null + off : nullptr, nsteps, apply_cnn, cnn_input_scale,
+                        st, Chunk{b0, b1 - b0}))) return rc;
+  }
+  return MLSIM_OK;
 }
 
 int mlsim_rollout_host(mlsim_plan* pl, float* hu, float* hv, float* hp, int32_t nsteps, int32_t apply_cnn,

@@ -295,12 +295,42 @@ template <int N> struct RowCfg {
   static constexpr size_t SMEM = fft_buf_elems<N, Q>() * sizeof(float2);
 };
 
+// Spectral column walker for the I/O phases: a thread owns ONE line and visits k = t, t + TPL, ...; the slab chunk
+// index / local column are advanced incrementally (no division per element).
+template <bool SLAB>
+struct SpecWalk {
+  size_t base;      // element offset of (row, column 0) in plain mode; of (chunk 0, row, 0) in slab mode
+  size_t chunk;     // slab: elements between consecutive rank chunks
+  int kl, kyw;
+  __device__ __forceinline__ void init(const SolverParams& p, int b, int row, int k, int rows) {
+    if constexpr (!SLAB) {
+      base = ((size_t)b * p.nx + row) * p.nycp + k;
+      chunk = 0; kl = 0; kyw = 0;
+    } else {
+      const int r = k / p.kyw;
+      kl = k - r * p.kyw; kyw = p.kyw;
+      chunk = (size_t)p.batch * rows * p.kywp;
+      base = (size_t)r * chunk + ((size_t)b * rows + row) * p.kywp;
+    }
+  }
+  __device__ __forceinline__ size_t off() const { return SLAB ? base + kl : base; }
+  __device__ __forceinline__ void advance(int dk) {
+    if constexpr (!SLAB) {
+      base += dk;
+    } else {
+      kl += dk;
+      while (kl >= kyw) { kl -= kyw; base += chunk; }
+    }
+  }
+};
+
 template <int N, bool SLAB>
 __global__ void __launch_bounds__(RowCfg<N>::THREADS)
 k_div_rfft(const float* __restrict__ u, const float* __restrict__ v, float2* __restrict__ S,
            const float2* __restrict__ tw, SolverParams p) {
   using C = RowCfg<N>;
   constexpr int Q = C::Q, NT = C::THREADS;
+  constexpr int TPL = NT / Q;                       // threads per line in the I/O phases (k / y fastest)
   extern __shared__ float4 smem4[];
   float2* buf = reinterpret_cast<float2*>(smem4);
 
@@ -308,38 +338,45 @@ k_div_rfft(const float* __restrict__ u, const float* __restrict__ v, float2* __r
   pdl_wait();
   const int b = blockIdx.y;
   const int i0 = blockIdx.x * (2 * Q);
-  const float* __restrict__ gu = u + (ptrdiff_t)b * p.img_stride;
-  const float* __restrict__ gv = v + (ptrdiff_t)b * p.img_stride;
+  const int ql = threadIdx.x / TPL, t = threadIdx.x % TPL;     // this thread's line (row pair) and lane within it
 
-  // divergence: a thread owns one y and two consecutive rows (= the two halves of one float2 of the line-fastest
-  // layout): coalesced 128-byte row loads, one conflict-free 64-bit shared store
-  for (int g = threadIdx.x; g < Q * N; g += NT) {
-    const int q = g / N, j = g - q * N;
-    const int i = i0 + 2 * q;
+  // divergence: the thread owns row pair (2 ql, 2 ql + 1) -- the two halves of one float2 of the line-fastest layout --
+  // and the columns t, t + TPL, ...: coalesced row loads through three hoisted row pointers, conflict-free 64-bit
+  // shared stores
+  {
+    const int i = i0 + 2 * ql;
     const int im = SLAB ? (i - 1) : ((i - 1) & (p.nx - 1));
-    const int jm = (j - 1) & (N - 1);
-    const float um = gu[(ptrdiff_t)im * N + j];
-    const float ua = gu[(ptrdiff_t)i * N + j], ub = gu[(ptrdiff_t)(i + 1) * N + j];
-    const float va = gv[(ptrdiff_t)i * N + j], vb = gv[(ptrdiff_t)(i + 1) * N + j];
-    const float vam = gv[(ptrdiff_t)i * N + jm], vbm = gv[(ptrdiff_t)(i + 1) * N + jm];
-    buf[fidx<Q>(j, q)] = make_float2((ua - um) * p.inv_hx + (va - vam) * p.inv_hy,
-                                     (ub - ua) * p.inv_hx + (vb - vbm) * p.inv_hy);
+    const float* __restrict__ ru = u + (ptrdiff_t)b * p.img_stride + (ptrdiff_t)i * N;
+    const float* __restrict__ rv = v + (ptrdiff_t)b * p.img_stride + (ptrdiff_t)i * N;
+    const float* __restrict__ rum = u + (ptrdiff_t)b * p.img_stride + (ptrdiff_t)im * N;
+#pragma unroll 4
+    for (int j = t; j < N; j += TPL) {
+      const int jm = (j - 1) & (N - 1);
+      const float um = rum[j];
+      const float ua = ru[j], ub = ru[N + j];
+      const float va = rv[j], vb = rv[N + j];
+      const float vam = rv[jm], vbm = rv[N + jm];
+      buf[fidx<Q>(j, ql)] = make_float2((ua - um) * p.inv_hx + (va - vam) * p.inv_hy,
+                                        (ub - ua) * p.inv_hx + (vb - vbm) * p.inv_hy);
+    }
   }
   __syncthreads();
 
   const int c = threadIdx.x % Q, j = threadIdx.x / Q;
   fft_lines_forward<N, Q>(buf, c, j, tw);
 
+  // untangle the two real rows of line ql and store their half spectra
   constexpr int nyc = N / 2 + 1;
-  for (int idx = threadIdx.x; idx < Q * nyc; idx += NT) {
-    const int q = idx / nyc, k = idx - q * nyc;
-    const float2 z = buf[fidx<Q>(k, q)];
-    const float2 zm = buf[fidx<Q>((N - k) & (N - 1), q)];
-    const float2 A = make_float2(0.5f * (z.x + zm.x), 0.5f * (z.y - zm.y));
-    const float2 B = make_float2(0.5f * (z.y + zm.y), -0.5f * (z.x - zm.x));
-    const size_t o = spec_off<SLAB>(p, b, i0 + 2 * q, k, p.nx);
-    S[o] = A;
-    S[o + (SLAB ? p.kywp : p.nycp)] = B;
+  SpecWalk<SLAB> w;
+  w.init(p, b, i0 + 2 * ql, t, p.nx);
+  const int pitch = SLAB ? p.kywp : p.nycp;
+  for (int k = t; k < nyc; k += TPL) {
+    const float2 z = buf[fidx<Q>(k, ql)];
+    const float2 zm = buf[fidx<Q>((N - k) & (N - 1), ql)];
+    const size_t o = w.off();
+    S[o] = make_float2(0.5f * (z.x + zm.x), 0.5f * (z.y - zm.y));
+    S[o + pitch] = make_float2(0.5f * (z.y + zm.y), -0.5f * (z.x - zm.x));
+    w.advance(TPL);
   }
 }
 
@@ -354,6 +391,7 @@ k_irfft_grad(const float2* __restrict__ S, const float* __restrict__ uin, const 
              const float2* __restrict__ tw, SolverParams p) {
   using C = RowCfg<N>;
   constexpr int Q = C::Q, NT = C::THREADS;
+  constexpr int TPL = NT / Q;
   extern __shared__ float4 smem4[];
   float2* buf = reinterpret_cast<float2*>(smem4);
 
@@ -362,19 +400,26 @@ k_irfft_grad(const float2* __restrict__ S, const float* __restrict__ uin, const 
   const int b = blockIdx.y;
   const int i0 = blockIdx.x * (2 * Q - 1);
   constexpr int nyc = N / 2 + 1;
+  const int ql = threadIdx.x / TPL, t = threadIdx.x % TPL;
 
-  for (int idx = threadIdx.x; idx < Q * nyc; idx += NT) {
-    const int q = idx / nyc, k = idx - q * nyc;
+  {
     // plain: periodic wrap; slab: the spectral rows are [0, nx] (row nx = halo), rows past it are never used
-    const int ia = SLAB ? min(i0 + 2 * q, p.nx) : ((i0 + 2 * q) & (p.nx - 1));
-    const int ib = SLAB ? min(i0 + 2 * q + 1, p.nx) : ((i0 + 2 * q + 1) & (p.nx - 1));
-    const float2 A = __ldg(&S[spec_off<SLAB>(p, b, ia, k, p.nx + 1)]);
-    const float2 B = __ldg(&S[spec_off<SLAB>(p, b, ib, k, p.nx + 1)]);
-    if (k == 0 || k == N / 2) {
-      buf[fidx<Q>(k, q)] = make_float2(A.x, B.x);          // c2r ignores Im of DC / Nyquist
-    } else {
-      buf[fidx<Q>(k, q)] = make_float2(A.x - B.y, A.y + B.x);
-      buf[fidx<Q>(N - k, q)] = make_float2(A.x + B.y, B.x - A.y);
+    const int ia = SLAB ? min(i0 + 2 * ql, p.nx) : ((i0 + 2 * ql) & (p.nx - 1));
+    const int ib = SLAB ? min(i0 + 2 * ql + 1, p.nx) : ((i0 + 2 * ql + 1) & (p.nx - 1));
+    SpecWalk<SLAB> wa, wb;
+    wa.init(p, b, ia, t, p.nx + 1);
+    wb.init(p, b, ib, t, p.nx + 1);
+    for (int k = t; k < nyc; k += TPL) {
+      const float2 A = __ldg(&S[wa.off()]);
+      const float2 B = __ldg(&S[wb.off()]);
+      if (k == 0 || k == N / 2) {
+        buf[fidx<Q>(k, ql)] = make_float2(A.x, B.x);          // c2r ignores Im of DC / Nyquist
+      } else {
+        buf[fidx<Q>(k, ql)] = make_float2(A.x - B.y, A.y + B.x);
+        buf[fidx<Q>(N - k, ql)] = make_float2(A.x + B.y, B.x - A.y);
+      }
+      wa.advance(TPL);
+      wb.advance(TPL);
     }
   }
   __syncthreads();
@@ -382,42 +427,49 @@ k_irfft_grad(const float2* __restrict__ S, const float* __restrict__ uin, const 
   const int c = threadIdx.x % Q, j = threadIdx.x / Q;
   fft_lines_inverse<N, Q>(buf, c, j, tw);
 
-  // Gradient subtraction.  A thread owns one y and a block of 4 consecutive rows: in the line-fastest layout the rows
-  // 2q, 2q+1 of one y are the two halves of one float2, so its pressure values are 3 + 2 conflict-free 64-bit
-  // shared loads (consecutive lanes <-> consecutive y: pitch Q+1 float2), and its global accesses are coalesced
-  // 128-byte rows.  All loads of an item are issued before its first store.
-  const ptrdiff_t img = (ptrdiff_t)b * p.img_stride;
+  // Gradient subtraction.  A thread owns a block of 4 consecutive rows and the columns t', t' + TPG, ...: in the
+  // line-fastest layout the rows 2q, 2q+1 of one y are the two halves of one float2, so its pressure values are 3 + 2
+  // conflict-free 64-bit shared loads (consecutive lanes <-> consecutive y: pitch Q+1 float2), and its global accesses
+  // are coalesced rows through hoisted row pointers.  All loads of an item are issued before its first store.
   constexpr int NROWS = (2 * Q - 1 > 0) ? 2 * Q - 1 : 1;
-  constexpr int NRG = (NROWS + 3) / 4;
-  for (int g = threadIdx.x; g < NRG * N; g += NT) {
-    const int rg = g / N, y = g - rg * N;
+  constexpr int NRG = (NROWS + 3) / 4;                      // row groups of 4
+  constexpr int TPG = (NT / NRG > N) ? N : NT / NRG;        // threads per row group (a power of two: NT, NRG are)
+  const int rg = threadIdx.x / TPG, ty = threadIdx.x % TPG;
+  if (rg < NRG) {
     const int r0 = 4 * rg, q0 = 2 * rg;
-    float uo[4], vo[4];
+    const ptrdiff_t row0 = (ptrdiff_t)b * p.img_stride + (ptrdiff_t)(i0 + r0) * N;
+    const float* __restrict__ pu = uin + row0;
+    const float* __restrict__ pv = vin + row0;
+    float* __restrict__ ou = uout + row0;
+    float* __restrict__ ov = vout + row0;
+    float* __restrict__ pp = pout ? pout + ((size_t)b * p.nx + i0 + r0) * N : nullptr;
     bool on[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      on[k] = (r0 + k < NROWS) && (i0 + r0 + k < p.nx);
-      if (on[k]) {
-        const ptrdiff_t off = img + (ptrdiff_t)(i0 + r0 + k) * N + y;
-        uo[k] = uin[off];
-        vo[k] = vin[off];
-      }
-    }
-    const int yn = (y + 1) & (N - 1);
-    const float2 A0 = buf[fidx<Q>(y, q0)];
-    const float2 A1 = (q0 + 1 < Q) ? buf[fidx<Q>(y, q0 + 1)] : make_float2(0.f, 0.f);
-    const float2 A2 = (q0 + 2 < Q) ? buf[fidx<Q>(y, q0 + 2)] : make_float2(0.f, 0.f);
-    const float2 B0 = buf[fidx<Q>(yn, q0)];
-    const float2 B1 = (q0 + 1 < Q) ? buf[fidx<Q>(yn, q0 + 1)] : make_float2(0.f, 0.f);
-    const float pr[5] = {A0.x, A0.y, A1.x, A1.y, A2.x};
-    const float py[4] = {B0.x, B0.y, B1.x, B1.y};
+    for (int k = 0; k < 4; ++k) on[k] = (r0 + k < NROWS) && (i0 + r0 + k < p.nx);
+    for (int y = ty; y < N; y += TPG) {
+      float uo[4], vo[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (!on[k]) continue;
-      const ptrdiff_t off = img + (ptrdiff_t)(i0 + r0 + k) * N + y;
-      uout[off] = uo[k] - (pr[k + 1] - pr[k]) * p.inv_hx;
-      vout[off] = vo[k] - (py[k] - pr[k]) * p.inv_hy;
-      if (pout) pout[((size_t)b * p.nx + i0 + r0 + k) * N + y] = pr[k];
+      for (int k = 0; k < 4; ++k) {
+        if (on[k]) {
+          uo[k] = pu[k * N + y];
+          vo[k] = pv[k * N + y];
+        }
+      }
+      const int yn = (y + 1) & (N - 1);
+      const float2 A0 = buf[fidx<Q>(y, q0)];
+      const float2 A1 = (q0 + 1 < Q) ? buf[fidx<Q>(y, q0 + 1)] : make_float2(0.f, 0.f);
+      const float2 A2 = (q0 + 2 < Q) ? buf[fidx<Q>(y, q0 + 2)] : make_float2(0.f, 0.f);
+      const float2 B0 = buf[fidx<Q>(yn, q0)];
+      const float2 B1 = (q0 + 1 < Q) ? buf[fidx<Q>(yn, q0 + 1)] : make_float2(0.f, 0.f);
+      const float pr[5] = {A0.x, A0.y, A1.x, A1.y, A2.x};
+      const float py[4] = {B0.x, B0.y, B1.x, B1.y};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!on[k]) continue;
+        ou[k * N + y] = uo[k] - (pr[k + 1] - pr[k]) * p.inv_hx;
+        ov[k * N + y] = vo[k] - (py[k] - pr[k]) * p.inv_hy;
+        if (pp) pp[k * N + y] = pr[k];
+      }
     }
   }
 }

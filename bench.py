@@ -22,6 +22,8 @@ import sys
 import threading
 import time
 
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # the version banner goes to stdout and would precede the JSON line
+    os.environ["NCCL_DEBUG"] = "WARN"
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -315,7 +317,7 @@ def run_slab(args):
     geom = SlabGeometry(nx=n, ny=n, batch=1, rank=rank, world=world)
     be = CudaSlabBackend(geom, device=local)
     be.set_cnn(model.cnn.folded_layers())
-    stp = SlabStepper(be, SlabComm(geom))
+    stp = SlabStepper(be, SlabComm(geom, p2p=bool(args.p2p)))
     # synthetic IC: band-limited random field built per slab (same generator family on every rank), made
     # divergence-free by the slab projection itself and scaled to max speed 7 (reference src/inference.py:54-58,76-78)
     g = torch.Generator(device=dev).manual_seed(42 + rank)
@@ -381,7 +383,7 @@ def run_slab(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 solver + bf16 conv (fp32 accumulate)", "data": "synthetic",
             "config": {"workload": f"single {n}x{n} periodic grid, batch 1, x-slab decomposition over {world} GPU(s) "
-                                   "(halo exchange + spectral all-to-all per RK stage over NCCL), RK4 solver step + MLACFD correction CNN",
+                                   f"(halo exchange over NCCL, spectral exchange {'as peer-memory stores from the producing kernels' if (args.p2p and world > 1) else 'as NCCL all-to-all'}), RK4 solver step + MLACFD correction CNN",
                        "l2": "fields 268 MB each at 8192^2 > 126 MB L2; no flush", "exchanges_per_step": 13},
             "roofline": {"kernel": "k_conv_mid<64>", "bound": "tensor", "achieved": mid_tflops, "peak": peaks["tensor_tflops"],
                          "unit": "TFLOP/s", "frac": mid_tflops / peaks["tensor_tflops"], "traffic": None,
@@ -443,6 +445,7 @@ def main():
     ap.add_argument("--workload", default="ensemble", choices=["ensemble", "slab", "datagen"],
                     help="ensemble: BASELINE configs[1] (default, the driver's line); slab: configs[4], one big grid over N GPUs")
     ap.add_argument("--nx", type=int, default=8192, help="grid size of the slab workload")
+    ap.add_argument("--p2p", type=int, default=1, help="slab workload: 1 = peer-memory spectral exchange (NVLink stores from the kernels), 0 = NCCL all-to-all")
     ap.add_argument("--grid", type=int, default=0, help="ensemble workload: grid size (default 256 = configs[1])")
     ap.add_argument("--batch", type=int, default=0, help="ensemble workload: trajectories per GPU (default 64)")
     args = ap.parse_args()

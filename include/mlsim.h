@@ -124,6 +124,12 @@ int  mlsim_slab_divergence_rfft(mlsim_plan* plan, const float* uv, void* spec_se
 int  mlsim_slab_stage_b(mlsim_plan* plan, const void* spec_recv, void* spec_send2, void* stream);
 int  mlsim_slab_stage_c(mlsim_plan* plan, const void* spec_recv2, float* uv, float* p_or_null, void* stream);
 int  mlsim_slab_cnn_correct(mlsim_plan* plan, float* uv, double cnn_input_scale, void* stream);
+/* Peer-memory (NVLink P2P) spectral exchange.  fwd_recv[r] / bwd_recv[r], r < slab_world: device address, valid in THIS
+ * process, of rank r's forward / backward receive buffer (CUDA IPC or symmetric memory; slab.py uses
+ * torch.distributed._symmetric_memory).  Afterwards mlsim_slab_stage_a with spec_send == NULL stores column chunk r
+ * straight into rank r's receive buffer, mlsim_slab_stage_b with spec_send2 == NULL does the same for the backward
+ * chunks, and the caller replaces each all-to-all by a cross-rank barrier.  NULL arguments switch back. */
+int  mlsim_slab_set_peers(mlsim_plan* plan, const uint64_t* fwd_recv, const uint64_t* bwd_recv);
 
 /* ---- data generation, reference src/data_generation.py:91-111,193-213 ----
  * mlsim_downsample_staggered: downsample_staggered_velocity(fine_grid, coarse_grid, (u, v)) -- u keeps the faces

@@ -47,6 +47,24 @@ struct SolverParams {
   int kyw, kywp;              // spectral columns per rank chunk and its padded pitch (float2 units)
 };
 
+// Slab mode: where spectral column chunk r lives.  With NCCL exchanges every entry points into one local send / recv
+// buffer (chunk r at r * chunk elements); with peer-memory exchanges entry r is rank r's receive buffer mapped into this
+// process (NVLink P2P), already offset to this rank's slot, so the producing kernel stores straight into the consumer's
+// memory and the all-to-all disappears.
+#define MLSIM_MAX_SLAB_RANKS 8
+struct SpecPeers {
+  float2* p[MLSIM_MAX_SLAB_RANKS];
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ float2* spec_peer(const SpecPeers& s, int r) {
+  float2* q = s.p[0];
+#pragma unroll
+  for (int i = 1; i < MLSIM_MAX_SLAB_RANKS; ++i)
+    if (r == i) q = s.p[i];
+  return q;
+}
+#endif
+
 // Stage coefficients of the RK4-with-projection scheme.
 //   mode 0: du,dv = F                       (test hook)
 //   mode 1: acc = u0 + ca*k ; ustar = u0 + cs*k            (stage 1: u_s == u0)

@@ -57,6 +57,8 @@ struct mlsim_plan {
   int r0 = 1, n2len = 0;                // nx(global) = r0 * n2len, n2len <= 2048
   // slab decomposition (cfg.slab_world >= 1): this rank owns global rows [rank*nxl, (rank+1)*nxl)
   bool slab = false;
+  bool have_peers = false;              // peer-memory spectral exchange (mlsim_slab_set_peers)
+  SpecPeers fwd_peers, bwd_peers;       // rank r's forward / backward receive buffer, offset to this rank's slot
   int nxg = 0, nxl = 0, ext_rows = 0, kyw = 0, kywp = 0, kyv = 0, ky0 = 0;
   // cnn
   std::vector<CnnLayer> layers;
@@ -311,7 +313,7 @@ int mlsim_plan_create(const mlsim_config* cfg, mlsim_plan** out) {
   const bool slab = cfg->slab_world >= 1;
   if (slab) {
     const int W = cfg->slab_world;
-    MLSIM_REQUIRE(is_pow2(W) && W <= 64, "slab_world must be a power of two");
+    MLSIM_REQUIRE(is_pow2(W) && W <= MLSIM_MAX_SLAB_RANKS, "slab_world must be a power of two <= 8 (one NVLink domain)");
     MLSIM_REQUIRE(cfg->slab_rank >= 0 && cfg->slab_rank < W, "slab_rank out of range");
     MLSIM_REQUIRE(cfg->nx / W >= 32, "a slab needs at least 32 rows per rank");
     MLSIM_REQUIRE(cfg->ny / 2 >= W * W, "ny too small for this many ranks (every rank needs spectral columns)");
@@ -761,7 +763,9 @@ int mlsim_slab_stage_a(mlsim_plan* pl, int32_t stage, const float* us, const flo
   MLSIM_REQUIRE(stage >= 0 && stage <= 3, "stage must be 0..3");
   int rc;
   if ((rc = check_field(us, "us")) || (rc = check_field(u0, "u0")) || (rc = check_field(acc, "acc")) ||
-      (rc = check_field(out, "out")) || (rc = check_field(spec_send, "spec_send"))) return rc;
+      (rc = check_field(out, "out"))) return rc;
+  if (spec_send == nullptr) MLSIM_REQUIRE(pl->have_peers, "spec_send is NULL and no peer buffers were registered (mlsim_slab_set_peers)");
+  else if ((rc = check_field(spec_send, "spec_send"))) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const float dt = (float)pl->cfg.dt;
   const UV s = uv_origin(pl, const_cast<float*>(us)), b = uv_origin(pl, const_cast<float*>(u0)), a = uv_origin(pl, acc),
@@ -776,28 +780,34 @@ int mlsim_slab_stage_a(mlsim_plan* pl, int32_t stage, const float* us, const flo
   }
   { ProfScope ps(pl, 0, st); if ((rc = launch_explicit(g, pl->sp, pl->d_forcing, st))) return rc; }
   ProfScope ps(pl, 1, st);
-  return launch_div_rfft(o.u, o.v, static_cast<float2*>(spec_send), pl->d_twy, pl->sp, st);
+  return launch_div_rfft(o.u, o.v, static_cast<float2*>(spec_send), pl->d_twy, pl->sp, st,
+                         spec_send ? nullptr : &pl->fwd_peers, pl->cfg.slab_world);
 }
 
 int mlsim_slab_divergence_rfft(mlsim_plan* pl, const float* uv, void* spec_send, void* stream) {
   if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
   MLSIM_SLAB_ONLY(pl);
   int rc;
-  if ((rc = check_field(uv, "uv")) || (rc = check_field(spec_send, "spec_send"))) return rc;
+  if ((rc = check_field(uv, "uv"))) return rc;
+  if (spec_send == nullptr) MLSIM_REQUIRE(pl->have_peers, "spec_send is NULL and no peer buffers were registered (mlsim_slab_set_peers)");
+  else if ((rc = check_field(spec_send, "spec_send"))) return rc;
   const UV o = uv_origin(pl, const_cast<float*>(uv));
-  return launch_div_rfft(o.u, o.v, static_cast<float2*>(spec_send), pl->d_twy, pl->sp, reinterpret_cast<cudaStream_t>(stream));
+  return launch_div_rfft(o.u, o.v, static_cast<float2*>(spec_send), pl->d_twy, pl->sp, reinterpret_cast<cudaStream_t>(stream),
+                         spec_send ? nullptr : &pl->fwd_peers, pl->cfg.slab_world);
 }
 
 int mlsim_slab_stage_b(mlsim_plan* pl, const void* spec_recv, void* spec_send2, void* stream) {
   if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
   MLSIM_SLAB_ONLY(pl);
   int rc;
-  if ((rc = check_field(spec_recv, "spec_recv")) || (rc = check_field(spec_send2, "spec_send2"))) return rc;
+  if ((rc = check_field(spec_recv, "spec_recv"))) return rc;
+  if (spec_send2 == nullptr) MLSIM_REQUIRE(pl->have_peers, "spec_send2 is NULL and no peer buffers were registered (mlsim_slab_set_peers)");
+  else if ((rc = check_field(spec_send2, "spec_send2"))) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   ProfScope ps(pl, 2, st);
   return launch_col_solve_slab(static_cast<const float2*>(spec_recv), static_cast<float2*>(spec_send2), pl->d_split,
                                pl->d_inv_eig, pl->d_twx, pl->d_tw_n2, pl->sp, pl->nxg, pl->cfg.slab_world, pl->kyv,
-                               pl->r0, st);
+                               pl->r0, st, spec_send2 ? nullptr : &pl->bwd_peers);
 }
 
 int mlsim_slab_stage_c(mlsim_plan* pl, const void* spec_recv2, float* uv, float* p_or_null, void* stream) {
@@ -809,7 +819,29 @@ int mlsim_slab_stage_c(mlsim_plan* pl, const void* spec_recv2, float* uv, float*
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const UV o = uv_origin(pl, uv);
   ProfScope ps(pl, 3, st);
-  return launch_irfft_grad(static_cast<const float2*>(spec_recv2), o.u, o.v, o.u, o.v, p_or_null, pl->d_twy, pl->sp, st);
+  return launch_irfft_grad(static_cast<const float2*>(spec_recv2), o.u, o.v, o.u, o.v, p_or_null, pl->d_twy, pl->sp, st,
+                           pl->cfg.slab_world);
+}
+
+// Peer-memory spectral exchange: fwd_recv[r] / bwd_recv[r] = base of rank r's forward / backward receive buffer as
+// mapped into THIS process (CUDA IPC / symmetric memory over NVLink).  Afterwards stage_a (spec_send == NULL) stores
+// column chunk r straight into rank r's buffer at this rank's slot, and stage_b (spec_send2 == NULL) does the same for
+// the backward chunks; the caller replaces each all-to-all by a cross-rank barrier.
+int mlsim_slab_set_peers(mlsim_plan* pl, const uint64_t* fwd_recv, const uint64_t* bwd_recv) {
+  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_SLAB_ONLY(pl);
+  if (!fwd_recv || !bwd_recv) { pl->have_peers = false; return MLSIM_OK; }
+  const int W = pl->cfg.slab_world, r = pl->cfg.slab_rank;
+  const size_t cf = (size_t)pl->cfg.batch * pl->nxl * pl->kywp, cb = (size_t)pl->cfg.batch * (pl->nxl + 1) * pl->kywp;
+  for (int i = 0; i < MLSIM_MAX_SLAB_RANKS; ++i) {
+    const int j = i < W ? i : 0;
+    MLSIM_REQUIRE(fwd_recv[j] != 0 && bwd_recv[j] != 0 && (fwd_recv[j] & 15u) == 0 && (bwd_recv[j] & 15u) == 0,
+                  "peer buffer pointers must be non-null and 16-byte aligned");
+    pl->fwd_peers.p[i] = reinterpret_cast<float2*>(fwd_recv[j]) + (size_t)r * cf;
+    pl->bwd_peers.p[i] = reinterpret_cast<float2*>(bwd_recv[j]) + (size_t)r * cb;
+  }
+  pl->have_peers = true;
+  return MLSIM_OK;
 }
 
 // v += model(v) on the slab.  The CNN pads with ZEROS at the edges of the global grid (Conv2d padding=1, reference

@@ -295,38 +295,43 @@ template <int N> struct RowCfg {
   static constexpr size_t SMEM = fft_buf_elems<N, Q>() * sizeof(float2);
 };
 
-// Spectral column walker for the I/O phases: a thread owns ONE line and visits k = t, t + TPL, ...; the slab chunk
-// index / local column are advanced incrementally (no division per element).
+// Spectral column walker for the I/O phases: a thread owns ONE line and visits k = t, t + TPL, ...; in slab mode the
+// chunk index / local column are advanced incrementally (no division per element) and the chunk's base pointer comes
+// from the SpecPeers table (local buffer or a peer's memory).
 template <bool SLAB>
 struct SpecWalk {
-  size_t base;      // element offset of (row, column 0) in plain mode; of (chunk 0, row, 0) in slab mode
-  size_t chunk;     // slab: elements between consecutive rank chunks
-  int kl, kyw;
-  __device__ __forceinline__ void init(const SolverParams& p, int b, int row, int k, int rows) {
+  float2* cur;      // plain: &S[row][k]; slab: &chunk_r[b][row][0]
+  size_t rowoff;    // slab: element offset of (b, row, 0) inside a chunk
+  int kl, kyw, r;
+  __device__ __forceinline__ void init(const SolverParams& p, float2* S, const SpecPeers& peers, int b, int row, int k,
+                                       int rows) {
     if constexpr (!SLAB) {
-      base = ((size_t)b * p.nx + row) * p.nycp + k;
-      chunk = 0; kl = 0; kyw = 0;
+      cur = S + ((size_t)b * p.nx + row) * p.nycp + k;
+      rowoff = 0; kl = 0; kyw = 0; r = 0;
     } else {
-      const int r = k / p.kyw;
+      r = k / p.kyw;
       kl = k - r * p.kyw; kyw = p.kyw;
-      chunk = (size_t)p.batch * rows * p.kywp;
-      base = (size_t)r * chunk + ((size_t)b * rows + row) * p.kywp;
+      rowoff = ((size_t)b * rows + row) * p.kywp;
+      cur = spec_peer(peers, r) + rowoff;
     }
   }
-  __device__ __forceinline__ size_t off() const { return SLAB ? base + kl : base; }
-  __device__ __forceinline__ void advance(int dk) {
+  __device__ __forceinline__ float2* ptr() const { return SLAB ? cur + kl : cur; }
+  __device__ __forceinline__ void advance(int dk, const SpecPeers& peers) {
     if constexpr (!SLAB) {
-      base += dk;
+      cur += dk;
     } else {
       kl += dk;
-      while (kl >= kyw) { kl -= kyw; base += chunk; }
+      if (kl >= kyw) {
+        while (kl >= kyw) { kl -= kyw; ++r; }
+        cur = spec_peer(peers, r < MLSIM_MAX_SLAB_RANKS ? r : 0) + rowoff;
+      }
     }
   }
 };
 
 template <int N, bool SLAB>
 __global__ void __launch_bounds__(RowCfg<N>::THREADS)
-k_div_rfft(const float* __restrict__ u, const float* __restrict__ v, float2* __restrict__ S,
+k_div_rfft(const float* __restrict__ u, const float* __restrict__ v, float2* __restrict__ S, SpecPeers peers,
            const float2* __restrict__ tw, SolverParams p) {
   using C = RowCfg<N>;
   constexpr int Q = C::Q, NT = C::THREADS;
@@ -368,15 +373,15 @@ k_div_rfft(const float* __restrict__ u, const float* __restrict__ v, float2* __r
   // untangle the two real rows of line ql and store their half spectra
   constexpr int nyc = N / 2 + 1;
   SpecWalk<SLAB> w;
-  w.init(p, b, i0 + 2 * ql, t, p.nx);
+  w.init(p, S, peers, b, i0 + 2 * ql, t, p.nx);
   const int pitch = SLAB ? p.kywp : p.nycp;
   for (int k = t; k < nyc; k += TPL) {
     const float2 z = buf[fidx<Q>(k, ql)];
     const float2 zm = buf[fidx<Q>((N - k) & (N - 1), ql)];
-    const size_t o = w.off();
-    S[o] = make_float2(0.5f * (z.x + zm.x), 0.5f * (z.y - zm.y));
-    S[o + pitch] = make_float2(0.5f * (z.y + zm.y), -0.5f * (z.x - zm.x));
-    w.advance(TPL);
+    float2* o = w.ptr();
+    o[0] = make_float2(0.5f * (z.x + zm.x), 0.5f * (z.y - zm.y));
+    o[pitch] = make_float2(0.5f * (z.y + zm.y), -0.5f * (z.x - zm.x));
+    w.advance(TPL, peers);
   }
 }
 
@@ -386,7 +391,7 @@ k_div_rfft(const float* __restrict__ u, const float* __restrict__ v, float2* __r
 // ---------------------------------------------------------------------------------------------
 template <int N, bool SLAB>
 __global__ void __launch_bounds__(RowCfg<N>::THREADS)
-k_irfft_grad(const float2* __restrict__ S, const float* __restrict__ uin, const float* __restrict__ vin,
+k_irfft_grad(const float2* __restrict__ S, SpecPeers peers, const float* __restrict__ uin, const float* __restrict__ vin,
              float* __restrict__ uout, float* __restrict__ vout, float* __restrict__ pout,
              const float2* __restrict__ tw, SolverParams p) {
   using C = RowCfg<N>;
@@ -407,19 +412,19 @@ k_irfft_grad(const float2* __restrict__ S, const float* __restrict__ uin, const 
     const int ia = SLAB ? min(i0 + 2 * ql, p.nx) : ((i0 + 2 * ql) & (p.nx - 1));
     const int ib = SLAB ? min(i0 + 2 * ql + 1, p.nx) : ((i0 + 2 * ql + 1) & (p.nx - 1));
     SpecWalk<SLAB> wa, wb;
-    wa.init(p, b, ia, t, p.nx + 1);
-    wb.init(p, b, ib, t, p.nx + 1);
+    wa.init(p, const_cast<float2*>(S), peers, b, ia, t, p.nx + 1);
+    wb.init(p, const_cast<float2*>(S), peers, b, ib, t, p.nx + 1);
     for (int k = t; k < nyc; k += TPL) {
-      const float2 A = __ldg(&S[wa.off()]);
-      const float2 B = __ldg(&S[wb.off()]);
+      const float2 A = __ldg(wa.ptr());
+      const float2 B = __ldg(wb.ptr());
       if (k == 0 || k == N / 2) {
         buf[fidx<Q>(k, ql)] = make_float2(A.x, B.x);          // c2r ignores Im of DC / Nyquist
       } else {
         buf[fidx<Q>(k, ql)] = make_float2(A.x - B.y, A.y + B.x);
         buf[fidx<Q>(N - k, ql)] = make_float2(A.x + B.y, B.x - A.y);
       }
-      wa.advance(TPL);
-      wb.advance(TPL);
+      wa.advance(TPL, peers);
+      wb.advance(TPL, peers);
     }
   }
   __syncthreads();
@@ -584,6 +589,7 @@ struct RowMap {          // element offset of (b, x, ky) = (x >> sh)*chunk_strid
   long long chunk_stride, img_stride;
   int dup_row;           // >= 0: rows with (x & mask) == 0 are also stored at local row dup_row of the previous chunk
   int nchunks;
+  int use_peers;         // chunk c lives at peers.p[c] (chunk_stride ignored): peer-memory exchange
 };
 __device__ __forceinline__ size_t rowmap_off(const RowMap& m, int b, int x, int ky) {
   return (size_t)(x >> m.sh) * m.chunk_stride + (size_t)b * m.img_stride + (size_t)(x & m.mask) * m.pitch + ky;
@@ -616,8 +622,8 @@ k_xsplit_fwd(const float2* __restrict__ S, RowMap m, float2* __restrict__ T, con
 
 template <int R0>
 __global__ void __launch_bounds__(128)
-k_xsplit_inv(const float2* __restrict__ T, float2* __restrict__ S, RowMap m, const float2* __restrict__ twx, int n2len,
-             int pitch_t) {
+k_xsplit_inv(const float2* __restrict__ T, float2* __restrict__ S, SpecPeers peers, RowMap m,
+             const float2* __restrict__ twx, int n2len, int pitch_t) {
   pdl_launch_dependents();
   pdl_wait();
   const int ky = blockIdx.x * blockDim.x + threadIdx.x;
@@ -638,10 +644,19 @@ k_xsplit_inv(const float2* __restrict__ T, float2* __restrict__ S, RowMap m, con
 #pragma unroll
   for (int n1 = 0; n1 < R0; ++n1) {
     const int x = n1 * n2len + n2;
-    S[rowmap_off(m, b, x, ky)] = v[n1];
-    if (m.dup_row >= 0 && (x & m.mask) == 0) {
-      const int ch = ((x >> m.sh) + m.nchunks - 1) % m.nchunks;
-      S[(size_t)ch * m.chunk_stride + (size_t)b * m.img_stride + (size_t)m.dup_row * m.pitch + ky] = v[n1];
+    if (!m.use_peers) {
+      S[rowmap_off(m, b, x, ky)] = v[n1];
+      if (m.dup_row >= 0 && (x & m.mask) == 0) {
+        const int ch = ((x >> m.sh) + m.nchunks - 1) % m.nchunks;
+        S[(size_t)ch * m.chunk_stride + (size_t)b * m.img_stride + (size_t)m.dup_row * m.pitch + ky] = v[n1];
+      }
+    } else {
+      const int ch = x >> m.sh;
+      spec_peer(peers, ch)[(size_t)b * m.img_stride + (size_t)(x & m.mask) * m.pitch + ky] = v[n1];
+      if (m.dup_row >= 0 && (x & m.mask) == 0) {
+        const int cp = (ch + m.nchunks - 1) % m.nchunks;
+        spec_peer(peers, cp)[(size_t)b * m.img_stride + (size_t)m.dup_row * m.pitch + ky] = v[n1];
+      }
     }
   }
 }
@@ -886,8 +901,8 @@ int launch_project_cluster(float* u, float* v, float* pout, const float* inv_eig
 // launchers
 // ---------------------------------------------------------------------------------------------
 template <int N, bool SLAB>
-static int launch_div_rfft_n(const float* u, const float* v, float2* S, const float2* tw, const SolverParams& p,
-                             cudaStream_t st) {
+static int launch_div_rfft_n(const float* u, const float* v, float2* S, const SpecPeers& peers, const float2* tw,
+                             const SolverParams& p, cudaStream_t st) {
   using C = RowCfg<N>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -895,13 +910,13 @@ static int launch_div_rfft_n(const float* u, const float* v, float2* S, const fl
     attr_done = true;
   }
   dim3 grid(p.nx / (2 * C::Q), p.batch);
-  MLSIM_CUDA_CHECK(launch_pdl(k_div_rfft<N, SLAB>, grid, dim3(C::THREADS), C::SMEM, st, u, v, S, tw, p));
+  MLSIM_CUDA_CHECK(launch_pdl(k_div_rfft<N, SLAB>, grid, dim3(C::THREADS), C::SMEM, st, u, v, S, peers, tw, p));
   return MLSIM_OK;
 }
 
 template <int N, bool SLAB>
-static int launch_irfft_grad_n(const float2* S, const float* uin, const float* vin, float* uout, float* vout,
-                               float* pout, const float2* tw, const SolverParams& p, cudaStream_t st) {
+static int launch_irfft_grad_n(const float2* S, const SpecPeers& peers, const float* uin, const float* vin, float* uout,
+                               float* vout, float* pout, const float2* tw, const SolverParams& p, cudaStream_t st) {
   using C = RowCfg<N>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -910,7 +925,7 @@ static int launch_irfft_grad_n(const float2* S, const float* uin, const float* v
   }
   const int rows = 2 * C::Q - 1;
   dim3 grid((p.nx + rows - 1) / rows, p.batch);
-  MLSIM_CUDA_CHECK(launch_pdl(k_irfft_grad<N, SLAB>, grid, dim3(C::THREADS), C::SMEM, st, S, uin, vin, uout, vout, pout, tw, p));
+  MLSIM_CUDA_CHECK(launch_pdl(k_irfft_grad<N, SLAB>, grid, dim3(C::THREADS), C::SMEM, st, S, peers, uin, vin, uout, vout, pout, tw, p));
   return MLSIM_OK;
 }
 
@@ -951,15 +966,29 @@ static int launch_col_solve_n(float2* S, const float* inv_eig, const float2* tw,
     default: set_error("unsupported column transform length (need a power of two in [64, 2048])"); return MLSIM_EINVAL; \
   }
 
+// slab mode: chunk r of the half spectrum goes to peers.p[r]; plain mode: S
+static SpecPeers local_chunks(float2* base, size_t chunk_elems, int world) {
+  SpecPeers q;
+  for (int r = 0; r < MLSIM_MAX_SLAB_RANKS; ++r) q.p[r] = base ? base + (size_t)(r < world ? r : 0) * chunk_elems : nullptr;
+  return q;
+}
 int launch_div_rfft(const float* u, const float* v, float2* S, const float2* tw_y, const SolverParams& p,
-                    cudaStream_t st) {
-  if (p.halo > 0) { MLSIM_DISPATCH_ROW(p.ny, (launch_div_rfft_n<N_, true>(u, v, S, tw_y, p, st))); }
-  MLSIM_DISPATCH_ROW(p.ny, (launch_div_rfft_n<N_, false>(u, v, S, tw_y, p, st)));
+                    cudaStream_t st, const SpecPeers* peers, int world) {
+  if (p.halo > 0) {
+    const SpecPeers q = peers ? *peers : local_chunks(S, (size_t)p.batch * p.nx * p.kywp, world);
+    MLSIM_DISPATCH_ROW(p.ny, (launch_div_rfft_n<N_, true>(u, v, S, q, tw_y, p, st)));
+  }
+  const SpecPeers none = local_chunks(nullptr, 0, 0);
+  MLSIM_DISPATCH_ROW(p.ny, (launch_div_rfft_n<N_, false>(u, v, S, none, tw_y, p, st)));
 }
 int launch_irfft_grad(const float2* S, const float* uin, const float* vin, float* uout, float* vout, float* pout,
-                      const float2* tw_y, const SolverParams& p, cudaStream_t st) {
-  if (p.halo > 0) { MLSIM_DISPATCH_ROW(p.ny, (launch_irfft_grad_n<N_, true>(S, uin, vin, uout, vout, pout, tw_y, p, st))); }
-  MLSIM_DISPATCH_ROW(p.ny, (launch_irfft_grad_n<N_, false>(S, uin, vin, uout, vout, pout, tw_y, p, st)));
+                      const float2* tw_y, const SolverParams& p, cudaStream_t st, int world) {
+  if (p.halo > 0) {
+    const SpecPeers q = local_chunks(const_cast<float2*>(S), (size_t)p.batch * (p.nx + 1) * p.kywp, world);
+    MLSIM_DISPATCH_ROW(p.ny, (launch_irfft_grad_n<N_, true>(S, q, uin, vin, uout, vout, pout, tw_y, p, st)));
+  }
+  const SpecPeers none = local_chunks(nullptr, 0, 0);
+  MLSIM_DISPATCH_ROW(p.ny, (launch_irfft_grad_n<N_, false>(S, none, uin, vin, uout, vout, pout, tw_y, p, st)));
 }
 // `n` rows per image, `images` images in the plain buffer S, image i scaled by table image i % eig_images
 int launch_col_solve(float2* S, const float* inv_eig, const float2* tw_x, const SolverParams& p, int n, int images,
@@ -970,29 +999,30 @@ int launch_col_solve(float2* S, const float* inv_eig, const float2* tw_x, const 
 // Row maps of the three spectral buffer layouts the split passes read / write.
 static RowMap rowmap_plain(int nx, int pitch) {
   RowMap m; m.sh = 31; m.mask = 0x7fffffff; m.pitch = pitch; m.chunk_stride = 0; m.img_stride = (long long)nx * pitch;
-  m.dup_row = -1; m.nchunks = 1; return m;
+  m.dup_row = -1; m.nchunks = 1; m.use_peers = 0; return m;
 }
 static RowMap rowmap_chunks(int nxl, int rows, int batch, int pitch, int world, bool dup) {
   RowMap m; m.sh = ilog2(nxl); m.mask = nxl - 1; m.pitch = pitch; m.img_stride = (long long)rows * pitch;
-  m.chunk_stride = (long long)batch * rows * pitch; m.dup_row = dup ? nxl : -1; m.nchunks = world; return m;
+  m.chunk_stride = (long long)batch * rows * pitch; m.dup_row = dup ? nxl : -1; m.nchunks = world; m.use_peers = 0; return m;
 }
 
 template <int R0>
-static int launch_xsplit_r(bool fwd, float2* S, const RowMap& m, float2* T, const float2* twx, int n2len, int pitch_t,
-                           int batch, cudaStream_t st) {
+static int launch_xsplit_r(bool fwd, float2* S, const SpecPeers& peers, const RowMap& m, float2* T, const float2* twx,
+                           int n2len, int pitch_t, int batch, cudaStream_t st) {
   dim3 grid((pitch_t + 127) / 128, n2len, batch);
   if (fwd) MLSIM_CUDA_CHECK(launch_pdl(k_xsplit_fwd<R0>, grid, dim3(128), 0, st, S, m, T, twx, n2len, pitch_t));
-  else MLSIM_CUDA_CHECK(launch_pdl(k_xsplit_inv<R0>, grid, dim3(128), 0, st, T, S, m, twx, n2len, pitch_t));
+  else MLSIM_CUDA_CHECK(launch_pdl(k_xsplit_inv<R0>, grid, dim3(128), 0, st, T, S, peers, m, twx, n2len, pitch_t));
   return MLSIM_OK;
 }
 static int launch_xsplit(bool fwd, int r0, float2* S, const RowMap& m, float2* T, const float2* twx, int n2len,
-                         int pitch_t, int batch, cudaStream_t st) {
+                         int pitch_t, int batch, cudaStream_t st, const SpecPeers* peers_or_null = nullptr) {
+  const SpecPeers peers = peers_or_null ? *peers_or_null : local_chunks(nullptr, 0, 0);
   switch (r0) {
-    case 1: return launch_xsplit_r<1>(fwd, S, m, T, twx, n2len, pitch_t, batch, st);
-    case 2: return launch_xsplit_r<2>(fwd, S, m, T, twx, n2len, pitch_t, batch, st);
-    case 4: return launch_xsplit_r<4>(fwd, S, m, T, twx, n2len, pitch_t, batch, st);
-    case 8: return launch_xsplit_r<8>(fwd, S, m, T, twx, n2len, pitch_t, batch, st);
-    case 16: return launch_xsplit_r<16>(fwd, S, m, T, twx, n2len, pitch_t, batch, st);
+    case 1: return launch_xsplit_r<1>(fwd, S, peers, m, T, twx, n2len, pitch_t, batch, st);
+    case 2: return launch_xsplit_r<2>(fwd, S, peers, m, T, twx, n2len, pitch_t, batch, st);
+    case 4: return launch_xsplit_r<4>(fwd, S, peers, m, T, twx, n2len, pitch_t, batch, st);
+    case 8: return launch_xsplit_r<8>(fwd, S, peers, m, T, twx, n2len, pitch_t, batch, st);
+    case 16: return launch_xsplit_r<16>(fwd, S, peers, m, T, twx, n2len, pitch_t, batch, st);
     default: set_error("unsupported outer radix of the split x-transform"); return MLSIM_EINVAL;
   }
 }
@@ -1011,16 +1041,18 @@ int launch_col_solve_split(float2* S, float2* T, const float* inv_eig_perm, cons
 // Slab decomposition, this rank's share of the spectrum (kyv valid columns, pitch kywp), all nxg rows:
 //   recv [world][b][nxl][kywp]  ->  T[b][r0][n2len][kywp]  -> K3 ->  send2 [world][b][nxl+1][kywp] (halo row duplicated)
 int launch_col_solve_slab(const float2* recv, float2* send2, float2* T, const float* inv_eig_perm, const float2* twx_full,
-                          const float2* tw_n2, const SolverParams& p, int nxg, int world, int kyv, int r0, cudaStream_t st) {
+                          const float2* tw_n2, const SolverParams& p, int nxg, int world, int kyv, int r0, cudaStream_t st,
+                          const SpecPeers* peers) {
   const int n2len = nxg / r0;
   const RowMap min_ = rowmap_chunks(p.nx, p.nx, p.batch, p.kywp, world, false);
-  const RowMap mout = rowmap_chunks(p.nx, p.nx + 1, p.batch, p.kywp, world, true);
+  RowMap mout = rowmap_chunks(p.nx, p.nx + 1, p.batch, p.kywp, world, true);
+  mout.use_peers = peers ? 1 : 0;
   SolverParams q = p;
   q.nyc = kyv; q.nycp = p.kywp;
   int rc;
   if ((rc = launch_xsplit(true, r0, const_cast<float2*>(recv), min_, T, twx_full, n2len, p.kywp, p.batch, st))) return rc;
   if ((rc = launch_col_solve(T, inv_eig_perm, tw_n2, q, n2len, p.batch * r0, r0, st))) return rc;
-  return launch_xsplit(false, r0, send2, mout, T, twx_full, n2len, p.kywp, p.batch, st);
+  return launch_xsplit(false, r0, send2, mout, T, twx_full, n2len, p.kywp, p.batch, st, peers);
 }
 
 }  // namespace mlsim

@@ -14,7 +14,10 @@ owns the global rows ``[r*nxl, (r+1)*nxl)`` (array axis 0 = x; rows stay contigu
     at the edges of the global grid, so this exchange is NOT periodic) -- the activations themselves never travel.
 
 All arithmetic is in the sm_100a kernels behind ``mlsim_slab_*`` (include/mlsim.h); this module only sequences them
-and moves bytes with ``torch.distributed`` (NCCL on GPUs).  ``SlabStepper`` is written against a small backend
+and moves bytes with ``torch.distributed`` (NCCL on GPUs).  With ``SlabComm(..., p2p=True)`` the two spectral
+all-to-alls per projection disappear: the receive buffers are symmetric memory (``torch.distributed._symmetric_memory``,
+NVLink peer mappings), the producing kernels (divergence + row FFT; the inverse split pass of the x-solve) store every
+column chunk straight into the consuming rank's buffer while they compute, and only a device-side barrier remains.  ``SlabStepper`` is written against a small backend
 interface so that the sequencing and every buffer layout can be checked on CPU (gloo, world size 2) against a layout
 -exact numpy model in ``tests/slab_model.py``; the product backend is ``CudaSlabBackend`` and there is no other.
 """
@@ -96,14 +99,49 @@ class SlabGeometry:
 
 
 class SlabComm:
-    """The three exchanges of the slab step over a torch.distributed process group (None: single rank)."""
+    """The three exchanges of the slab step over a torch.distributed process group (None: single rank).
 
-    def __init__(self, geom: SlabGeometry, group=None):
+    p2p=True (GPUs of one NVLink domain, world > 1): spectral chunks travel as peer-memory stores issued by the
+    producing kernels; ``spectral_exchange`` is then only a cross-rank barrier."""
+
+    BARRIER_TIMEOUT_MS = 20000
+
+    def __init__(self, geom: SlabGeometry, group=None, p2p: bool = False):
         self.g = geom
         self.group = group
         if geom.world > 1 and not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("slab world > 1 needs an initialised torch.distributed process group")
+        self.p2p = bool(p2p) and geom.world > 1
         self._stage = {}
+        self._symm = []           # (tensor, handle) of the symmetric receive buffers
+
+    # ------------------------------------------------------------------ spectral buffers
+    def make_spectral_buffers(self, backend):
+        """(send, recv, send2, recv2).  NCCL: four local buffers.  p2p: recv / recv2 are symmetric memory registered
+        with the backend (mlsim_slab_set_peers); send / send2 are None (the kernels write into the peers)."""
+        if not self.p2p:
+            return backend.new_spec(False), backend.new_spec(False), backend.new_spec(True), backend.new_spec(True)
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = self.group if self.group is not None else dist.group.WORLD
+        bufs, ptrs = [], []
+        for backward in (False, True):
+            t = symm_mem.empty(self.g.spec_shape(backward), dtype=torch.float32, device=backend.device)
+            t.zero_()                                    # padding columns are never written by the kernels
+            h = symm_mem.rendezvous(t, grp)
+            self._symm.append((t, h))
+            bufs.append(t)
+            ptrs.append([int(x) for x in h.buffer_ptrs])
+        torch.cuda.synchronize(backend.device)
+        dist.barrier(group=self.group)                   # every rank's buffers are zeroed before anyone stores into them
+        backend.set_peers(ptrs[0], ptrs[1])
+        return None, bufs[0], None, bufs[1]
+
+    def spectral_exchange(self, send, recv, which: int) -> None:
+        """Chunk r of this rank's half spectrum -> rank r (which: 0 forward, 1 backward)."""
+        if self.p2p:
+            self._symm[which][1].barrier(channel=which, timeout_ms=self.BARRIER_TIMEOUT_MS)
+        else:
+            self.all_to_all(send, recv)
 
     def _bufs(self, like: torch.Tensor, n: int):
         key = (n, like.device, like.dtype)
@@ -187,15 +225,19 @@ class CudaSlabBackend:
     def _st() -> int:
         return torch.cuda.current_stream().cuda_stream
 
+    @staticmethod
+    def _p(t):
+        return None if t is None else t.data_ptr()      # None: the kernels store into the registered peer buffers
+
     def stage_a(self, stage, us, u0, acc, out, spec_send):
         _lib.check(self._lib.mlsim_slab_stage_a(self._h, stage, us.data_ptr(), u0.data_ptr(), acc.data_ptr(),
-                                                out.data_ptr(), spec_send.data_ptr(), self._st()))
+                                                out.data_ptr(), self._p(spec_send), self._st()))
 
     def divergence_rfft(self, uv, spec_send):
-        _lib.check(self._lib.mlsim_slab_divergence_rfft(self._h, uv.data_ptr(), spec_send.data_ptr(), self._st()))
+        _lib.check(self._lib.mlsim_slab_divergence_rfft(self._h, uv.data_ptr(), self._p(spec_send), self._st()))
 
     def stage_b(self, spec_recv, spec_send2):
-        _lib.check(self._lib.mlsim_slab_stage_b(self._h, spec_recv.data_ptr(), spec_send2.data_ptr(), self._st()))
+        _lib.check(self._lib.mlsim_slab_stage_b(self._h, spec_recv.data_ptr(), self._p(spec_send2), self._st()))
 
     def stage_c(self, spec_recv2, uv, p=None):
         _lib.check(self._lib.mlsim_slab_stage_c(self._h, spec_recv2.data_ptr(), uv.data_ptr(),
@@ -203,6 +245,12 @@ class CudaSlabBackend:
 
     def cnn_correct(self, uv, scale):
         _lib.check(self._lib.mlsim_slab_cnn_correct(self._h, uv.data_ptr(), float(scale), self._st()))
+
+    def set_peers(self, fwd_ptrs, bwd_ptrs):
+        n = len(fwd_ptrs)
+        a = (C.c_uint64 * n)(*fwd_ptrs)
+        b = (C.c_uint64 * n)(*bwd_ptrs)
+        _lib.check(self._lib.mlsim_slab_set_peers(self._h, a, b))
 
     def set_cnn(self, layers):
         self.plan.set_cnn(layers)
@@ -221,8 +269,7 @@ class SlabStepper:
         self.comm = comm if comm is not None else SlabComm(self.g)
         b = backend
         self.state, self.w1, self.w2, self.acc = (b.new_field_pair() for _ in range(4))
-        self.send, self.recv = b.new_spec(False), b.new_spec(False)
-        self.send2, self.recv2 = b.new_spec(True), b.new_spec(True)
+        self.send, self.recv, self.send2, self.recv2 = self.comm.make_spectral_buffers(b)
         self.pressure = None
         self.exchanges = 0
 
@@ -257,9 +304,9 @@ class SlabStepper:
     # ------------------------------------------------------------------ the step
     def _project_tail(self, out, p=None):
         c, be = self.comm, self.be
-        c.all_to_all(self.send, self.recv)
+        c.spectral_exchange(self.send, self.recv, 0)
         be.stage_b(self.recv, self.send2)
-        c.all_to_all(self.send2, self.recv2)
+        c.spectral_exchange(self.send2, self.recv2, 1)
         be.stage_c(self.recv2, out, p)
         self.exchanges += 2
 

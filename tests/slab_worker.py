@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--out", default="")
+    ap.add_argument("--p2p", type=int, default=0)
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -46,7 +47,7 @@ def main():
     model = models.buildModel(cfgj)
     model.load_state_dict(sd)
     be.set_cnn(model.cnn.folded_layers())
-    stp = SlabStepper(be, SlabComm(geom))
+    stp = SlabStepper(be, SlabComm(geom, p2p=bool(a.p2p)))
 
     res = {}
     stp.scatter(u64.float().to(dev), v64.float().to(dev))
@@ -64,7 +65,7 @@ def main():
         model.attach(plan)
         pu, pv = u64.float().to(dev), v64.float().to(dev)
         plan.step(pu, pv, nsteps=a.steps, apply_cnn=True)
-        res = {"world": world, "solver_vs_oracle_u": rel(u, ou), "solver_vs_oracle_v": rel(v, ov),
+        res = {"world": world, "p2p": a.p2p, "solver_vs_oracle_u": rel(u, ou), "solver_vs_oracle_v": rel(v, ov),
                "o32_vs_oracle_u": rel(qu, ou), "o32_vs_oracle_v": rel(qv, ov),
                "cnn_vs_bf16_oracle_u": rel(uc, eu), "cnn_vs_bf16_oracle_v": rel(vc, ev),
                "vs_plain_plan_u": rel(uc, pu), "vs_plain_plan_v": rel(vc, pv), "exchanges": stp.exchanges}

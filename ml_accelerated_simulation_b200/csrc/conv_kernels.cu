@@ -27,6 +27,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// max(x, 0) and round-to-nearest bf16 of two values in ONE instruction; `a` goes to the low half (even channel)
+__device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
 
 // =============================================================================================
 // First layer: 2 -> 64 channels.  K = 9 taps * 2 ch = 18, zero padded to 32 (two K16 MMAs).
@@ -44,14 +50,12 @@ __global__ void __launch_bounds__(CF_THREADS)
 k_conv_first(ConvFirstArgs a) {
   __shared__ __align__(128) uint8_t sA[2][4 * CF_LBO_A];
   __shared__ __align__(128) uint8_t sW[CF_WBYTES];
-  __shared__ float sBias[64];
   __shared__ __align__(8) uint64_t mbar[2];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < CF_WBYTES / 16; i += CF_THREADS)
     reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(a.wimg) + i);
-  if (tid < 64) sBias[tid] = __ldg(reinterpret_cast<const float*>(a.wimg + CF_WBYTES) + tid);
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
@@ -74,23 +78,41 @@ k_conv_first(ConvFirstArgs a) {
   const int ntiles = a.batch * a.nx * nyt;
   const size_t plane = (size_t)(a.ny + 2);
 
+  // Every CTA walks a CONTIGUOUS range of tiles (row tiles of one image row after the other), so the position
+  // (b, x, yt) is decoded once and then advanced incrementally -- no integer division on the per-tile path.
+  struct Pos { int b, x, yt; };
+  const int per = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int t0 = (int)blockIdx.x * per;
+  const int t1 = min(t0 + per, ntiles);
+  const int dir = a.reverse ? -1 : 1;
+  auto decode = [&](int t) {
+    const int tile = a.reverse ? (ntiles - 1 - t) : t;
+    Pos q;
+    q.yt = tile % nyt;
+    q.x = (tile / nyt) % a.nx;
+    q.b = tile / (nyt * a.nx);
+    return q;
+  };
+  auto advance = [&](Pos q) {
+    q.yt += dir;
+    if (q.yt == nyt) { q.yt = 0; if (++q.x == a.nx) { q.x = 0; ++q.b; } }
+    else if (q.yt < 0) { q.yt = nyt - 1; if (--q.x < 0) { q.x = a.nx - 1; --q.b; } }
+    return q;
+  };
+
   // ---- im2col row of this thread's pixel: k = (i*3 + j)*2 + ch, i <-> dx+1, j <-> dy+1 ----
-  auto load_vals = [&](int tile_, float (&val)[18]) {
-    const int tile = a.reverse ? (ntiles - 1 - tile_) : tile_;
-    const int yt = tile % nyt;
-    const int x = (tile / nyt) % a.nx;
-    const int b = tile / (nyt * a.nx);
-    const int y = yt * 128 + tid;
-    const float* __restrict__ gu = a.u + (size_t)b * a.img_stride;
-    const float* __restrict__ gv = a.v + (size_t)b * a.img_stride;
+  auto load_vals = [&](const Pos& q, float (&val)[18]) {
+    const int y = q.yt * 128 + tid;
+    const float* __restrict__ gu = a.u + (size_t)q.b * a.img_stride + (ptrdiff_t)q.x * a.ny + y;
+    const float* __restrict__ gv = a.v + (size_t)q.b * a.img_stride + (ptrdiff_t)q.x * a.ny + y;
+    const bool rowok[3] = {q.x > 0, true, q.x + 1 < a.nx};
+    const bool colok[3] = {y > 0 && y - 1 < a.ny, y < a.ny, y + 1 < a.ny};
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      const int xx = x + i - 1;
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        const int yy = y + j - 1;
-        const bool in = (xx >= 0) && (xx < a.nx) && (yy >= 0) && (yy < a.ny);
-        const size_t off = (size_t)xx * a.ny + yy;
+        const bool in = rowok[i] && colok[j];
+        const ptrdiff_t off = (ptrdiff_t)(i - 1) * a.ny + (j - 1);
         val[(i * 3 + j) * 2 + 0] = in ? __ldg(gu + off) : 0.0f;
         val[(i * 3 + j) * 2 + 1] = in ? __ldg(gv + off) : 0.0f;
       }
@@ -105,7 +127,9 @@ k_conv_first(ConvFirstArgs a) {
     c0.z = pack_bf16(s[4], s[5]);   c0.w = pack_bf16(s[6], s[7]);
     c1.x = pack_bf16(s[8], s[9]);   c1.y = pack_bf16(s[10], s[11]);
     c1.z = pack_bf16(s[12], s[13]); c1.w = pack_bf16(s[14], s[15]);
-    c2.x = pack_bf16(s[16], s[17]); c2.y = 0u; c2.z = 0u; c2.w = 0u;
+    c2.x = pack_bf16(s[16], s[17]);
+    c2.y = 0x3f803f80u;                 // k = 18, 19: constant 1.0 -> the GEMM adds bias_hi + bias_lo (packed weights)
+    c2.z = 0u; c2.w = 0u;
     uint8_t* A = sA[buf];
     *reinterpret_cast<uint4*>(A + 0 * CF_LBO_A + tid * 16) = c0;
     *reinterpret_cast<uint4*>(A + 1 * CF_LBO_A + tid * 16) = c1;
@@ -126,20 +150,20 @@ k_conv_first(ConvFirstArgs a) {
     }
   };
 
-  int tile = blockIdx.x;
   float val[18];
-  if (tile < ntiles) {
-    load_vals(tile, val);
+  Pos cur = decode(t0 < ntiles ? t0 : 0);
+  if (t0 < t1) {
+    load_vals(cur, val);
     store_a(0, val);
     __syncthreads();
     issue(0);
   }
   uint32_t parity0 = 0, parity1 = 0;
-  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+  for (int t = t0, it = 0; t < t1; ++t, ++it) {
     const int buf = it & 1;
-    const int next = tile + gridDim.x;
-    const bool has_next = next < ntiles;
-    if (has_next) load_vals(next, val);                 // loads fly while we wait for this tile's MMAs
+    const bool has_next = t + 1 < t1;
+    const Pos nxt = advance(cur);
+    if (has_next) load_vals(nxt, val);                  // loads fly while we wait for this tile's MMAs
     if (buf == 0) { mbar_wait(&mbar[0], parity0); parity0 ^= 1; }
     else          { mbar_wait(&mbar[1], parity1); parity1 ^= 1; }
     tc_fence_after();
@@ -153,29 +177,23 @@ k_conv_first(ConvFirstArgs a) {
     __syncthreads();                                    // A[buf^1] complete; accumulator `buf` fully read
     if (has_next) issue(buf ^ 1);
 
-    const int tile_r = a.reverse ? (ntiles - 1 - tile) : tile;
-    const int yt = tile_r % nyt;
-    const int x = (tile_r / nyt) % a.nx;
-    const int b = tile_r / (nyt * a.nx);
-    const int y = yt * 128 + tid;
+    const int y = cur.yt * 128 + tid;
     if (y < a.ny) {
       uint8_t* orow = reinterpret_cast<uint8_t*>(a.out) +
-                      ((((size_t)b * a.nx + x) * 8) * plane + (size_t)(y + 1)) * 16;
+                      ((((size_t)cur.b * a.nx + cur.x) * 8) * plane + (size_t)(y + 1)) * 16;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        float f[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int ch = c * 8 + e;
-          const float acc = __uint_as_float(ch < 32 ? r0[ch & 31] : r1[ch & 31]);
-          f[e] = fmaxf(acc + sBias[ch], 0.0f);
-        }
+        // the bias is already in the accumulator: ReLU + bf16 pack is one cvt.rn.relu per channel pair
+        const uint32_t* r = (c < 4) ? &r0[c * 8] : &r1[(c - 4) * 8];
         uint4 o;
-        o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
-        o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+        o.x = pack_bf16_relu(__uint_as_float(r[0]), __uint_as_float(r[1]));
+        o.y = pack_bf16_relu(__uint_as_float(r[2]), __uint_as_float(r[3]));
+        o.z = pack_bf16_relu(__uint_as_float(r[4]), __uint_as_float(r[5]));
+        o.w = pack_bf16_relu(__uint_as_float(r[6]), __uint_as_float(r[7]));
         *reinterpret_cast<uint4*>(orow + (size_t)c * plane * 16) = o;
       }
     }
+    cur = nxt;
   }
 
   tc_fence_before();
@@ -217,7 +235,7 @@ template <int NB> struct ConvMidSmem {
 };
 
 template <int NB, bool LAST>
-__global__ void __launch_bounds__(LAST ? CM_THREADS_LAST : CM_THREADS_MID, 1)
+__global__ void __launch_bounds__(LAST ? CM_THREADS_LAST : CM_THREADS_MID, LAST ? 2 : 1)
 k_conv_mid(ConvMidArgs a) {
   constexpr int EPI_WARPS = LAST ? 4 : 8;
   using L = ConvMidSmem<NB>;
@@ -407,17 +425,12 @@ k_conv_mid(ConvMidArgs a) {
         // last layer: fetch the state this row's correction is added to BEFORE waiting for the accumulator, so the
         // global-load latency hides behind the wait instead of serialising the epilogue
         float u_old = 0.0f, v_old = 0.0f;
-        uint4 rres[LAST ? 8 : 4];                         // shortcut operand, fetched before the accumulator wait
+        uint4 rres[LAST ? 1 : 4];                         // mid layers: shortcut operand, fetched before the accumulator wait
         if constexpr (LAST) {
           if (a.y_nchw == nullptr && y < a.ny) {
             const size_t off0 = (size_t)b * a.img_stride + (size_t)x * a.ny + y;
             u_old = a.u[off0];
             v_old = a.v[off0];
-          }
-          if (a.res_mode == 3 && y < a.ny) {
-            const uint8_t* rrow = reinterpret_cast<const uint8_t*>(a.res) + ((((size_t)b * a.nx + x) * 8) * plane + (size_t)(y + 1)) * 16;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) rres[c] = __ldg(reinterpret_cast<const uint4*>(rrow + (size_t)c * plane * 16));
           }
         } else {
           if (a.res_mode == 1 && y < a.ny) {
@@ -479,13 +492,14 @@ k_conv_mid(ConvMidArgs a) {
                   f[e] = fmaf(sExtra[2 * ch], u_old, fmaf(sExtra[2 * ch + 1], v_old, f[e]));
                 }
               }
-              if (a.relu) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
-              }
               uint4 o;
-              o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
-              o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+              if (a.relu) {
+                o.x = pack_bf16_relu(f[0], f[1]); o.y = pack_bf16_relu(f[2], f[3]);
+                o.z = pack_bf16_relu(f[4], f[5]); o.w = pack_bf16_relu(f[6], f[7]);
+              } else {
+                o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+                o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+              }
               *reinterpret_cast<uint4*>(orow + (size_t)c * plane * 16) = o;
             }
           }
@@ -511,9 +525,11 @@ k_conv_mid(ConvMidArgs a) {
 #pragma unroll
             for (int co = 0; co < 16; ++co) o[co] = __uint_as_float(r[co]) + sBias[co];
             if (a.res_mode == 3) {                        // 1x1 shortcut of the block input (64 channels of this pixel)
-#pragma unroll
+              const uint8_t* rrow = reinterpret_cast<const uint8_t*>(a.res) + ((((size_t)b * a.nx + x) * 8) * plane + (size_t)(y + 1)) * 16;
+#pragma unroll 2
               for (int c = 0; c < 8; ++c) {
-                const uint32_t w[4] = {rres[c].x, rres[c].y, rres[c].z, rres[c].w};
+                const uint4 rr = __ldg(reinterpret_cast<const uint4*>(rrow + (size_t)c * plane * 16));
+                const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
                 for (int e2 = 0; e2 < 4; ++e2) {
                   const float x0 = __uint_as_float(w[e2] << 16), x1 = __uint_as_float(w[e2] & 0xffff0000u);

@@ -446,13 +446,21 @@ int64_t mlsim_cnn_pack_host(int32_t kind, int32_t cin, int32_t cout, const doubl
   uint16_t* q = reinterpret_cast<uint16_t*>(img);
   int nbias;
   if (kind == 0) {
-    // [chunk c (4)][n (64)][8] with k = c*8+e = (i*3+j)*2 + ch   (i <-> dx+1, j <-> dy+1)
+    // [chunk c (4)][n (64)][8] with k = c*8+e = (i*3+j)*2 + ch   (i <-> dx+1, j <-> dy+1);
+    // k = 18, 19 multiply a constant-1 input: the bias rounded to bf16 and the remainder of that rounding, so the GEMM
+    // itself adds the bias to 2^-17 relative accuracy and the epilogue is a bare ReLU + pack
     for (int c = 0; c < 4; ++c)
       for (int n = 0; n < 64; ++n)
         for (int e = 0; e < 8; ++e) {
           const int k = c * 8 + e;
           float val = 0.0f;
           if (k < 18) { const int tap = k / 2, ch = k % 2; val = W(n, ch, tap / 3, tap % 3); }
+          else if (k < 20 && n < cout) {
+            const float bf = (float)bias[n];
+            const uint32_t hb = (uint32_t)f32_to_bf16_rne(bf) << 16;
+            float hi; memcpy(&hi, &hb, 4);
+            val = (k == 18) ? hi : (bf - hi);
+          }
           q[((size_t)c * 64 + n) * 8 + e] = f32_to_bf16_rne(val);
         }
     nbias = 64;

@@ -45,7 +45,9 @@ def test_three_layer_network_matches_torch(built_lib, nx, ny, rs):
     r2 = F.conv2d(r1, _q(torch.tensor(w2)), fb(b2), padding=1)
     a0 = M.unpack_activation(act0, B, nx, ny)
     a1 = M.unpack_activation(act1, B, nx, ny)
-    assert np.array_equal(a0[:, :5], r0.numpy().astype(np.float32)) and not a0[:, 5:].any()
+    # first layer: the bias travels through the GEMM as bf16 hi + lo parts (2^-17 relative): bf16 ulp flips only
+    assert np.abs(a0[:, :5] - r0.numpy()).max() <= 2 ** -7 * np.abs(r0.numpy()).max() and not a0[:, 5:].any()
+    assert np.abs(a0[:, :5] - r0.numpy()).mean() < 1e-6
     assert np.abs(a1[:, :7] - r1.numpy()).max() <= 2 ** -7 * np.abs(r1.numpy()).max()    # bf16 ulp flips only
     assert np.abs(a1[:, :7] - r1.numpy()).mean() < 1e-5 and not a1[:, 7:].any()
     assert np.abs(y[:, :2] - r2.numpy()).max() < 1e-2 * np.abs(r2.numpy()).max()

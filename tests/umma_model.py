@@ -111,6 +111,7 @@ def conv_first_model(u, v, wimg: np.ndarray, scale: float):
                             if 0 <= xx < nx and 0 <= yy < ny:
                                 val[(i * 3 + j) * 2 + 0] = np.float32(u[b, xx, yy]) * np.float32(scale)
                                 val[(i * 3 + j) * 2 + 1] = np.float32(v[b, xx, yy]) * np.float32(scale)
+                    val[18] = val[19] = 1.0                      # bias columns (bias_hi, bias_lo in the packed weights)
                     a16[m] = bf16_bits(val)
                 for c in range(4):
                     blk = np.ascontiguousarray(a16[:, c * 8:(c + 1) * 8]).view(np.uint8).reshape(-1)
@@ -123,7 +124,7 @@ def conv_first_model(u, v, wimg: np.ndarray, scale: float):
                     y = yt * 128 + m
                     if y >= ny:
                         continue
-                    f = np.maximum(tmem[m].astype(np.float32) + bias, 0).astype(np.float32)
+                    f = np.maximum(tmem[m].astype(np.float32), 0).astype(np.float32)     # bias came through the GEMM
                     h = bf16_bits(f)
                     for c in range(8):
                         o = act_offset(b, x, c, y + 1, nx, ny)

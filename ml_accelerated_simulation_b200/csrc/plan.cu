@@ -71,6 +71,9 @@ struct mlsim_plan {
   // host-rollout staging
   float* d_hu = nullptr; float* d_hv = nullptr; float* d_hp = nullptr;
   cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
+  static constexpr int MAX_SPLIT = 8;
+  cudaStream_t split_stream[MAX_SPLIT - 1] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[MAX_SPLIT - 1] = {};
   static constexpr int MAX_CHUNKS = 4;
   cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_done[MAX_CHUNKS] = {};
   // timing scratch
@@ -286,9 +289,35 @@ int cnn_apply(mlsim_plan* pl, const float* u_in, const float* v_in, float* u, fl
 int run_steps(mlsim_plan* pl, float* u, float* v, float* p_or_null, int nsteps, int apply_cnn, double scale,
               cudaStream_t st, Chunk c) {
   int rc;
+  // The batch is cut into MLSIM_SOLVER_STREAMS blocks of independent trajectories whose solver steps run on separate
+  // streams: kernels of different blocks are in different phases (load / transform / store), so their latencies
+  // overlap where one big launch runs its CTAs in lockstep.  Joined before the correction network.
+  // Measured at config 2 (bench.py, 200 steps): solver only 0.307 / 0.287 / 0.284 ms with 1 / 2 / 4 blocks; with the
+  // correction network behind every step 1.823 (1) / 1.785 (2) / 1.805 ms (4): each join before the CNN costs a little,
+  // so rollouts with the network use 2 blocks and bare solver rollouts (data generation) 4.
+  static const int nstreams_env = [] { const char* e = getenv("MLSIM_SOLVER_STREAMS"); return e ? atoi(e) : 0; }();
+  int ns = nstreams_env > 0 ? nstreams_env : (apply_cnn ? 2 : 4);
+  if (ns > mlsim_plan::MAX_SPLIT) ns = mlsim_plan::MAX_SPLIT;
+  if (ns > c.nb) ns = c.nb;
   for (int s = 0; s < nsteps; ++s) {
     float* pp = (s == nsteps - 1) ? p_or_null : nullptr;
-    if ((rc = solver_step(pl, u, v, pp, st, c))) return rc;
+    if (ns == 1) {
+      if ((rc = solver_step(pl, u, v, pp, st, c))) return rc;
+    } else {
+      const size_t img = (size_t)pl->cfg.nx * pl->cfg.ny;
+      MLSIM_CUDA_CHECK(cudaEventRecord(pl->ev_fork, st));
+      for (int k = 0; k < ns; ++k) {
+        const int b0 = (int)((long)c.nb * k / ns), b1 = (int)((long)c.nb * (k + 1) / ns);
+        const size_t off = (size_t)b0 * img;
+        cudaStream_t sk = (k == 0) ? st : pl->split_stream[k - 1];
+        if (k > 0) MLSIM_CUDA_CHECK(cudaStreamWaitEvent(sk, pl->ev_fork, 0));
+        if ((rc = solver_step(pl, u + off, v + off, pp ? pp + off : nullptr, sk, Chunk{c.b0 + b0, b1 - b0}))) return rc;
+        if (k > 0) {
+          MLSIM_CUDA_CHECK(cudaEventRecord(pl->ev_join[k - 1], sk));
+          MLSIM_CUDA_CHECK(cudaStreamWaitEvent(st, pl->ev_join[k - 1], 0));
+        }
+      }
+    }
     if (apply_cnn && (rc = cnn_apply(pl, u, v, u, v, nullptr, scale, st, c))) return rc;
   }
   return MLSIM_OK;
@@ -403,6 +432,11 @@ int mlsim_plan_create(const mlsim_config* cfg, mlsim_plan** out) {
   }
   if (!rc) {
     cudaError_t e2 = cudaStreamCreateWithFlags(&pl->own_stream, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < mlsim_plan::MAX_SPLIT - 1 && e2 == cudaSuccess; ++i) {
+      e2 = cudaStreamCreateWithFlags(&pl->split_stream[i], cudaStreamNonBlocking);
+      if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&pl->ev_join[i], cudaEventDisableTiming);
+    }
     if (e2 != cudaSuccess) { set_error(cudaGetErrorString(e2)); rc = MLSIM_ECUDA; }
   }
   if (rc) { mlsim_plan_destroy(pl); return rc; }
@@ -420,6 +454,11 @@ int mlsim_plan_destroy(mlsim_plan* pl) {
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& l : pl->layers) if (l.d_wimg) cudaFree(l.d_wimg);
   if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
+  for (int i = 0; i < mlsim_plan::MAX_SPLIT - 1; ++i) {
+    if (pl->split_stream[i]) cudaStreamDestroy(pl->split_stream[i]);
+    if (pl->ev_join[i]) cudaEventDestroy(pl->ev_join[i]);
+  }
+  if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
   if (pl->in_stream) cudaStreamDestroy(pl->in_stream);
   if (pl->out_stream) cudaStreamDestroy(pl->out_stream);
   for (int i = 0; i < mlsim_plan::MAX_CHUNKS; ++i) { if (pl->ev_in[i]) cudaEventDestroy(pl->ev_in[i]); if (pl->ev_done[i]) cudaEventDestroy(pl->ev_done[i]); }

@@ -287,7 +287,7 @@ int cnn_apply(mlsim_plan* pl, const float* u_in, const float* v_in, float* u, fl
 
 // nsteps of {solver step; optional correction} on one block of the batch (pointers already offset to it)
 int run_steps(mlsim_plan* pl, float* u, float* v, float* p_or_null, int nsteps, int apply_cnn, double scale,
-              cudaStream_t st, Chunk c) {
+              cudaStream_t st, Chunk c, bool allow_split = true) {
   int rc;
   // The batch is cut into MLSIM_SOLVER_STREAMS blocks of independent trajectories whose solver steps run on separate
   // streams: kernels of different blocks are in different phases (load / transform / store), so their latencies
@@ -298,6 +298,7 @@ int run_steps(mlsim_plan* pl, float* u, float* v, float* p_or_null, int nsteps, 
   static const int nstreams_env = [] { const char* e = getenv("MLSIM_SOLVER_STREAMS"); return e ? atoi(e) : 0; }();
   int ns = nstreams_env > 0 ? nstreams_env : (apply_cnn ? 2 : 4);
   if (ns > mlsim_plan::MAX_SPLIT) ns = mlsim_plan::MAX_SPLIT;
+  if (!allow_split) ns = 1;
   if (ns > c.nb) ns = c.nb;
   for (int s = 0; s < nsteps; ++s) {
     float* pp = (s == nsteps - 1) ? p_or_null : nullptr;
@@ -678,6 +679,27 @@ int mlsim_step(mlsim_plan* pl, float* u, float* v, float* p_or_null, int32_t nst
   static const int nchunks_env = [] { const char* e = getenv("MLSIM_STEP_CHUNKS"); return e ? atoi(e) : 1; }();
   const int B = pl->cfg.batch;
   const int nchunks = (nchunks_env >= 1 && nchunks_env <= B) ? nchunks_env : 1;
+  // experiment hook: whole steps (solver + correction) of independent batch blocks on separate streams, so that one
+  // block's issue-bound solver kernels can share the SMs with the other block's tensor-bound convolutions
+  static const int full_streams = [] { const char* e = getenv("MLSIM_FULL_STREAMS"); return e ? atoi(e) : 1; }();
+  if (full_streams >= 2 && B >= full_streams && nsteps > 0) {
+    const int ns = full_streams > mlsim_plan::MAX_SPLIT ? mlsim_plan::MAX_SPLIT : full_streams;
+    const size_t img = (size_t)pl->cfg.nx * pl->cfg.ny;
+    MLSIM_CUDA_CHECK(cudaEventRecord(pl->ev_fork, st));
+    for (int k = 0; k < ns; ++k) {
+      const int b0 = (int)((long)B * k / ns), b1 = (int)((long)B * (k + 1) / ns);
+      const size_t off = (size_t)b0 * img;
+      cudaStream_t sk = (k == 0) ? st : pl->split_stream[k - 1];
+      if (k > 0) MLSIM_CUDA_CHECK(cudaStreamWaitEvent(sk, pl->ev_fork, 0));
+      if ((rc = run_steps(pl, u + off, v + off, p_or_null ? p_or_null + off : nullptr, nsteps, apply_cnn, cnn_input_scale,
+                          sk, Chunk{b0, b1 - b0}, false))) return rc;
+      if (k > 0) {
+        MLSIM_CUDA_CHECK(cudaEventRecord(pl->ev_join[k - 1], sk));
+        MLSIM_CUDA_CHECK(cudaStreamWaitEvent(st, pl->ev_join[k - 1], 0));
+      }
+    }
+    return MLSIM_OK;
+  }
   if (nchunks == 1) return run_steps(pl, u, v, p_or_null, nsteps, apply_cnn, cnn_input_scale, st, Chunk{0, B});
   const size_t img = (size_t)pl->cfg.nx * pl->cfg.ny;
   for (int k = 0; k < nchunks; ++k) {

@@ -94,7 +94,10 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     g = os.path.join(ROOT, "gpurun_out")
     with open(os.path.join(OUT, f"{tag}_ncu_summary.txt"), "w") as fh:
-        fh.write("ncu summaries of `python bench.py --steps 2 --warmup 1` (config 2: 256x256, batch 64) on one B200\n\n")
+        fh.write("ncu summaries of `python bench.py --steps 2 --warmup 1` (config 2: 256x256, batch 64) on one B200\n"
+                 "(the solver kernels are launched per batch block -- 2 blocks with the CNN, 4 for bare solver steps, on separate\n"
+                 " streams -- so their per-launch figures below are per block of 32 / 16 trajectories; the torch / cuFFT kernels in\n"
+                 " the launch list belong to the initial-condition generator, not to the step)\n\n")
         lc = os.path.join(g, "launches.csv")
         if os.path.exists(lc):
             summarize_launches(lc, fh)

@@ -285,6 +285,15 @@ int cnn_apply(mlsim_plan* pl, const float* u_in, const float* v_in, float* u, fl
   return run_cnn_layers(pl, u_in, v_in, u, v, y_nchw, scale, c.nx, ck.nb, (long long)c.nx * c.ny, aoff, st);
 }
 
+// number of independent batch blocks the solver part of a step is cut into (one stream each)
+int solver_blocks(int apply_cnn, int nb) {
+  static const int nstreams_env = [] { const char* e = getenv("MLSIM_SOLVER_STREAMS"); return e ? atoi(e) : 0; }();
+  int ns = nstreams_env > 0 ? nstreams_env : (apply_cnn ? 2 : 4);
+  if (ns > mlsim_plan::MAX_SPLIT) ns = mlsim_plan::MAX_SPLIT;
+  if (ns > nb) ns = nb;
+  return ns < 1 ? 1 : ns;
+}
+
 // nsteps of {solver step; optional correction} on one block of the batch (pointers already offset to it)
 int run_steps(mlsim_plan* pl, float* u, float* v, float* p_or_null, int nsteps, int apply_cnn, double scale,
               cudaStream_t st, Chunk c, bool allow_split = true) {
@@ -295,11 +304,7 @@ int run_steps(mlsim_plan* pl, float* u, float* v, float* p_or_null, int nsteps, 
   // Measured at config 2 (bench.py, 200 steps): solver only 0.307 / 0.287 / 0.284 ms with 1 / 2 / 4 blocks; with the
   // correction network behind every step 1.823 (1) / 1.785 (2) / 1.805 ms (4): each join before the CNN costs a little,
   // so rollouts with the network use 2 blocks and bare solver rollouts (data generation) 4.
-  static const int nstreams_env = [] { const char* e = getenv("MLSIM_SOLVER_STREAMS"); return e ? atoi(e) : 0; }();
-  int ns = nstreams_env > 0 ? nstreams_env : (apply_cnn ? 2 : 4);
-  if (ns > mlsim_plan::MAX_SPLIT) ns = mlsim_plan::MAX_SPLIT;
-  if (!allow_split) ns = 1;
-  if (ns > c.nb) ns = c.nb;
+  int ns = allow_split ? solver_blocks(apply_cnn, c.nb) : 1;
   for (int s = 0; s < nsteps; ++s) {
     float* pp = (s == nsteps - 1) ? p_or_null : nullptr;
     if (ns == 1) {
@@ -976,6 +981,7 @@ int mlsim_launches_per_step(mlsim_plan* pl, int32_t apply_cnn) {
   if (!pl) return MLSIM_EINVAL;
   int n = pl->cluster_projection ? 8 : 16;   // 4 stages x (explicit + cluster projection | explicit, div+rfft, column solve, irfft+grad)
   if (pl->slab || pl->r0 > 1) n = 4 * 6;     // split x-transform: explicit, div+rfft, pass A, column solve, pass C, irfft+grad
+  if (!pl->slab) n *= solver_blocks(apply_cnn && pl->cnn_ready, pl->cfg.batch);   // one set of solver launches per batch block
   if (apply_cnn && pl->cnn_ready) n += (int)pl->layers.size();
   return n;
 }

@@ -400,14 +400,12 @@ int mlsim_plan_create(const mlsim_config* cfg, mlsim_plan** out) {
   sp.halo = slab ? MLSIM_SLAB_HALO : 0;
   sp.kyw = pl->kyw; sp.kywp = pl->kywp;
   pl->field_elems = (size_t)cfg->batch * sp.nx * cfg->ny;
-  // Single-kernel projection: measured on B200 -- 128^2 x 512: 0.103 ms vs 0.117 ms for K2+K3+K4 (one CTA per image,
-  // no cluster barrier); 256^2 x 64: 0.0665 ms vs 0.0525 ms (4-CTA cluster, DSMEM transposes; the L2-resident
-  // spectral round trip is cheaper than the cluster barriers).  Default: on for nx <= 128, off above;
-  // MLSIM_CLUSTER_PROJECTION=0/1 overrides.
+  // Single-kernel projection (thread-block cluster per image, DSMEM half spectrum): measured on B200 against the
+  // three-kernel path -- 256^2 x 64: 0.0665 vs 0.0525 ms per projection; after the K2/K4 rewrites also 128^2 x 512
+  // (solver step 0.711 vs 0.565 ms) and 64^2 x 2048 (0.542 vs 0.529 ms).  Opt-in only: MLSIM_CLUSTER_PROJECTION=1.
   {
     const char* ev = getenv("MLSIM_CLUSTER_PROJECTION");
-    const bool want = ev ? (ev[0] == '1') : (cfg->nx <= 128);
-    pl->cluster_projection = !slab && project_cluster_supported(sp) && want;
+    pl->cluster_projection = !slab && project_cluster_supported(sp) && ev != nullptr && ev[0] == '1';
   }
 
   int rc = build_tables(pl);

@@ -380,3 +380,29 @@ def test_full_size_config3_cnn_crops(mlsim, mlacfd):
         got = y[b, :, x0:x0 + 80, y0:y0 + 80][:, xs, ys]
         assert ((got - ye[:, xs, ys]).norm() / ye[:, xs, ys].norm()).item() <= 1e-3
     plan.close()
+
+
+def test_trajectories_are_independent_of_batch_composition(mlsim, mlacfd):
+    """BASELINE config 4 shape (many 128x128 trajectories per GPU): the batch is cut into blocks that run on separate
+    streams and the conv kernels pick their strip length from the batch size -- neither may couple trajectories.
+    The first and last trajectory of a 96-trajectory run must equal the same two trajectories run alone."""
+    from ml_accelerated_simulation_b200 import models
+    cfgj, sd = mlacfd
+    cfg, u64, v64 = _ic(128, 128, 96, seed=77)
+    model = models.buildModel(cfgj)
+    model.load_state_dict(sd)
+    big = _plan(mlsim, cfg, 96)
+    model.attach(big)
+    u, v = u64.float().to(DEV), v64.float().to(DEV)
+    big.step(u, v, nsteps=3, apply_cnn=True)
+    pick = [0, 95]
+    small = _plan(mlsim, cfg, 2)
+    model.attach(small)
+    us, vs = u64[pick].float().to(DEV).contiguous(), v64[pick].float().to(DEV).contiguous()
+    small.step(us, vs, nsteps=3, apply_cnn=True)
+    assert rel(u[pick], us) < 2e-6 and rel(v[pick], vs) < 2e-6        # fp32 summation order of the accumulator ring only
+    ou, ov, _ = OC.rollout(u64[pick], v64[pick], cfg, 3, cfgj, sd, 1.0, round_bf16=True)
+    qu, qv, _ = OC.rollout(u64[pick].float(), v64[pick].float(), cfg, 3, cfgj, sd, 1.0, round_bf16=True)
+    assert rel(u[pick], ou) <= 4 * rel(qu, ou) + 1e-6 and rel(v[pick], ov) <= 4 * rel(qv, ov) + 1e-6
+    big.close()
+    small.close()

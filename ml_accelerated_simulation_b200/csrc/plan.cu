@@ -735,12 +735,38 @@ int mlsim_rollout_host(mlsim_plan* pl, float* hu, float* hv, float* hp, int32_t 
   // Three-stage pipeline over blocks of independent trajectories: H2D (copy engine) | steps (SMs) | D2H (copy
   // engine).  Trajectories do not interact, so block k+1 uploads while block k computes and block k-1 downloads.
   const int B = pl->cfg.batch;
+  // Block sizes: small first and last blocks (their upload / download is the only transfer time that is not hidden),
+  // a large middle block (launch efficiency), all rounded to whole "rounds" of the persistent conv grid
+  // (sm_count CTAs / work items per image) so that no block leaves most SMs idle in its last round.
+  int bounds[mlsim_plan::MAX_CHUNKS + 1] = {0};
   int nchunks = B >= 16 ? 4 : (B >= 2 ? 2 : 1);
-  if (const char* e = getenv("MLSIM_HOST_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= mlsim_plan::MAX_CHUNKS && v <= B) nchunks = v; }
+  for (int k = 0; k <= nchunks; ++k) bounds[k] = (int)((long)B * k / nchunks);
+  if (B >= 24 && apply_cnn && pl->cnn_ready) {
+    // one "round" = the images whose conv work items fill every persistent CTA exactly once
+    const int items_per_img = ((pl->cfg.nx + pl->rs - 1) / pl->rs) * ((pl->cfg.ny + 127) / 128);
+    const double round_imgs = (double)pl->sm_count / (items_per_img > 0 ? items_per_img : 1);
+    const int total = (int)ceil(B / round_imgs - 1e-9);
+    if (total >= 3) {                                   // [1 round | the bulk | ~a quarter]: measured best at config 2 (9, 37, 18)
+      int last = (total + 2) / 4;
+      if (last < 1) last = 1;
+      const int e1 = (int)floor(1 * round_imgs + 1e-9), e2 = (int)floor((total - last) * round_imgs + 1e-9);
+      if (e1 >= 1 && e2 > e1 && e2 < B) { nchunks = 3; bounds[0] = 0; bounds[1] = e1; bounds[2] = e2; bounds[3] = B; }
+    }
+  }
+  if (const char* e = getenv("MLSIM_HOST_CHUNKS")) {          // developer override: equal blocks
+    const int v = atoi(e);
+    if (v >= 1 && v <= mlsim_plan::MAX_CHUNKS && v <= B) { nchunks = v; for (int k = 0; k <= v; ++k) bounds[k] = (int)((long)B * k / v); }
+  }
+  if (const char* e = getenv("MLSIM_HOST_CHUNK_SIZES")) {     // developer override: explicit sizes "a,b,c"
+    int n = 0, acc = 0; const char* q = e;
+    int tmp[mlsim_plan::MAX_CHUNKS + 1] = {0};
+    while (*q && n < mlsim_plan::MAX_CHUNKS) { const int v = atoi(q); if (v <= 0) break; acc += v; tmp[++n] = acc; while (*q && *q != ',') ++q; if (*q == ',') ++q; }
+    if (n >= 1 && acc == B) { nchunks = n; for (int k = 0; k <= n; ++k) bounds[k] = tmp[k]; }
+  }
   const size_t img = (size_t)pl->cfg.nx * pl->cfg.ny;
   cudaStream_t sc = pl->own_stream;
   for (int k = 0; k < nchunks; ++k) {
-    const int b0 = (int)((long)B * k / nchunks), b1 = (int)((long)B * (k + 1) / nchunks);
+    const int b0 = bounds[k], b1 = bounds[k + 1];
     const size_t off = (size_t)b0 * img, cnt = (size_t)(b1 - b0) * img;
     MLSIM_CUDA_CHECK(cudaMemcpyAsync(pl->d_hu + off, hu + off, cnt * sizeof(float), cudaMemcpyHostToDevice, pl->in_stream));
     MLSIM_CUDA_CHECK(cudaMemcpyAsync(pl->d_hv + off, hv + off, cnt * sizeof(float), cudaMemcpyHostToDevice, pl->in_stream));

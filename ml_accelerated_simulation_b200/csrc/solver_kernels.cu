@@ -391,8 +391,8 @@ k_div_rfft(const float* __restrict__ u, const float* __restrict__ v, float2* __r
 // ---------------------------------------------------------------------------------------------
 template <int N, bool SLAB>
 __global__ void __launch_bounds__(RowCfg<N>::THREADS)
-k_irfft_grad(const float2* __restrict__ S, SpecPeers peers, const float* __restrict__ uin, const float* __restrict__ vin,
-             float* __restrict__ uout, float* __restrict__ vout, float* __restrict__ pout,
+k_irfft_grad(const float2* __restrict__ S, SpecPeers peers, const float* uin, const float* vin,   // uin may alias uout
+             float* uout, float* vout, float* __restrict__ pout,                                    // (in-place update)
              const float2* __restrict__ tw, SolverParams p) {
   using C = RowCfg<N>;
   constexpr int Q = C::Q, NT = C::THREADS;
@@ -443,10 +443,10 @@ k_irfft_grad(const float2* __restrict__ S, SpecPeers peers, const float* __restr
   if (rg < NRG) {
     const int r0 = 4 * rg, q0 = 2 * rg;
     const ptrdiff_t row0 = (ptrdiff_t)b * p.img_stride + (ptrdiff_t)(i0 + r0) * N;
-    const float* __restrict__ pu = uin + row0;
-    const float* __restrict__ pv = vin + row0;
-    float* __restrict__ ou = uout + row0;
-    float* __restrict__ ov = vout + row0;
+    const float* pu = uin + row0;
+    const float* pv = vin + row0;
+    float* ou = uout + row0;
+    float* ov = vout + row0;
     float* __restrict__ pp = pout ? pout + ((size_t)b * p.nx + i0 + r0) * N : nullptr;
     bool on[4];
 #pragma unroll

@@ -406,3 +406,26 @@ def test_trajectories_are_independent_of_batch_composition(mlsim, mlacfd):
     assert rel(u[pick], ou) <= 4 * rel(qu, ou) + 1e-6 and rel(v[pick], ov) <= 4 * rel(qv, ov) + 1e-6
     big.close()
     small.close()
+
+
+@pytest.mark.parametrize("batch,apply_cnn", [(40, True), (5, True), (33, False), (1, True)])
+def test_host_rollout_equals_device_rollout(mlsim, mlacfd, batch, apply_cnn):
+    """mlsim_rollout_host (the e2e call: H2D, steps, D2H pipelined over blocks of trajectories, block sizes chosen from the
+    conv grid) must give exactly what the device-resident rollout gives, with pinned and with pageable host memory."""
+    from ml_accelerated_simulation_b200 import models
+    cfgj, sd = mlacfd
+    cfg, u64, v64 = _ic(64, 64, batch, seed=5)
+    model = models.buildModel(cfgj)
+    model.load_state_dict(sd)
+    plan = _plan(mlsim, cfg, batch)
+    model.attach(plan)
+    u, v = u64.float().to(DEV), v64.float().to(DEV)
+    p = plan.new_field()
+    plan.step(u, v, nsteps=3, apply_cnn=apply_cnn, p=p)
+    for pinned in (True, False):
+        hu, hv, hp = u64.float().clone(), v64.float().clone(), torch.zeros(batch, 64, 64)
+        if pinned:
+            hu, hv, hp = hu.pin_memory(), hv.pin_memory(), hp.pin_memory()
+        plan.rollout_host(hu, hv, 3, apply_cnn=apply_cnn, hp=hp)
+        assert rel(hu, u) < 2e-6 and rel(hv, v) < 2e-6 and rel(hp, p) < 2e-5
+    plan.close()

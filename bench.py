@@ -261,9 +261,11 @@ def run_ours(args):
     mid_tflops = MID_FLOP_PER_CELL * cells / (mid_avg_ms * 1e-3) / 1e12
     solver_rate = cells / (solver_ms * 1e-3)
     if world == 1:      # the CPU baseline is a rank-0, N=1 figure (torchrun pins OMP threads to 1 per rank)
-        cpu_rate, cpu_sec, cpu_threads = cpu_oracle_rate(2, 2, 1, state=(u0[:2].cpu(), v0[:2].cpu()))
+        import torch as _t
+        _t.set_num_threads(os.cpu_count() or 1)
+        cpu_rate, cpu_sec, cpu_threads = cpu_oracle_rate(1, 10, 1, state=(u0[:1].cpu(), v0[:1].cpu()))
         cpu_baseline = {"value": cpu_rate, "unit": UNIT, "cores": cpu_threads, "kind": "port",
-                        "sample": "2 of 64 trajectories, 2 steps of fp64 oracle (solver + CNN)"}
+                        "sample": f"1 of {BATCH} trajectories, 10 steps of the fp64 oracle (solver + CNN) after 1 warm-up step"}
     else:
         cpu_baseline = None
     launches_per_step = plan.launches_per_step(True)

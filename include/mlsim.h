@@ -130,6 +130,10 @@ int  mlsim_slab_cnn_correct(mlsim_plan* plan, float* uv, double cnn_input_scale,
  * straight into rank r's receive buffer, mlsim_slab_stage_b with spec_send2 == NULL does the same for the backward
  * chunks, and the caller replaces each all-to-all by a cross-rank barrier.  NULL arguments switch back. */
 int  mlsim_slab_set_peers(mlsim_plan* plan, const uint64_t* fwd_recv, const uint64_t* bwd_recv);
+/* Peer-memory halo exchange: copy this rank's top `lo` rows into the upper neighbour's low halo rows and its bottom `hi`
+ * rows into the lower neighbour's high halo rows.  up_uv / dn_uv: the neighbours' field pair of the same role as mapped
+ * into this process (NULL: skip that side -- the global edges of the non-periodic CNN halo).  Follow with a barrier. */
+int  mlsim_slab_halo_push(mlsim_plan* plan, const float* uv, float* up_uv, float* dn_uv, int32_t lo, int32_t hi, void* stream);
 
 /* ---- data generation, reference src/data_generation.py:91-111,193-213 ----
  * mlsim_downsample_staggered: downsample_staggered_velocity(fine_grid, coarse_grid, (u, v)) -- u keeps the faces

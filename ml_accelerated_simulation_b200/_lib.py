@@ -57,6 +57,7 @@ _SIGNATURES = {
     "mlsim_slab_stage_b": (C.c_int, [C.c_void_p] * 4),
     "mlsim_slab_stage_c": (C.c_int, [C.c_void_p] * 5),
     "mlsim_slab_set_peers": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "mlsim_slab_halo_push": (C.c_int, [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_void_p]),
     "mlsim_slab_cnn_correct": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     "mlsim_downsample_staggered": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p]),
     "mlsim_datagen_pair": (C.c_int, [C.c_void_p] * 6 + [C.c_int32, C.c_int32, C.c_void_p]),

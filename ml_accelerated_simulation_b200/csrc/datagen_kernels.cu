@@ -48,6 +48,46 @@ k_downsample_staggered(const float* __restrict__ u, const float* __restrict__ v,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Slab decomposition: push this rank's edge rows into the neighbours' halo rows (peer memory over NVLink).
+//   top `lo` rows  [nxl-lo, nxl) -> UPPER neighbour's rows [-lo, 0)         bottom `hi` rows [0, hi) -> LOWER neighbour's
+//   rows [nxl, nxl+hi).  Field pair layout uv[2][batch][ext_rows][ny], local row i at ext row i + halo; float4 copies.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_halo_push(const float* __restrict__ uv, float* __restrict__ up_uv, float* __restrict__ dn_uv, int images, int ext_rows,
+            int ny, int nxl, int halo, int lo, int hi) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int ny4 = ny >> 2;
+  const size_t per_img_up = (size_t)lo * ny4, per_img_dn = (size_t)hi * ny4;
+  const size_t n_up = up_uv ? per_img_up * images : 0, n_dn = dn_uv ? per_img_dn * images : 0;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n_up + n_dn; e += (size_t)gridDim.x * blockDim.x) {
+    if (e < n_up) {
+      const size_t img = e / per_img_up, r = e - img * per_img_up;                 // r = row * ny4 + col4
+      const size_t row = r / ny4, c4 = r - row * ny4;
+      const float4 val = reinterpret_cast<const float4*>(uv + (img * ext_rows + halo + nxl - lo + row) * ny)[c4];
+      reinterpret_cast<float4*>(up_uv + (img * ext_rows + halo - lo + row) * ny)[c4] = val;
+    } else {
+      const size_t f = e - n_up;
+      const size_t img = f / per_img_dn, r = f - img * per_img_dn;
+      const size_t row = r / ny4, c4 = r - row * ny4;
+      const float4 val = reinterpret_cast<const float4*>(uv + (img * ext_rows + halo + row) * ny)[c4];
+      reinterpret_cast<float4*>(dn_uv + (img * ext_rows + halo + nxl + row) * ny)[c4] = val;
+    }
+  }
+}
+
+int launch_halo_push(const float* uv, float* up_uv, float* dn_uv, int images, int ext_rows, int ny, int nxl, int halo,
+                     int lo, int hi, cudaStream_t st) {
+  const size_t n = (size_t)images * (lo + hi) * (ny / 4);
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  MLSIM_CUDA_CHECK(launch_pdl(k_halo_push, dim3((unsigned)blocks), dim3(256), 0, st, uv, up_uv, dn_uv, images, ext_rows, ny,
+                              nxl, halo, lo, hi));
+  return MLSIM_OK;
+}
+
 int launch_downsample_staggered(const float* u, const float* v, float* cu, float* cv, int batch, int nx, int ny, int f,
                                 cudaStream_t st) {
   const size_t nout = 2 * (size_t)batch * (nx / f) * (ny / f);

@@ -921,6 +921,22 @@ int mlsim_slab_stage_c(mlsim_plan* pl, const void* spec_recv2, float* uv, float*
                            pl->cfg.slab_world);
 }
 
+// Peer-memory halo exchange: copy this rank's top `lo` rows into the upper neighbour's low halo and its bottom `hi`
+// rows into the lower neighbour's high halo.  up_uv / dn_uv: the neighbours' field pair (same buffer role) as mapped
+// into this process, or NULL to skip that side (edges of a non-periodic exchange).  The caller follows with a barrier.
+int mlsim_slab_halo_push(mlsim_plan* pl, const float* uv, float* up_uv, float* dn_uv, int32_t lo, int32_t hi, void* stream) {
+  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_SLAB_ONLY(pl);
+  int rc;
+  if ((rc = check_field(uv, "uv"))) return rc;
+  if (up_uv && (rc = check_field(up_uv, "up_uv"))) return rc;
+  if (dn_uv && (rc = check_field(dn_uv, "dn_uv"))) return rc;
+  MLSIM_REQUIRE(lo >= 0 && hi >= 0 && lo <= MLSIM_SLAB_HALO && hi <= MLSIM_SLAB_HALO && lo <= pl->nxl && hi <= pl->nxl, "halo width out of range");
+  if ((!up_uv || lo == 0) && (!dn_uv || hi == 0)) return MLSIM_OK;
+  return launch_halo_push(uv, lo > 0 ? up_uv : nullptr, hi > 0 ? dn_uv : nullptr, 2 * pl->cfg.batch, pl->ext_rows, pl->cfg.ny,
+                          pl->nxl, MLSIM_SLAB_HALO, lo, hi, reinterpret_cast<cudaStream_t>(stream));
+}
+
 // Peer-memory spectral exchange: fwd_recv[r] / bwd_recv[r] = base of rank r's forward / backward receive buffer as
 // mapped into THIS process (CUDA IPC / symmetric memory over NVLink).  Afterwards stage_a (spec_send == NULL) stores
 // column chunk r straight into rank r's buffer at this rank's slot, and stage_b (spec_send2 == NULL) does the same for

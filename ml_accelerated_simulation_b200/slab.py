@@ -136,6 +136,33 @@ class SlabComm:
         backend.set_peers(ptrs[0], ptrs[1])
         return None, bufs[0], None, bufs[1]
 
+    # ------------------------------------------------------------------ field buffers
+    def make_field_buffers(self, backend):
+        """(state, w1, w2, acc).  p2p: the three buffers whose halos are exchanged are symmetric memory, so a rank can
+        push its edge rows straight into its neighbours' halo rows."""
+        if not self.p2p:
+            return tuple(backend.new_field_pair() for _ in range(4))
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = self.group if self.group is not None else dist.group.WORLD
+        out = []
+        self._field_peers = {}
+        self._backend = backend
+        for _ in range(3):
+            t = symm_mem.empty(self.g.field_shape(), dtype=torch.float32, device=backend.device)
+            t.zero_()
+            h = symm_mem.rendezvous(t, grp)
+            self._field_peers[t.data_ptr()] = ([int(x) for x in h.buffer_ptrs], h)
+            out.append(t)
+        torch.cuda.synchronize(backend.device)
+        dist.barrier(group=self.group)
+        return out[0], out[1], out[2], backend.new_field_pair()
+
+    def fence(self) -> None:
+        """Cross-rank barrier on the compute stream (p2p mode: nobody may push into a neighbour that is still working on
+        the rows being replaced -- used after the correction network)."""
+        if self.p2p:
+            self._symm[0][1].barrier(channel=2, timeout_ms=self.BARRIER_TIMEOUT_MS)
+
     def spectral_exchange(self, send, recv, which: int) -> None:
         """Chunk r of this rank's half spectrum -> rank r (which: 0 forward, 1 backward)."""
         if self.p2p:
@@ -165,6 +192,13 @@ class SlabComm:
         up, down = (g.rank + 1) % g.world, (g.rank - 1) % g.world
         has_up = periodic or g.rank < g.world - 1
         has_down = periodic or g.rank > 0
+        peers = getattr(self, "_field_peers", {}).get(uv.data_ptr()) if self.p2p else None
+        if peers is not None:
+            # peer memory: one small kernel stores the edge rows into the neighbours' halos, then a device barrier
+            ptrs, h = peers
+            self._backend.halo_push(uv, ptrs[up] if has_up else None, ptrs[down] if has_down else None, lo, hi)
+            h.barrier(channel=0, timeout_ms=self.BARRIER_TIMEOUT_MS)
+            return
         s_up, r_dn, _, _ = self._bufs(uv, lo)
         _, _, s_dn, r_up = self._bufs(uv, hi)
         ops = []
@@ -246,6 +280,9 @@ class CudaSlabBackend:
     def cnn_correct(self, uv, scale):
         _lib.check(self._lib.mlsim_slab_cnn_correct(self._h, uv.data_ptr(), float(scale), self._st()))
 
+    def halo_push(self, uv, up_ptr, dn_ptr, lo, hi):
+        _lib.check(self._lib.mlsim_slab_halo_push(self._h, uv.data_ptr(), up_ptr, dn_ptr, int(lo), int(hi), self._st()))
+
     def set_peers(self, fwd_ptrs, bwd_ptrs):
         n = len(fwd_ptrs)
         a = (C.c_uint64 * n)(*fwd_ptrs)
@@ -268,7 +305,7 @@ class SlabStepper:
         self.g: SlabGeometry = backend.geom
         self.comm = comm if comm is not None else SlabComm(self.g)
         b = backend
-        self.state, self.w1, self.w2, self.acc = (b.new_field_pair() for _ in range(4))
+        self.state, self.w1, self.w2, self.acc = self.comm.make_field_buffers(b)
         self.send, self.recv, self.send2, self.recv2 = self.comm.make_spectral_buffers(b)
         self.pressure = None
         self.exchanges = 0
@@ -336,3 +373,4 @@ class SlabStepper:
                 c.halo_exchange(self.state, CNN_HALO, CNN_HALO, False)
                 self.exchanges += 1
                 be.cnn_correct(self.state, input_scale)
+                c.fence()            # p2p: the next step's halo pushes must not land while a neighbour's network still runs

@@ -150,6 +150,48 @@ def cpu_oracle_rate(nsample: int, steps: int, warmup: int, state=None):
     return nsample * NX * NY * steps / dt, dt / steps, torch.get_num_threads()
 
 
+def _config1_cpu():
+    """BASELINE configs[0]: the reference's own CPU-runnable case, 64x64, batch 1, solver + CNN, 100-step rollout."""
+    import torch
+    from oracle import cnn as OC
+    from oracle import solver as S
+    cfg = S.SolverConfig(nx=64, ny=64)
+    u, v = S.filtered_velocity_field(cfg, 1, seed=42)
+    cfgj, sd = _model_state()
+    with torch.inference_mode():
+        OC.rollout(u, v, cfg, 2, cfgj, sd, 1.0)
+        t = time.perf_counter()
+        u, v, _ = OC.rollout(u, v, cfg, 100, cfgj, sd, 1.0)
+        dt = time.perf_counter() - t
+    assert bool(torch.isfinite(u).all())
+    return {"value": 64 * 64 * 100 / dt, "unit": UNIT, "ms_per_step": dt * 10, "cores": torch.get_num_threads()}
+
+
+def _config1_gpu(model, dev):
+    """The same configs[0] rollout on the device (latency-bound: 4096 cells per step)."""
+    import torch
+    from ml_accelerated_simulation_b200 import Plan, PlanConfig
+    from ml_accelerated_simulation_b200 import grids
+    from ml_accelerated_simulation_b200.initial_conditions import filtered_velocity_field
+    import math
+    grid = grids.Grid((64, 64), domain=((0, 2 * math.pi), (0, 2 * math.pi)), device=dev)
+    v0 = filtered_velocity_field(grid, 7.0, 4.0, iterations=16, random_state=42, device=dev, batch_size=1, dtype=torch.float32)
+    u, v = v0[0].data.contiguous(), v0[1].data.contiguous()
+    plan = Plan(PlanConfig(nx=64, ny=64, batch=1, device=dev.index or 0))
+    model.attach(plan)
+    plan.step(u, v, nsteps=10, apply_cnn=True)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    plan.step(u, v, nsteps=100, apply_cnn=True)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    ok = bool(torch.isfinite(u).all())
+    plan.close()
+    return {"value": 64 * 64 * 100 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / 100, "finite": ok}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (fp64 torch ops on the host;
     solver restated in oracle/solver.py because torch_cfd is not installable here, CNN = oracle/cnn.py pinned
@@ -162,8 +204,16 @@ def run_reference(args):
     nsample = 1
     steps = min(args.steps, 40)                 # bounded: ~1.3 s of 16-core CPU work per sampled step
     rate, sec_per_step, threads = cpu_oracle_rate(nsample, steps, min(args.warmup, 2))
+    # SURVEY.md 8d extras: the same sample on ONE thread, and BASELINE configs[0] (64x64, batch 1, 100 steps) in full
+    extras = {}
+    if args.gpus == 1:
+        torch.set_num_threads(1)
+        r1, _, _ = cpu_oracle_rate(nsample, 2, 1)
+        torch.set_num_threads(os.cpu_count() or 1)
+        extras["single_thread"] = {"value": r1, "unit": UNIT, "cores": 1}
+        extras["config1_64x64_b1_100steps"] = _config1_cpu()
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", **({"cpu_extras": extras} if extras else {}), "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": sec_per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "timed_on": "host CPU"},
@@ -269,6 +319,7 @@ def run_ours(args):
     else:
         cpu_baseline = None
     launches_per_step = plan.launches_per_step(True)
+    config1 = _config1_gpu(model, dev) if world == 1 else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -290,6 +341,7 @@ def run_ours(args):
                 "steps": ke, "api": "Plan.rollout_host -> mlsim_rollout_host (pinned host buffers)"},
         "gpu_launches": launches_per_step * K,
         "clocks": clocks,
+        "config1_64x64_b1_100steps": config1,
     }
     print(json.dumps(line), flush=True)
     plan.close()

@@ -429,3 +429,31 @@ def test_host_rollout_equals_device_rollout(mlsim, mlacfd, batch, apply_cnn):
         plan.rollout_host(hu, hv, 3, apply_cnn=apply_cnn, hp=hp)
         assert rel(hu, u) < 2e-6 and rel(hv, v) < 2e-6 and rel(hp, p) < 2e-5
     plan.close()
+
+
+@pytest.mark.parametrize("nx,ny,batch,apply_cnn", [(64, 64, 1, True), (64, 128, 3, True), (128, 128, 2, False)])
+def test_many_steps_per_call_equal_step_by_step(mlsim, mlacfd, nx, ny, batch, apply_cnn):
+    """mlsim_step(nsteps = n) must be bit-identical to n calls with nsteps = 1 (same launches, same streams), including
+    the pressure output of the last step, also when called again on the same or on other tensors."""
+    from ml_accelerated_simulation_b200 import models
+    cfgj, sd = mlacfd
+    cfg, u64, v64 = _ic(nx, ny, batch, seed=31)
+    model = models.buildModel(cfgj)
+    model.load_state_dict(sd)
+    plan = _plan(mlsim, cfg, batch)
+    model.attach(plan)
+    n = 43
+    ua, va = u64.float().to(DEV), v64.float().to(DEV)
+    pa = plan.new_field()
+    for s in range(n):
+        plan.step(ua, va, nsteps=1, apply_cnn=apply_cnn, p=pa if s == n - 1 else None)
+    for rep in range(2):
+        ub, vb = u64.float().to(DEV), v64.float().to(DEV)
+        pb = plan.new_field()
+        if rep == 1:
+            ub, vb = ub.clone(), vb.clone()                # other addresses
+        plan.step(ub, vb, nsteps=n, apply_cnn=apply_cnn, p=pb)
+        assert torch.equal(ub, ua) and torch.equal(vb, va) and torch.equal(pb, pa)
+    plan.step(ub, vb, nsteps=20, apply_cnn=apply_cnn)      # same tensors again
+    assert torch.isfinite(ub).all()
+    plan.close()

@@ -98,6 +98,10 @@ int  mlsim_rollout_host(mlsim_plan* plan, float* host_u, float* host_v, float* h
 int  mlsim_explicit_terms(mlsim_plan* plan, const float* u, const float* v, float* du, float* dv, void* stream);
 /* P(u,v): ...pressure_projection (App. A.4), in place; p_or_null optional */
 int  mlsim_project(mlsim_plan* plan, float* u, float* v, float* p_or_null, void* stream);
+/* out = irfft2(rfft2(in) * table) on the projection's transform kernels: the spectral filter inside
+ * filtered_velocity_field (src/inference.py:76-78, src/data_generation.py:153-155,194-196).  table: HOST fp64
+ * [nx][ny/2+1], natural kx order.  Set-up call: synchronises `stream` while the table is uploaded. */
+int  mlsim_spectral_multiply(mlsim_plan* plan, const double* table, const float* in, float* out, void* stream);
 /* fdm.divergence(v) (test/sim_test.py:42) */
 int  mlsim_divergence(mlsim_plan* plan, const float* u, const float* v, float* div, void* stream);
 /* y = model(stack((u,v),1) * input_scale): y is [batch][cout_last][nx][ny] fp32 (NCHW) */

@@ -45,6 +45,9 @@ struct SolverParams {
   // address local row 0 of halo-extended buffers (rows [-halo, nx+halo) are valid memory, no periodic wrap in x)
   int halo;
   int kyw, kywp;              // spectral columns per rank chunk and its padded pitch (float2 units)
+  int raw;                    // 1: K2 transforms the field `u` itself (no divergence), K4 only writes the inverse
+                              //    transform to `pout` -- together with K3 and a caller-supplied spectral table this is
+                              //    out = irfft2(rfft2(in) * table) (initial-condition filter, mlsim_spectral_multiply)
 };
 
 // Slab mode: where spectral column chunk r lives.  With NCCL exchanges every entry points into one local send / recv

@@ -53,6 +53,7 @@ struct mlsim_plan {
   float* d_accu = nullptr; float* d_accv = nullptr;
   float2* d_spec = nullptr;
   float2* d_tw_n2 = nullptr;            // twiddles of the in-smem column transform (length n2len; == d_twx when r0 == 1)
+  float* d_filt = nullptr;              // caller-supplied spectral table (mlsim_spectral_multiply), same order as d_inv_eig
   float2* d_split = nullptr;            // T buffer of the split x-transform (r0 > 1 or slab mode)
   int r0 = 1, n2len = 0;                // nx(global) = r0 * n2len, n2len <= 2048
   // slab decomposition (cfg.slab_world >= 1): this rank owns global rows [rank*nxl, (rank+1)*nxl)
@@ -399,6 +400,7 @@ int mlsim_plan_create(const mlsim_config* cfg, mlsim_plan** out) {
   sp.img_stride = slab ? (long long)pl->ext_rows * cfg->ny : (long long)cfg->nx * cfg->ny;
   sp.halo = slab ? MLSIM_SLAB_HALO : 0;
   sp.kyw = pl->kyw; sp.kywp = pl->kywp;
+  sp.raw = 0;
   pl->field_elems = (size_t)cfg->batch * sp.nx * cfg->ny;
   // Single-kernel projection (thread-block cluster per image, DSMEM half spectrum): measured on B200 against the
   // three-kernel path -- 256^2 x 64: 0.0665 vs 0.0525 ms per projection; after the K2/K4 rewrites also 128^2 x 512
@@ -453,7 +455,7 @@ int mlsim_plan_destroy(mlsim_plan* pl) {
   cudaSetDevice(pl->cfg.device);
   cudaDeviceSynchronize();
   void* ptrs[] = {pl->d_forcing, pl->d_inv_eig, pl->d_twx, pl->d_twy, pl->d_w1u, pl->d_w1v, pl->d_w2u, pl->d_w2v,
-                  pl->d_accu, pl->d_accv, pl->d_spec, pl->d_tw_n2, pl->d_split, pl->d_act[0], pl->d_act[1], pl->d_act[2], pl->d_hu, pl->d_hv, pl->d_hp,
+                  pl->d_accu, pl->d_accv, pl->d_spec, pl->d_tw_n2, pl->d_split, pl->d_filt, pl->d_act[0], pl->d_act[1], pl->d_act[2], pl->d_hu, pl->d_hv, pl->d_hp,
                   pl->d_tu, pl->d_tv, pl->d_dbg};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& l : pl->layers) if (l.d_wimg) cudaFree(l.d_wimg);
@@ -802,6 +804,35 @@ int mlsim_project(mlsim_plan* pl, float* u, float* v, float* p_or_null, void* st
   int rc;
   if ((rc = check_field(u, "u")) || (rc = check_field(v, "v"))) return rc;
   return project(pl, u, v, p_or_null, reinterpret_cast<cudaStream_t>(stream), Chunk{0, pl->cfg.batch});
+}
+
+// out = irfft2(rfft2(in) * table): the spectral filter of the initial-condition generator (torch_cfd's
+// filtered_velocity_field, reference src/inference.py:76-78) on the projection's own transform kernels.
+// table: HOST fp64 [nx][ny/2+1] in natural kx order.  Set-up path: synchronises `stream` (table upload).
+int mlsim_spectral_multiply(mlsim_plan* pl, const double* table, const float* in, float* out, void* stream) {
+  if (!pl || !table) { set_error("null argument"); return MLSIM_EINVAL; }
+  MLSIM_PLAIN_ONLY(pl);
+  int rc;
+  if ((rc = check_field(in, "in")) || (rc = check_field(out, "out"))) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int nx = pl->cfg.nx, nyc = pl->sp.nyc, r0 = pl->r0, n2 = pl->n2len;
+  std::vector<float> t((size_t)nx * nyc);
+  const double norm = 1.0 / ((double)nx * pl->cfg.ny);
+  for (int k1 = 0; k1 < r0; ++k1)
+    for (int k2 = 0; k2 < n2; ++k2) {
+      const int kx = k1 + r0 * k2;
+      for (int k = 0; k < nyc; ++k) t[((size_t)k1 * n2 + k2) * nyc + k] = (float)(table[(size_t)kx * nyc + k] * norm);
+    }
+  if (!pl->d_filt && (rc = dev_alloc(pl, &pl->d_filt, t.size()))) return rc;
+  MLSIM_CUDA_CHECK(cudaStreamSynchronize(st));            // an earlier call may still be reading the table
+  MLSIM_CUDA_CHECK(cudaMemcpy(pl->d_filt, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+  SolverParams sp = pl->sp;
+  sp.raw = 1;
+  if ((rc = launch_div_rfft(in, in, pl->d_spec, pl->d_twy, sp, st))) return rc;
+  if (pl->r0 == 1) rc = launch_col_solve(pl->d_spec, pl->d_filt, pl->d_twx, sp, sp.nx, sp.batch, 1, st);
+  else rc = launch_col_solve_split(pl->d_spec, pl->d_split, pl->d_filt, pl->d_twx, pl->d_tw_n2, sp, pl->r0, st);
+  if (rc) return rc;
+  return launch_irfft_grad(pl->d_spec, in, in, out, out, out, pl->d_twy, sp, st);
 }
 
 int mlsim_divergence(mlsim_plan* pl, const float* u, const float* v, float* d, void* stream) {

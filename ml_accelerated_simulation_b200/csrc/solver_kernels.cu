@@ -354,6 +354,9 @@ k_div_rfft(const float* __restrict__ u, const float* __restrict__ v, float2* __r
     const float* __restrict__ ru = u + (ptrdiff_t)b * p.img_stride + (ptrdiff_t)i * N;
     const float* __restrict__ rv = v + (ptrdiff_t)b * p.img_stride + (ptrdiff_t)i * N;
     const float* __restrict__ rum = u + (ptrdiff_t)b * p.img_stride + (ptrdiff_t)im * N;
+    if (p.raw) {                    // plain transform of the field itself (spectral filter path)
+      for (int j = t; j < N; j += TPL) buf[fidx<Q>(j, ql)] = make_float2(ru[j], ru[N + j]);
+    } else
 #pragma unroll 4
     for (int j = t; j < N; j += TPL) {
       const int jm = (j - 1) & (N - 1);
@@ -451,6 +454,16 @@ k_irfft_grad(const float2* __restrict__ S, SpecPeers peers, const float* uin, co
     bool on[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) on[k] = (r0 + k < NROWS) && (i0 + r0 + k < p.nx);
+    if (p.raw) {                    // inverse transform only: write the rows to pout
+      for (int y = ty; y < N; y += TPG) {
+        const float2 A0 = buf[fidx<Q>(y, q0)];
+        const float2 A1 = (q0 + 1 < Q) ? buf[fidx<Q>(y, q0 + 1)] : make_float2(0.f, 0.f);
+        const float pr[4] = {A0.x, A0.y, A1.x, A1.y};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (on[k]) pp[k * N + y] = pr[k];
+      }
+    } else
     for (int y = ty; y < N; y += TPG) {
       float uo[4], vo[4];
 #pragma unroll

@@ -2,7 +2,8 @@
 
 Setup code, run once per rollout (not on the per-step hot path): a band-limited random field is made
 divergence free by the CUDA projection kernels and rescaled to ``max_velocity``.
-The spectral filtering of the white noise uses torch.fft on the device.
+The spectral filtering of the white noise runs on the projection's own transform kernels
+(``mlsim_spectral_multiply``); no library FFT is involved.
 """
 from __future__ import annotations
 
@@ -15,11 +16,13 @@ from .grids import Grid, GridVariable, GridVariableVector
 from .plan import Plan, PlanConfig
 
 
-def _spectral_filter(grid: Grid, peak_wavenumber: float, device) -> torch.Tensor:
+def _spectral_filter(grid: Grid, peak_wavenumber: float) -> torch.Tensor:
+    """Host fp64 table [nx, ny//2+1]: log-normal band around ``peak_wavenumber`` divided by |k| (0 at k = 0)."""
     nx, ny = grid.shape
     (x0, x1), (y0, y1) = grid.domain
-    kx = torch.fft.fftfreq(nx, d=1.0 / nx, dtype=torch.float64, device=device) * (2 * math.pi / (x1 - x0))
-    ky = torch.fft.rfftfreq(ny, d=1.0 / ny, dtype=torch.float64, device=device) * (2 * math.pi / (y1 - y0))
+    ix = torch.arange(nx, dtype=torch.float64)
+    kx = torch.where(ix < (nx + 1) // 2, ix, ix - nx) * (2 * math.pi / (x1 - x0))         # fftfreq ordering
+    ky = torch.arange(ny // 2 + 1, dtype=torch.float64) * (2 * math.pi / (y1 - y0))
     kk = torch.sqrt(kx[:, None] ** 2 + ky[None, :] ** 2)
     logvar = 0.25
     mu = math.log(peak_wavenumber) + logvar
@@ -37,14 +40,14 @@ def filtered_velocity_field(grid: Grid, max_velocity: float = 1.0, peak_wavenumb
     dtype = dtype or torch.get_default_dtype()
     nx, ny = grid.shape
     g = torch.Generator(device="cpu").manual_seed(int(random_state))
-    filt = _spectral_filter(grid, peak_wavenumber, device)
-    comps = []
-    for _ in range(2):
-        noise = torch.randn(batch_size, nx, ny, generator=g, dtype=torch.float64).to(device)
-        comps.append(torch.fft.irfft2(torch.fft.rfft2(noise) * filt, s=(nx, ny)))
+    filt = _spectral_filter(grid, peak_wavenumber)
     (x0, x1), (y0, y1) = grid.domain
     plan = Plan(PlanConfig(nx=nx, ny=ny, batch=batch_size, lx=x1 - x0, ly=y1 - y0, dt=1.0,
                            device=device.index or 0))
+    comps = []
+    for _ in range(2):
+        noise = torch.randn(batch_size, nx, ny, generator=g, dtype=torch.float64).to(device, torch.float32).contiguous()
+        comps.append(plan.spectral_multiply(noise, filt))
     # normalise first so fp32 projection works at O(1) magnitudes
     u, v = comps
     speed = torch.sqrt(u * u + v * v).amax(dim=(-2, -1), keepdim=True)

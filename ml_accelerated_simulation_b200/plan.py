@@ -156,6 +156,16 @@ class Plan:
         _lib.check(self._lib.mlsim_project(self._h, u.data_ptr(), v.data_ptr(), _ptr(p), self._stream()))
         return p
 
+    def spectral_multiply(self, field: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+        """irfft2(rfft2(field) * table) on the plan's own transform kernels; table: host fp64 [nx, ny//2+1]."""
+        self._field(field, "field")
+        t = table.detach().to("cpu", torch.float64).contiguous()
+        if tuple(t.shape) != (self.cfg.nx, self.cfg.ny // 2 + 1):
+            raise ValueError(f"table must have shape {(self.cfg.nx, self.cfg.ny // 2 + 1)}")
+        out = self.new_field()
+        _lib.check(self._lib.mlsim_spectral_multiply(self._h, t.data_ptr(), field.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
     def divergence(self, u, v):
         self._field(u, "u"); self._field(v, "v")
         d = self.new_field()

@@ -457,3 +457,29 @@ def test_many_steps_per_call_equal_step_by_step(mlsim, mlacfd, nx, ny, batch, ap
     plan.step(ub, vb, nsteps=20, apply_cnn=apply_cnn)      # same tensors again
     assert torch.isfinite(ub).all()
     plan.close()
+
+
+@pytest.mark.parametrize("nx,ny,batch", [(64, 64, 2), (128, 256, 1), (4096, 64, 1)])
+def test_spectral_multiply_and_initial_condition(mlsim, nx, ny, batch):
+    """mlsim_spectral_multiply (the IC generator's band-pass filter on the projection's transform kernels, no library
+    FFT) against torch.fft in fp64, and filtered_velocity_field against the oracle's generator on the same noise."""
+    import math
+    from ml_accelerated_simulation_b200 import grids
+    from ml_accelerated_simulation_b200.initial_conditions import _spectral_filter, filtered_velocity_field
+    grid = grids.Grid((nx, ny), domain=((0, 2 * math.pi), (0, 2 * math.pi)))
+    table = _spectral_filter(grid, 4.0)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(batch, nx, ny, generator=g, dtype=torch.float64)
+    plan = mlsim.Plan(mlsim.PlanConfig(nx=nx, ny=ny, batch=batch))
+    y = plan.spectral_multiply(x.float().to(DEV), table)
+    ref = torch.fft.irfft2(torch.fft.rfft2(x) * table, s=(nx, ny))
+    assert rel(y, ref) < 2e-6
+    plan.close()
+    if nx <= 256:
+        cfg = S.SolverConfig(nx=nx, ny=ny)
+        ou, ov = S.filtered_velocity_field(cfg, batch, seed=42, iterations=3)
+        v0 = filtered_velocity_field(grid, 7.0, 4.0, iterations=3, random_state=42, device=DEV, batch_size=batch,
+                                     dtype=torch.float32)
+        assert rel(v0[0].data, ou) < 1e-4 and rel(v0[1].data, ov) < 1e-4
+        speed = torch.sqrt(v0[0].data ** 2 + v0[1].data ** 2).amax(dim=(-2, -1))
+        assert torch.allclose(speed.cpu(), torch.full((batch,), 7.0), atol=1e-4)

@@ -102,6 +102,8 @@ int  mlsim_project(mlsim_plan* plan, float* u, float* v, float* p_or_null, void*
  * filtered_velocity_field (src/inference.py:76-78, src/data_generation.py:153-155,194-196).  table: HOST fp64
  * [nx][ny/2+1], natural kx order.  Set-up call: synchronises `stream` while the table is uploaded. */
 int  mlsim_spectral_multiply(mlsim_plan* plan, const double* table, const float* in, float* out, void* stream);
+/* per trajectory: u, v *= max_velocity / max sqrt(u^2 + v^2) (the rescaling step of filtered_velocity_field) */
+int  mlsim_normalize_speed(mlsim_plan* plan, float* u, float* v, double max_velocity, void* stream);
 /* fdm.divergence(v) (test/sim_test.py:42) */
 int  mlsim_divergence(mlsim_plan* plan, const float* u, const float* v, float* div, void* stream);
 /* y = model(stack((u,v),1) * input_scale): y is [batch][cout_last][nx][ny] fp32 (NCHW) */

@@ -49,6 +49,7 @@ _SIGNATURES = {
     "mlsim_explicit_terms": (C.c_int, [C.c_void_p] * 5 + [C.c_void_p]),
     "mlsim_project": (C.c_int, [C.c_void_p] * 4 + [C.c_void_p]),
     "mlsim_spectral_multiply": (C.c_int, [C.c_void_p] * 4 + [C.c_void_p]),
+    "mlsim_normalize_speed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     "mlsim_divergence": (C.c_int, [C.c_void_p] * 4 + [C.c_void_p]),
     "mlsim_cnn_forward": (C.c_int, [C.c_void_p] * 4 + [C.c_double, C.c_void_p]),
     "mlsim_cnn_correct": (C.c_int, [C.c_void_p] * 3 + [C.c_double, C.c_void_p]),

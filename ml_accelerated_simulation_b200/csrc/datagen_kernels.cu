@@ -88,6 +88,57 @@ int launch_halo_push(const float* uv, float* up_uv, float* dn_uv, int images, in
   return MLSIM_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Initial-condition normalisation (torch_cfd filtered_velocity_field): per trajectory
+//   s = max sqrt(u^2 + v^2);  u, v *= max_velocity / s.      Two passes: warp-shuffle + atomicMax reduction, rescale.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_speed_max(const float* __restrict__ u, const float* __restrict__ v, unsigned int* __restrict__ smax2, int n_per_img) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.y;
+  const float4* pu = reinterpret_cast<const float4*>(u + (size_t)b * n_per_img);
+  const float4* pv = reinterpret_cast<const float4*>(v + (size_t)b * n_per_img);
+  float m = 0.0f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_per_img / 4; i += gridDim.x * blockDim.x) {
+    const float4 a = __ldg(pu + i), c = __ldg(pv + i);
+    m = fmaxf(m, fmaxf(fmaxf(a.x * a.x + c.x * c.x, a.y * a.y + c.y * c.y), fmaxf(a.z * a.z + c.z * c.z, a.w * a.w + c.w * c.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(&smax2[b], __float_as_uint(m));      // non-negative floats order like their bit patterns
+}
+
+__global__ void __launch_bounds__(256)
+k_speed_rescale(float* __restrict__ u, float* __restrict__ v, const unsigned int* __restrict__ smax2, int n_per_img,
+                float max_velocity) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.y;
+  const float s2 = __uint_as_float(smax2[b]);
+  const float f = s2 > 0.0f ? max_velocity * rsqrtf(s2) : 1.0f;
+  float4* pu = reinterpret_cast<float4*>(u + (size_t)b * n_per_img);
+  float4* pv = reinterpret_cast<float4*>(v + (size_t)b * n_per_img);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_per_img / 4; i += gridDim.x * blockDim.x) {
+    float4 a = pu[i], c = pv[i];
+    a.x *= f; a.y *= f; a.z *= f; a.w *= f;
+    c.x *= f; c.y *= f; c.z *= f; c.w *= f;
+    pu[i] = a; pv[i] = c;
+  }
+}
+
+int launch_normalize_speed(float* u, float* v, unsigned int* scratch, int batch, int n_per_img, float max_velocity,
+                           cudaStream_t st) {
+  MLSIM_CUDA_CHECK(cudaMemsetAsync(scratch, 0, (size_t)batch * sizeof(unsigned int), st));
+  int bx = (n_per_img / 4 + 255) / 256;
+  if (bx > 64) bx = 64;
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, (unsigned)batch);
+  MLSIM_CUDA_CHECK(launch_pdl(k_speed_max, grid, dim3(256), 0, st, (const float*)u, (const float*)v, scratch, n_per_img));
+  MLSIM_CUDA_CHECK(launch_pdl(k_speed_rescale, grid, dim3(256), 0, st, u, v, (const unsigned int*)scratch, n_per_img, max_velocity));
+  return MLSIM_OK;
+}
+
 int launch_downsample_staggered(const float* u, const float* v, float* cu, float* cv, int batch, int nx, int ny, int f,
                                 cudaStream_t st) {
   const size_t nout = 2 * (size_t)batch * (nx / f) * (ny / f);

@@ -53,6 +53,7 @@ struct mlsim_plan {
   float* d_accu = nullptr; float* d_accv = nullptr;
   float2* d_spec = nullptr;
   float2* d_tw_n2 = nullptr;            // twiddles of the in-smem column transform (length n2len; == d_twx when r0 == 1)
+  unsigned int* d_smax = nullptr;       // per-trajectory max speed^2 (mlsim_normalize_speed)
   float* d_filt = nullptr;              // caller-supplied spectral table (mlsim_spectral_multiply), same order as d_inv_eig
   float2* d_split = nullptr;            // T buffer of the split x-transform (r0 > 1 or slab mode)
   int r0 = 1, n2len = 0;                // nx(global) = r0 * n2len, n2len <= 2048
@@ -455,7 +456,7 @@ int mlsim_plan_destroy(mlsim_plan* pl) {
   cudaSetDevice(pl->cfg.device);
   cudaDeviceSynchronize();
   void* ptrs[] = {pl->d_forcing, pl->d_inv_eig, pl->d_twx, pl->d_twy, pl->d_w1u, pl->d_w1v, pl->d_w2u, pl->d_w2v,
-                  pl->d_accu, pl->d_accv, pl->d_spec, pl->d_tw_n2, pl->d_split, pl->d_filt, pl->d_act[0], pl->d_act[1], pl->d_act[2], pl->d_hu, pl->d_hv, pl->d_hp,
+                  pl->d_accu, pl->d_accv, pl->d_spec, pl->d_tw_n2, pl->d_split, pl->d_filt, pl->d_smax, pl->d_act[0], pl->d_act[1], pl->d_act[2], pl->d_hu, pl->d_hv, pl->d_hp,
                   pl->d_tu, pl->d_tv, pl->d_dbg};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& l : pl->layers) if (l.d_wimg) cudaFree(l.d_wimg);
@@ -833,6 +834,18 @@ int mlsim_spectral_multiply(mlsim_plan* pl, const double* table, const float* in
   else rc = launch_col_solve_split(pl->d_spec, pl->d_split, pl->d_filt, pl->d_twx, pl->d_tw_n2, sp, pl->r0, st);
   if (rc) return rc;
   return launch_irfft_grad(pl->d_spec, in, in, out, out, out, pl->d_twy, sp, st);
+}
+
+// Per trajectory: u, v *= max_velocity / max sqrt(u^2 + v^2) -- the rescaling step of filtered_velocity_field.
+int mlsim_normalize_speed(mlsim_plan* pl, float* u, float* v, double max_velocity, void* stream) {
+  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_PLAIN_ONLY(pl);
+  int rc;
+  if ((rc = check_field(u, "u")) || (rc = check_field(v, "v"))) return rc;
+  MLSIM_REQUIRE(max_velocity > 0, "max_velocity must be positive");
+  if (!pl->d_smax && (rc = dev_alloc(pl, &pl->d_smax, (size_t)pl->cfg.batch))) return rc;
+  return launch_normalize_speed(u, v, pl->d_smax, pl->cfg.batch, pl->cfg.nx * pl->cfg.ny, (float)max_velocity,
+                                reinterpret_cast<cudaStream_t>(stream));
 }
 
 int mlsim_divergence(mlsim_plan* pl, const float* u, const float* v, float* d, void* stream) {

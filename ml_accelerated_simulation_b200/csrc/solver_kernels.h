@@ -21,6 +21,8 @@ bool project_cluster_supported(const SolverParams& p);
 int launch_project_cluster(float* u, float* v, float* pout, const float* inv_eig, const float2* tw,
                            const SolverParams& p, cudaStream_t st);
 // datagen_kernels.cu
+int launch_normalize_speed(float* u, float* v, unsigned int* scratch, int batch, int n_per_img, float max_velocity,
+                           cudaStream_t st);
 int launch_halo_push(const float* uv, float* up_uv, float* dn_uv, int images, int ext_rows, int ny, int nxl, int halo,
                      int lo, int hi, cudaStream_t st);
 int launch_downsample_staggered(const float* u, const float* v, float* cu, float* cv, int batch, int nx, int ny, int f,

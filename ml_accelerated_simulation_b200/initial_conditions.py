@@ -50,14 +50,10 @@ def filtered_velocity_field(grid: Grid, max_velocity: float = 1.0, peak_wavenumb
         comps.append(plan.spectral_multiply(noise, filt))
     # normalise first so fp32 projection works at O(1) magnitudes
     u, v = comps
-    speed = torch.sqrt(u * u + v * v).amax(dim=(-2, -1), keepdim=True)
-    u = (u * (max_velocity / speed)).to(torch.float32).contiguous()
-    v = (v * (max_velocity / speed)).to(torch.float32).contiguous()
+    plan.normalize_speed(u, v, max_velocity)
     for _ in range(iterations):
         plan.project(u, v, want_p=False)
-        speed = torch.sqrt(u * u + v * v).amax(dim=(-2, -1), keepdim=True)
-        u.mul_(max_velocity / speed)
-        v.mul_(max_velocity / speed)
+        plan.normalize_speed(u, v, max_velocity)
     plan.close()
     bc = PeriodicBoundaryConditions()
     return GridVariableVector((GridVariable(u.to(dtype), (1.0, 0.5), grid, bc),

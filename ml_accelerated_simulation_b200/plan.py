@@ -166,6 +166,11 @@ class Plan:
         _lib.check(self._lib.mlsim_spectral_multiply(self._h, t.data_ptr(), field.data_ptr(), out.data_ptr(), self._stream()))
         return out
 
+    def normalize_speed(self, u, v, max_velocity: float) -> None:
+        """In place, per trajectory: u, v *= max_velocity / max sqrt(u^2 + v^2)."""
+        self._field(u, "u"); self._field(v, "v")
+        _lib.check(self._lib.mlsim_normalize_speed(self._h, u.data_ptr(), v.data_ptr(), float(max_velocity), self._stream()))
+
     def divergence(self, u, v):
         self._field(u, "u"); self._field(v, "v")
         d = self.new_field()

@@ -50,6 +50,21 @@ __device__ __forceinline__ float face_flux(float cl, float c, float cr, float cr
   return fmaf(t2, (e > 0.0f) ? g : 0.0f, low) * w2;
 }
 
+// Same flux from precomputed differences (dl = c - cl, d = cr - c, dr = crr - cr): neighbouring faces share them and the
+// Laplacian is d - dl, so the stencil loads every difference once.
+template <int ADV>
+__device__ __forceinline__ float face_flux_d(float c, float cr, float dl, float d, float dr, float w2, float hq) {
+  const bool pos = w2 > 0.0f;
+  const float low = pos ? c : cr;
+  if (ADV == MLSIM_ADV_UPWIND) return low * w2;
+  const float t2 = fmaf(-hq, w2, pos ? 1.0f : -1.0f);
+  if (ADV == MLSIM_ADV_LAX_WENDROFF) return fmaf(t2, 0.5f * d, low) * w2;
+  const float num = pos ? dl : dr;
+  const float e = num * d;
+  const float g = e * rcp_approx(d + num);
+  return fmaf(t2, (e > 0.0f) ? g : 0.0f, low) * w2;
+}
+
 // SLAB (x-slab decomposition): no periodic wrap in x; the tile rows come from the halo-extended buffers (row index
 // clamped to the valid rows [-halo, nx+halo)), and one extra leading tile (blockIdx.y == 0 <-> rows [-32, 0)) computes
 // output row -1 -- the x-halo of u* that the divergence of the local row 0 needs -- so no second exchange is required.
@@ -131,22 +146,43 @@ k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
       au = *reinterpret_cast<const float4*>(a.accu + off);
       av = *reinterpret_cast<const float4*>(a.accv + off);
     }
-    float fxu[4], fxv[4], fyu[5], fyv[5];
+    float fxu[4], fxv[4], fyu[5], fyv[5], lapu[4], lapv[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int j = lj + k;
-      const float wxu = SU(i, j) + SU(i + 1, j);
-      fxu[k] = face_flux<ADV>(SU(i - 1, j), SU(i, j), SU(i + 1, j), SU(i + 2, j), wxu, hcx);
-      const float wxv = SU(i, j) + SU(i, j + 1);
-      fxv[k] = face_flux<ADV>(SV(i - 1, j), SV(i, j), SV(i + 1, j), SV(i + 2, j), wxv, hcx);
+      // x-direction differences of this column: (i-1 -> i), (i -> i+1), (i+1 -> i+2)
+      const float um = SU(i - 1, j), u0 = SU(i, j), u1 = SU(i + 1, j), u2 = SU(i + 2, j);
+      const float vm = SV(i - 1, j), v0 = SV(i, j), v1 = SV(i + 1, j), v2 = SV(i + 2, j);
+      const float dum = u0 - um, du0 = u1 - u0, dup = u2 - u1;
+      const float dvm = v0 - vm, dv0 = v1 - v0, dvp = v2 - v1;
+      const float wxu = u0 + u1;
+      fxu[k] = face_flux_d<ADV>(u0, u1, dum, du0, dup, wxu, hcx);
+      const float wxv = u0 + SU(i, j + 1);
+      fxv[k] = face_flux_d<ADV>(v0, v1, dvm, dv0, dvp, wxv, hcx);
+      lapu[k] = (du0 - dum) * p.nu_hx2;
+      lapv[k] = (dv0 - dvm) * p.nu_hx2;
     }
+    {
+      // y-direction differences of the row: columns lj-2 .. lj+5 -> 7 differences shared by the 5 faces and 4 Laplacians
+      float dyu[7], dyv[7];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const int j = lj - 1 + k;               // y-face between columns j and j+1
-      const float wyu = SV(i, j) + SV(i + 1, j);
-      fyu[k] = face_flux<ADV>(SU(i, j - 1), SU(i, j), SU(i, j + 1), SU(i, j + 2), wyu, hcy);
-      const float wyv = SV(i, j) + SV(i, j + 1);
-      fyv[k] = face_flux<ADV>(SV(i, j - 1), SV(i, j), SV(i, j + 1), SV(i, j + 2), wyv, hcy);
+      for (int m = 0; m < 7; ++m) {
+        dyu[m] = SU(i, lj - 1 + m) - SU(i, lj - 2 + m);
+        dyv[m] = SV(i, lj - 1 + m) - SV(i, lj - 2 + m);
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int j = lj - 1 + k;               // y-face between columns j and j+1
+        const float wyu = SV(i, j) + SV(i + 1, j);
+        fyu[k] = face_flux_d<ADV>(SU(i, j), SU(i, j + 1), dyu[k], dyu[k + 1], dyu[k + 2], wyu, hcy);
+        const float wyv = SV(i, j) + SV(i, j + 1);
+        fyv[k] = face_flux_d<ADV>(SV(i, j), SV(i, j + 1), dyv[k], dyv[k + 1], dyv[k + 2], wyv, hcy);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        lapu[k] = fmaf(dyu[k + 2] - dyu[k + 1], p.nu_hy2, lapu[k]);
+        lapv[k] = fmaf(dyv[k + 2] - dyv[k + 1], p.nu_hy2, lapv[k]);
+      }
     }
     float ku[4], kv[4];
 #pragma unroll
@@ -155,12 +191,8 @@ k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
       const float cu = SU(i, j), cv = SV(i, j);
       const float advu = -((fxu[k] - fxu_prev[k]) * hix + (fyu[k + 1] - fyu[k]) * hiy);
       const float advv = -((fxv[k] - fxv_prev[k]) * hix + (fyv[k + 1] - fyv[k]) * hiy);
-      const float lapu = (SU(i - 1, j) + SU(i + 1, j) - 2.0f * cu) * p.nu_hx2 +
-                         (SU(i, j - 1) + SU(i, j + 1) - 2.0f * cu) * p.nu_hy2;
-      const float lapv = (SV(i - 1, j) + SV(i + 1, j) - 2.0f * cv) * p.nu_hx2 +
-                         (SV(i, j - 1) + SV(i, j + 1) - 2.0f * cv) * p.nu_hy2;
-      ku[k] = advu + lapu - p.drag * cu + frc[k];
-      kv[k] = advv + lapv - p.drag * cv;
+      ku[k] = advu + lapu[k] - p.drag * cu + frc[k];
+      kv[k] = advv + lapv[k] - p.drag * cv;
       fxu_prev[k] = fxu[k];
       fxv_prev[k] = fxv[k];
     }

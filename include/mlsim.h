@@ -50,6 +50,15 @@ typedef struct {
   int32_t slab_rank, slab_world;  /* slab_world == 0: plain plan (whole grid on this device).  slab_world >= 1: this
                                    * rank owns global rows [slab_rank*nx/slab_world, (slab_rank+1)*nx/slab_world) of one
                                    * grid decomposed along x; only the mlsim_slab_* / mlsim_cnn_* entry points apply */
+  /* Execution tuning (0 = the measured default for the shape).  Results do not depend on these: trajectories are
+   * independent, so the block structure only changes how launches overlap. */
+  int32_t solver_blocks;          /* 1..8: independent batch blocks whose solver steps run on separate streams
+                                   * (default: 2 when the correction network follows every step, 4 for bare solver rollouts) */
+  int32_t host_blocks;            /* 1..4: equal batch blocks of the H2D | step | D2H pipeline of mlsim_rollout_host
+                                   * (default: sized in whole rounds of the persistent conv grid) */
+  int32_t cluster_projection;     /* 1: single-kernel projection (thread-block cluster per image, half spectrum in
+                                   * distributed shared memory); plain square 64 / 128 / 256 grids only.  Measured slower
+                                   * than the three-kernel projection at every BASELINE config, hence off by default */
 } mlsim_config;
 
 int  mlsim_plan_create (const mlsim_config* cfg, mlsim_plan** out);
@@ -153,6 +162,15 @@ int  mlsim_downsample_staggered(const float* u, const float* v, float* cu, float
                                 int32_t ny, int32_t factor, void* stream);
 int  mlsim_datagen_pair(mlsim_plan* fine, mlsim_plan* coarse, float* u, float* v, float* cu, float* cv,
                         int32_t n_between, int32_t n_inner, void* stream);
+
+/* ---- divergence guard (reference test/sim_test.py:82-87 tests isnan on the host after every step) ----
+ * With every > 0, after each `every`-th step of mlsim_step / mlsim_rollout_host a small kernel scans (u, v) and
+ * publishes, in a pinned host word, the index of the first step (counted from this call, starting at 1) after which
+ * a non-finite value was present.  No synchronisation is added to the step path.  every = 0 disables the guard. */
+int  mlsim_finite_check_enable(mlsim_plan* plan, int32_t every);
+/* Non-blocking: *first_bad_step = what the device has published so far (-1: every check so far passed);
+ * *steps_issued = steps enqueued since mlsim_finite_check_enable.  Synchronise the stream first for a final answer. */
+int  mlsim_finite_check_read(mlsim_plan* plan, int64_t* first_bad_step, int64_t* steps_issued);
 
 /* ---- introspection ---- */
 /* number of kernel launches one mlsim_step(nsteps=1) issues (solver only, or solver + cnn) */

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("MLSIM_LIB") or os.path.join(HERE, "libmlsim_b200.so")     # MLSIM_LIB: developer override (tuning variants)
+LIB_PATH = os.path.join(HERE, "libmlsim_b200.so")
 
 MLSIM_OK = 0
 
@@ -24,6 +24,7 @@ class MlsimConfig(C.Structure):
         ("advection", C.c_int32), ("lw_dt_scale", C.c_double),
         ("device", C.c_int32),
         ("slab_rank", C.c_int32), ("slab_world", C.c_int32),
+        ("solver_blocks", C.c_int32), ("host_blocks", C.c_int32), ("cluster_projection", C.c_int32),
     ]
 
 
@@ -63,6 +64,8 @@ _SIGNATURES = {
     "mlsim_slab_cnn_correct": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     "mlsim_downsample_staggered": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p]),
     "mlsim_datagen_pair": (C.c_int, [C.c_void_p] * 6 + [C.c_int32, C.c_int32, C.c_void_p]),
+    "mlsim_finite_check_enable": (C.c_int, [C.c_void_p, C.c_int32]),
+    "mlsim_finite_check_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mlsim_launches_per_step": (C.c_int, [C.c_void_p, C.c_int32]),
     "mlsim_workspace_bytes": (C.c_int64, [C.c_void_p]),
     "mlsim_time_kernel": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_void_p]),

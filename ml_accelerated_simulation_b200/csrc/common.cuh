@@ -109,6 +109,21 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
 }
 #endif
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: set it once per (kernel, device), so that a
+// second plan on another GPU of the same process gets it too.  `kernel` may contain template commas: pass it in parentheses.
+#define MLSIM_MAX_DEVICES 64
+#define MLSIM_SET_SMEM_ONCE(kernel, bytes)                                                                      \
+  do {                                                                                                          \
+    static bool done_[MLSIM_MAX_DEVICES] = {};                                                                  \
+    int dev_ = 0;                                                                                               \
+    MLSIM_CUDA_CHECK(cudaGetDevice(&dev_));                                                                     \
+    const bool in_ = dev_ >= 0 && dev_ < MLSIM_MAX_DEVICES;                                                     \
+    if (!in_ || !done_[dev_]) {                                                                                 \
+      MLSIM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      if (in_) done_[dev_] = true;                                                                              \
+    }                                                                                                           \
+  } while (0)
+
 static inline int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
 static inline bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 

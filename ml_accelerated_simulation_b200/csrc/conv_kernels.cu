@@ -596,11 +596,7 @@ int conv_pick_strip(int nx, int ny, int batch, int sm_count) {
 template <int NB, bool LAST>
 static int launch_conv_mid_t(const ConvMidArgs& a, int sm_count, cudaStream_t st) {
   using L = ConvMidSmem<NB>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    MLSIM_CUDA_CHECK(cudaFuncSetAttribute(k_conv_mid<NB, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_done = true;
-  }
+  MLSIM_SET_SMEM_ONCE((k_conv_mid<NB, LAST>), L::TOTAL);
   const int nyt = (a.ny + 127) / 128;
   const int nstrips = (a.nx + a.rs - 1) / a.rs;
   const long nitems = (long)a.batch * nstrips * nyt;

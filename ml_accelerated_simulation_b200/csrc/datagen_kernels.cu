@@ -148,4 +148,35 @@ int launch_downsample_staggered(const float* u, const float* v, float* cu, float
   return MLSIM_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Divergence guard (reference test/sim_test.py:82-87 tests isnan on the host after every step): scan (u, v) for
+// non-finite values and record the smallest step index at which one was present.  One float4 pass over the state
+// (8 B/cell) every `every` steps; the flag is a device word that the caller copies to pinned host memory
+// asynchronously, so the step path never synchronises.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_finite_check(const float4* __restrict__ u, const float4* __restrict__ v, size_t n4, unsigned long long step,
+               unsigned long long* __restrict__ flag) {
+  pdl_launch_dependents();
+  pdl_wait();
+  bool bad = false;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(u + e), b = __ldg(v + e);
+    // x - x is 0 for finite x and NaN for +-inf / NaN
+    const float t = (a.x - a.x) + (a.y - a.y) + (a.z - a.z) + (a.w - a.w) + (b.x - b.x) + (b.y - b.y) + (b.z - b.z) + (b.w - b.w);
+    bad |= !(t == 0.0f);
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicMin(flag, step);
+}
+
+int launch_finite_check(const float* u, const float* v, size_t n, unsigned long long step, unsigned long long* flag,
+                        cudaStream_t st) {
+  const size_t n4 = n / 4;                       // field sizes are multiples of 4 (ny is a power of two >= 64)
+  const size_t want = (n4 + 255) / 256;
+  const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+  MLSIM_CUDA_CHECK(launch_pdl(k_finite_check, dim3(grid), dim3(256), 0, st, reinterpret_cast<const float4*>(u),
+                              reinterpret_cast<const float4*>(v), n4, step, flag));
+  return MLSIM_OK;
+}
+
 }  // namespace mlsim

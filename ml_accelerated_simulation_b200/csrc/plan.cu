@@ -7,6 +7,8 @@
 #include <utility>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges are no-ops unless a profiler is attached
+
 #include "common.cuh"
 #include "conv_kernels.h"
 #include "solver_kernels.h"
@@ -31,6 +33,21 @@ struct CnnLayer {
 }  // namespace mlsim
 
 using namespace mlsim;
+
+// Every launching entry point: the plan's device becomes current (one plan == one device; the per-device kernel
+// attributes and the launches themselves follow the current device).
+#define MLSIM_ENTER(pl)                                           \
+  do {                                                            \
+    if (!(pl)) { set_error("null plan"); return MLSIM_EINVAL; }   \
+    MLSIM_CUDA_CHECK(cudaSetDevice((pl)->cfg.device));            \
+  } while (0)
+
+namespace {
+struct NvtxRange {                     // named ranges around the solver stages / the network
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace
 
 #define MLSIM_SLAB_HALO 8          /* halo rows on each side of the halo-extended field buffers */
 #define MLSIM_SLAB_CNN_HALO 7      /* rows of state the 7-layer 3x3 CNN needs from each neighbour (one per layer) */
@@ -78,6 +95,11 @@ struct mlsim_plan {
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_SPLIT - 1] = {};
   static constexpr int MAX_CHUNKS = 4;
   cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_done[MAX_CHUNKS] = {};
+  // divergence guard (mlsim_finite_check_*): device flag = first bad step, mirrored into pinned host memory
+  int fc_every = 0;
+  long long fc_steps = 0;
+  unsigned long long* d_fcflag = nullptr;
+  unsigned long long* h_fcflag = nullptr;
   // timing scratch
   float* d_tu = nullptr; float* d_tv = nullptr;
   unsigned long long* d_dbg = nullptr;   // per-CTA cycle counters of the conv kernels under mlsim_time_kernel
@@ -188,6 +210,7 @@ struct Chunk {
 
 // P(u,v) in place on (u,v): K2 -> K3 -> K4
 int project(mlsim_plan* pl, float* u, float* v, float* p_or_null, cudaStream_t st, Chunk c) {
+  NvtxRange nvtx("mlsim.projection");
   int rc;
   const SolverParams sp = c.sp(pl);
   if (pl->cluster_projection) {           // small square grids: the whole projection in one cluster kernel
@@ -207,12 +230,14 @@ int project(mlsim_plan* pl, float* u, float* v, float* p_or_null, cudaStream_t s
 }
 
 int explicit_prof(mlsim_plan* pl, const StageArgs& a, cudaStream_t st, Chunk c) {
+  NvtxRange nvtx("mlsim.explicit_terms");
   ProfScope ps(pl, 0, st);
   return launch_explicit(a, c.sp(pl), pl->d_forcing, st);
 }
 
 // One classic-RK4 step with a projection after every stage, in place on (u,v).
 int solver_step(mlsim_plan* pl, float* u, float* v, float* p_or_null, cudaStream_t st, Chunk c) {
+  NvtxRange nvtx("mlsim.solver_step (RK4: 4 x [explicit terms, projection])");
   const float dt = (float)pl->cfg.dt;
   const size_t o = c.foff(pl);
   float *w1u = pl->d_w1u + o, *w1v = pl->d_w1v + o, *w2u = pl->d_w2u + o, *w2v = pl->d_w2v + o;
@@ -245,6 +270,7 @@ int solver_step(mlsim_plan* pl, float* u, float* v, float* p_or_null, cudaStream
 // (with the ResNet shortcuts fused into their epilogues), last conv + shortcut + correction add (or y_nchw).
 int run_cnn_layers(mlsim_plan* pl, const float* u_in, const float* v_in, float* u, float* v, float* y_nchw, double scale,
                    int rows, int batch, long long img_stride, size_t aoff, cudaStream_t st) {
+  NvtxRange nvtx("mlsim.correction_cnn (v += model(v))");
   const mlsim_config& c = pl->cfg;
   const int L = (int)pl->layers.size();
   int rc;
@@ -288,9 +314,8 @@ int cnn_apply(mlsim_plan* pl, const float* u_in, const float* v_in, float* u, fl
 }
 
 // number of independent batch blocks the solver part of a step is cut into (one stream each)
-int solver_blocks(int apply_cnn, int nb) {
-  static const int nstreams_env = [] { const char* e = getenv("MLSIM_SOLVER_STREAMS"); return e ? atoi(e) : 0; }();
-  int ns = nstreams_env > 0 ? nstreams_env : (apply_cnn ? 2 : 4);
+int solver_blocks(const mlsim_plan* pl, int apply_cnn, int nb) {
+  int ns = pl->cfg.solver_blocks > 0 ? pl->cfg.solver_blocks : (apply_cnn ? 2 : 4);
   if (ns > mlsim_plan::MAX_SPLIT) ns = mlsim_plan::MAX_SPLIT;
   if (ns > nb) ns = nb;
   return ns < 1 ? 1 : ns;
@@ -300,13 +325,13 @@ int solver_blocks(int apply_cnn, int nb) {
 int run_steps(mlsim_plan* pl, float* u, float* v, float* p_or_null, int nsteps, int apply_cnn, double scale,
               cudaStream_t st, Chunk c, bool allow_split = true) {
   int rc;
-  // The batch is cut into MLSIM_SOLVER_STREAMS blocks of independent trajectories whose solver steps run on separate
+  // The batch is cut into mlsim_config.solver_blocks blocks of independent trajectories whose solver steps run on separate
   // streams: kernels of different blocks are in different phases (load / transform / store), so their latencies
   // overlap where one big launch runs its CTAs in lockstep.  Joined before the correction network.
   // Measured at config 2 (bench.py, 200 steps): solver only 0.307 / 0.287 / 0.284 ms with 1 / 2 / 4 blocks; with the
   // correction network behind every step 1.823 (1) / 1.785 (2) / 1.805 ms (4): each join before the CNN costs a little,
   // so rollouts with the network use 2 blocks and bare solver rollouts (data generation) 4.
-  int ns = allow_split ? solver_blocks(apply_cnn, c.nb) : 1;
+  int ns = allow_split ? solver_blocks(pl, apply_cnn, c.nb) : 1;
   for (int s = 0; s < nsteps; ++s) {
     float* pp = (s == nsteps - 1) ? p_or_null : nullptr;
     if (ns == 1) {
@@ -327,6 +352,11 @@ int run_steps(mlsim_plan* pl, float* u, float* v, float* p_or_null, int nsteps, 
       }
     }
     if (apply_cnn && (rc = cnn_apply(pl, u, v, u, v, nullptr, scale, st, c))) return rc;
+    if (pl->fc_every > 0 && (pl->fc_steps + s + 1) % pl->fc_every == 0) {
+      if ((rc = launch_finite_check(u, v, (size_t)c.nb * pl->cfg.nx * pl->cfg.ny, (unsigned long long)(pl->fc_steps + s + 1),
+                                    pl->d_fcflag, st))) return rc;
+      MLSIM_CUDA_CHECK(cudaMemcpyAsync(pl->h_fcflag, pl->d_fcflag, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    }
   }
   return MLSIM_OK;
 }
@@ -346,6 +376,13 @@ int mlsim_plan_create(const mlsim_config* cfg, mlsim_plan** out) {
   MLSIM_REQUIRE(cfg->batch >= 1 && cfg->batch <= 65535, "batch must be in [1, 65535]");
   MLSIM_REQUIRE(cfg->lx > 0 && cfg->ly > 0 && cfg->dt > 0 && cfg->density > 0, "lx, ly, dt, density must be positive");
   MLSIM_REQUIRE(cfg->advection >= 0 && cfg->advection <= 2, "unknown advection scheme");
+  MLSIM_REQUIRE(cfg->solver_blocks >= 0 && cfg->solver_blocks <= mlsim_plan::MAX_SPLIT, "solver_blocks must be in [0, 8]");
+  MLSIM_REQUIRE(cfg->host_blocks >= 0 && cfg->host_blocks <= mlsim_plan::MAX_CHUNKS, "host_blocks must be in [0, 4]");
+  // KolmogorovForcing(diam, wave_number): the reference only ever builds it with diam = domain length = 2*pi
+  // (src/inference.py:61,81-82), where "sin(k y)" and "sin(2 pi k y / diam)" coincide.  For any other domain the two
+  // readings of the third-party formula differ and neither can be checked here, so it is refused rather than guessed.
+  MLSIM_REQUIRE(cfg->forcing_scale == 0.0 || fabs(cfg->ly - 2.0 * 3.14159265358979323846) < 1e-9,
+                "Kolmogorov forcing is defined here for ly = 2*pi only (set forcing_scale = 0 for other domains)");
   MLSIM_REQUIRE((long)cfg->batch * (cfg->nx > 2048 ? cfg->nx / 2048 : 1) <= 65535, "batch * (nx/2048) must be <= 65535");
   const bool slab = cfg->slab_world >= 1;
   if (slab) {
@@ -405,11 +442,13 @@ int mlsim_plan_create(const mlsim_config* cfg, mlsim_plan** out) {
   pl->field_elems = (size_t)cfg->batch * sp.nx * cfg->ny;
   // Single-kernel projection (thread-block cluster per image, DSMEM half spectrum): measured on B200 against the
   // three-kernel path -- 256^2 x 64: 0.0665 vs 0.0525 ms per projection; after the K2/K4 rewrites also 128^2 x 512
-  // (solver step 0.711 vs 0.565 ms) and 64^2 x 2048 (0.542 vs 0.529 ms).  Opt-in only: MLSIM_CLUSTER_PROJECTION=1.
-  {
-    const char* ev = getenv("MLSIM_CLUSTER_PROJECTION");
-    pl->cluster_projection = !slab && project_cluster_supported(sp) && ev != nullptr && ev[0] == '1';
+  // (solver step 0.711 vs 0.565 ms) and 64^2 x 2048 (0.542 vs 0.529 ms).  Opt-in only: mlsim_config.cluster_projection.
+  if (cfg->cluster_projection && (slab || !project_cluster_supported(sp))) {
+    set_error("cluster_projection needs a plain square 64 / 128 / 256 grid");
+    delete pl;
+    return MLSIM_EINVAL;
   }
+  pl->cluster_projection = cfg->cluster_projection != 0;
 
   int rc = build_tables(pl);
   const size_t n = pl->field_elems;
@@ -459,6 +498,8 @@ int mlsim_plan_destroy(mlsim_plan* pl) {
                   pl->d_accu, pl->d_accv, pl->d_spec, pl->d_tw_n2, pl->d_split, pl->d_filt, pl->d_smax, pl->d_act[0], pl->d_act[1], pl->d_act[2], pl->d_hu, pl->d_hv, pl->d_hp,
                   pl->d_tu, pl->d_tv, pl->d_dbg};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (pl->d_fcflag) cudaFree(pl->d_fcflag);
+  if (pl->h_fcflag) cudaFreeHost(pl->h_fcflag);
   for (auto& l : pl->layers) if (l.d_wimg) cudaFree(l.d_wimg);
   if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
   for (int i = 0; i < mlsim_plan::MAX_SPLIT - 1; ++i) {
@@ -529,7 +570,7 @@ int64_t mlsim_cnn_pack_host(int32_t kind, int32_t cin, int32_t cout, const doubl
 }
 
 int mlsim_cnn_begin(mlsim_plan* pl, int32_t nlayers) {
-  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_ENTER(pl);
   MLSIM_REQUIRE(nlayers >= 2 && nlayers <= 64, "the tensor-core path needs 2..64 conv layers");
   for (auto& l : pl->layers) if (l.d_wimg) { cudaFree(l.d_wimg); l.d_wimg = nullptr; }
   pl->layers.assign(nlayers, CnnLayer());
@@ -567,7 +608,7 @@ int mlsim_cnn_set_layer(mlsim_plan* pl, int32_t layer, int32_t cin, int32_t cout
 
 int mlsim_cnn_set_shortcut(mlsim_plan* pl, int32_t layer, int32_t src_layer, const void* w1x1, const void* b1x1,
                            int32_t src_dtype) {
-  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_ENTER(pl);
   const int L = (int)pl->layers.size();
   MLSIM_REQUIRE(layer >= 1 && layer < L && pl->layers[layer].set, "set the layer before its shortcut (layer >= 1)");
   MLSIM_REQUIRE(src_layer >= -1 && src_layer < layer - 1, "the shortcut source must be an earlier layer's output (-1: network input)");
@@ -593,7 +634,7 @@ int mlsim_cnn_set_shortcut(mlsim_plan* pl, int32_t layer, int32_t src_layer, con
 }
 
 int mlsim_cnn_finalize(mlsim_plan* pl) {
-  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_ENTER(pl);
   const int L = (int)pl->layers.size();
   MLSIM_REQUIRE(L >= 2, "no layers declared");
   for (int i = 0; i < L; ++i) {
@@ -673,48 +714,18 @@ int mlsim_cnn_finalize(mlsim_plan* pl) {
 
 int mlsim_step(mlsim_plan* pl, float* u, float* v, float* p_or_null, int32_t nsteps, int32_t apply_cnn,
                double cnn_input_scale, void* stream) {
-  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_ENTER(pl);
   MLSIM_PLAIN_ONLY(pl);
   int rc;
   if ((rc = check_field(u, "u")) || (rc = check_field(v, "v"))) return rc;
   if (p_or_null && (rc = check_field(p_or_null, "p"))) return rc;
   MLSIM_REQUIRE(nsteps >= 0, "nsteps must be >= 0");
   if (apply_cnn && !pl->cnn_ready) { set_error("apply_cnn set but the correction network is not finalised"); return MLSIM_ESTATE; }
+  if (apply_cnn) MLSIM_REQUIRE(pl->layers.back().cout == 2, "v += model(v) needs a 2-channel network output (u, v)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // experiment hook: run the batch in independent blocks, block after block (smaller per-launch working set)
-  static const int nchunks_env = [] { const char* e = getenv("MLSIM_STEP_CHUNKS"); return e ? atoi(e) : 1; }();
-  const int B = pl->cfg.batch;
-  const int nchunks = (nchunks_env >= 1 && nchunks_env <= B) ? nchunks_env : 1;
-  // experiment hook: whole steps (solver + correction) of independent batch blocks on separate streams, so that one
-  // block's issue-bound solver kernels can share the SMs with the other block's tensor-bound convolutions
-  static const int full_streams = [] { const char* e = getenv("MLSIM_FULL_STREAMS"); return e ? atoi(e) : 1; }();
-  if (full_streams >= 2 && B >= full_streams && nsteps > 0) {
-    const int ns = full_streams > mlsim_plan::MAX_SPLIT ? mlsim_plan::MAX_SPLIT : full_streams;
-    const size_t img = (size_t)pl->cfg.nx * pl->cfg.ny;
-    MLSIM_CUDA_CHECK(cudaEventRecord(pl->ev_fork, st));
-    for (int k = 0; k < ns; ++k) {
-      const int b0 = (int)((long)B * k / ns), b1 = (int)((long)B * (k + 1) / ns);
-      const size_t off = (size_t)b0 * img;
-      cudaStream_t sk = (k == 0) ? st : pl->split_stream[k - 1];
-      if (k > 0) MLSIM_CUDA_CHECK(cudaStreamWaitEvent(sk, pl->ev_fork, 0));
-      if ((rc = run_steps(pl, u + off, v + off, p_or_null ? p_or_null + off : nullptr, nsteps, apply_cnn, cnn_input_scale,
-                          sk, Chunk{b0, b1 - b0}, false))) return rc;
-      if (k > 0) {
-        MLSIM_CUDA_CHECK(cudaEventRecord(pl->ev_join[k - 1], sk));
-        MLSIM_CUDA_CHECK(cudaStreamWaitEvent(st, pl->ev_join[k - 1], 0));
-      }
-    }
-    return MLSIM_OK;
-  }
-  if (nchunks == 1) return run_steps(pl, u, v, p_or_null, nsteps, apply_cnn, cnn_input_scale, st, Chunk{0, B});
-  const size_t img = (size_t)pl->cfg.nx * pl->cfg.ny;
-  for (int k = 0; k < nchunks; ++k) {
-    const int b0 = (int)((long)B * k / nchunks), b1 = (int)((long)B * (k + 1) / nchunks);
-    const size_t off = (size_t)b0 * img;
-    if ((rc = run_steps(pl, u + off, v + off, p_or_null ? p_or_null + off : nullptr, nsteps, apply_cnn, cnn_input_scale,
-                        st, Chunk{b0, b1 - b0}))) return rc;
-  }
-  return MLSIM_OK;
+  const int rc2 = run_steps(pl, u, v, p_or_null, nsteps, apply_cnn, cnn_input_scale, st, Chunk{0, pl->cfg.batch});
+  if (!rc2) pl->fc_steps += nsteps;
+  return rc2;
 }
 
 int mlsim_rollout_host(mlsim_plan* pl, float* hu, float* hv, float* hp, int32_t nsteps, int32_t apply_cnn,
@@ -723,6 +734,7 @@ int mlsim_rollout_host(mlsim_plan* pl, float* hu, float* hv, float* hp, int32_t 
   MLSIM_PLAIN_ONLY(pl);
   MLSIM_REQUIRE(nsteps >= 0, "nsteps must be >= 0");
   if (apply_cnn && !pl->cnn_ready) { set_error("apply_cnn set but the correction network is not finalised"); return MLSIM_ESTATE; }
+  if (apply_cnn) MLSIM_REQUIRE(pl->layers.back().cout == 2, "v += model(v) needs a 2-channel network output (u, v)");
   MLSIM_CUDA_CHECK(cudaSetDevice(pl->cfg.device));
   const size_t n = pl->field_elems;
   int rc;
@@ -756,15 +768,10 @@ int mlsim_rollout_host(mlsim_plan* pl, float* hu, float* hv, float* hp, int32_t 
       if (e1 >= 1 && e2 > e1 && e2 < B) { nchunks = 3; bounds[0] = 0; bounds[1] = e1; bounds[2] = e2; bounds[3] = B; }
     }
   }
-  if (const char* e = getenv("MLSIM_HOST_CHUNKS")) {          // developer override: equal blocks
-    const int v = atoi(e);
-    if (v >= 1 && v <= mlsim_plan::MAX_CHUNKS && v <= B) { nchunks = v; for (int k = 0; k <= v; ++k) bounds[k] = (int)((long)B * k / v); }
-  }
-  if (const char* e = getenv("MLSIM_HOST_CHUNK_SIZES")) {     // developer override: explicit sizes "a,b,c"
-    int n = 0, acc = 0; const char* q = e;
-    int tmp[mlsim_plan::MAX_CHUNKS + 1] = {0};
-    while (*q && n < mlsim_plan::MAX_CHUNKS) { const int v = atoi(q); if (v <= 0) break; acc += v; tmp[++n] = acc; while (*q && *q != ',') ++q; if (*q == ',') ++q; }
-    if (n >= 1 && acc == B) { nchunks = n; for (int k = 0; k <= n; ++k) bounds[k] = tmp[k]; }
+  if (pl->cfg.host_blocks > 0) {                               // caller's choice: equal blocks
+    const int v = pl->cfg.host_blocks < B ? pl->cfg.host_blocks : B;
+    nchunks = v;
+    for (int k = 0; k <= v; ++k) bounds[k] = (int)((long)B * k / v);
   }
   const size_t img = (size_t)pl->cfg.nx * pl->cfg.ny;
   cudaStream_t sc = pl->own_stream;
@@ -785,11 +792,12 @@ int mlsim_rollout_host(mlsim_plan* pl, float* hu, float* hv, float* hp, int32_t 
   }
   MLSIM_CUDA_CHECK(cudaStreamSynchronize(pl->out_stream));
   MLSIM_CUDA_CHECK(cudaStreamSynchronize(sc));
+  pl->fc_steps += nsteps;
   return MLSIM_OK;
 }
 
 int mlsim_explicit_terms(mlsim_plan* pl, const float* u, const float* v, float* du, float* dv, void* stream) {
-  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_ENTER(pl);
   MLSIM_PLAIN_ONLY(pl);
   int rc;
   if ((rc = check_field(u, "u")) || (rc = check_field(v, "v")) || (rc = check_field(du, "du")) || (rc = check_field(dv, "dv"))) return rc;
@@ -800,7 +808,7 @@ int mlsim_explicit_terms(mlsim_plan* pl, const float* u, const float* v, float* 
 }
 
 int mlsim_project(mlsim_plan* pl, float* u, float* v, float* p_or_null, void* stream) {
-  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_ENTER(pl);
   MLSIM_PLAIN_ONLY(pl);
   int rc;
   if ((rc = check_field(u, "u")) || (rc = check_field(v, "v"))) return rc;
@@ -812,6 +820,7 @@ int mlsim_project(mlsim_plan* pl, float* u, float* v, float* p_or_null, void* st
 // table: HOST fp64 [nx][ny/2+1] in natural kx order.  Set-up path: synchronises `stream` (table upload).
 int mlsim_spectral_multiply(mlsim_plan* pl, const double* table, const float* in, float* out, void* stream) {
   if (!pl || !table) { set_error("null argument"); return MLSIM_EINVAL; }
+  MLSIM_CUDA_CHECK(cudaSetDevice(pl->cfg.device));
   MLSIM_PLAIN_ONLY(pl);
   int rc;
   if ((rc = check_field(in, "in")) || (rc = check_field(out, "out"))) return rc;
@@ -838,7 +847,7 @@ int mlsim_spectral_multiply(mlsim_plan* pl, const double* table, const float* in
 
 // Per trajectory: u, v *= max_velocity / max sqrt(u^2 + v^2) -- the rescaling step of filtered_velocity_field.
 int mlsim_normalize_speed(mlsim_plan* pl, float* u, float* v, double max_velocity, void* stream) {
-  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_ENTER(pl);
   MLSIM_PLAIN_ONLY(pl);
   int rc;
   if ((rc = check_field(u, "u")) || (rc = check_field(v, "v"))) return rc;
@@ -849,7 +858,7 @@ int mlsim_normalize_speed(mlsim_plan* pl, float* u, float* v, double max_velocit
 }
 
 int mlsim_divergence(mlsim_plan* pl, const float* u, const float* v, float* d, void* stream) {
-  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_ENTER(pl);
   MLSIM_PLAIN_ONLY(pl);
   int rc;
   if ((rc = check_field(u, "u")) || (rc = check_field(v, "v")) || (rc = check_field(d, "div"))) return rc;
@@ -857,7 +866,7 @@ int mlsim_divergence(mlsim_plan* pl, const float* u, const float* v, float* d, v
 }
 
 int mlsim_cnn_forward(mlsim_plan* pl, const float* u, const float* v, float* y, double scale, void* stream) {
-  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_ENTER(pl);
   MLSIM_PLAIN_ONLY(pl);
   int rc;
   if ((rc = check_field(u, "u")) || (rc = check_field(v, "v")) || (rc = check_field(y, "y"))) return rc;
@@ -865,7 +874,7 @@ int mlsim_cnn_forward(mlsim_plan* pl, const float* u, const float* v, float* y, 
 }
 
 int mlsim_cnn_correct(mlsim_plan* pl, float* u, float* v, double scale, void* stream) {
-  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_ENTER(pl);
   MLSIM_PLAIN_ONLY(pl);
   int rc;
   if ((rc = check_field(u, "u")) || (rc = check_field(v, "v"))) return rc;
@@ -900,7 +909,7 @@ int mlsim_slab_geometry(mlsim_plan* pl, int64_t* out8) {
 
 int mlsim_slab_stage_a(mlsim_plan* pl, int32_t stage, const float* us, const float* u0, float* acc, float* out,
                        void* spec_send, void* stream) {
-  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_ENTER(pl);
   MLSIM_SLAB_ONLY(pl);
   MLSIM_REQUIRE(stage >= 0 && stage <= 3, "stage must be 0..3");
   int rc;
@@ -927,7 +936,7 @@ int mlsim_slab_stage_a(mlsim_plan* pl, int32_t stage, const float* us, const flo
 }
 
 int mlsim_slab_divergence_rfft(mlsim_plan* pl, const float* uv, void* spec_send, void* stream) {
-  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_ENTER(pl);
   MLSIM_SLAB_ONLY(pl);
   int rc;
   if ((rc = check_field(uv, "uv"))) return rc;
@@ -939,7 +948,7 @@ int mlsim_slab_divergence_rfft(mlsim_plan* pl, const float* uv, void* spec_send,
 }
 
 int mlsim_slab_stage_b(mlsim_plan* pl, const void* spec_recv, void* spec_send2, void* stream) {
-  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_ENTER(pl);
   MLSIM_SLAB_ONLY(pl);
   int rc;
   if ((rc = check_field(spec_recv, "spec_recv"))) return rc;
@@ -953,7 +962,7 @@ int mlsim_slab_stage_b(mlsim_plan* pl, const void* spec_recv, void* spec_send2, 
 }
 
 int mlsim_slab_stage_c(mlsim_plan* pl, const void* spec_recv2, float* uv, float* p_or_null, void* stream) {
-  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_ENTER(pl);
   MLSIM_SLAB_ONLY(pl);
   int rc;
   if ((rc = check_field(spec_recv2, "spec_recv2")) || (rc = check_field(uv, "uv"))) return rc;
@@ -969,7 +978,7 @@ int mlsim_slab_stage_c(mlsim_plan* pl, const void* spec_recv2, float* uv, float*
 // rows into the lower neighbour's high halo.  up_uv / dn_uv: the neighbours' field pair (same buffer role) as mapped
 // into this process, or NULL to skip that side (edges of a non-periodic exchange).  The caller follows with a barrier.
 int mlsim_slab_halo_push(mlsim_plan* pl, const float* uv, float* up_uv, float* dn_uv, int32_t lo, int32_t hi, void* stream) {
-  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_ENTER(pl);
   MLSIM_SLAB_ONLY(pl);
   int rc;
   if ((rc = check_field(uv, "uv"))) return rc;
@@ -986,7 +995,7 @@ int mlsim_slab_halo_push(mlsim_plan* pl, const float* uv, float* up_uv, float* d
 // column chunk r straight into rank r's buffer at this rank's slot, and stage_b (spec_send2 == NULL) does the same for
 // the backward chunks; the caller replaces each all-to-all by a cross-rank barrier.
 int mlsim_slab_set_peers(mlsim_plan* pl, const uint64_t* fwd_recv, const uint64_t* bwd_recv) {
-  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_ENTER(pl);
   MLSIM_SLAB_ONLY(pl);
   if (!fwd_recv || !bwd_recv) { pl->have_peers = false; return MLSIM_OK; }
   const int W = pl->cfg.slab_world, r = pl->cfg.slab_rank;
@@ -1007,7 +1016,7 @@ int mlsim_slab_set_peers(mlsim_plan* pl, const uint64_t* fwd_recv, const uint64_
 // (halo rows [-7, 0) and [nxl, nxl+7) must be current), the network runs on rows [lo, hi) = the slab plus those
 // halos (the outermost l rows of layer l's output are contaminated by the artificial edge and never reach local rows).
 int mlsim_slab_cnn_correct(mlsim_plan* pl, float* uv, double scale, void* stream) {
-  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_ENTER(pl);
   MLSIM_SLAB_ONLY(pl);
   int rc;
   if ((rc = check_field(uv, "uv"))) return rc;
@@ -1036,6 +1045,12 @@ int mlsim_downsample_staggered(const float* u, const float* v, float* cu, float*
   int rc;
   if ((rc = check_field(u, "u")) || (rc = check_field(v, "v")) || (rc = check_field(cu, "cu")) || (rc = check_field(cv, "cv"))) return rc;
   MLSIM_REQUIRE(batch >= 1 && nx >= 1 && ny >= 1 && factor >= 1, "bad shape");
+  {
+    cudaPointerAttributes at;                      // no plan here: launch on the device that owns the fields
+    MLSIM_CUDA_CHECK(cudaPointerGetAttributes(&at, u));
+    MLSIM_REQUIRE(at.type == cudaMemoryTypeDevice, "u must be device memory");
+    MLSIM_CUDA_CHECK(cudaSetDevice(at.device));
+  }
   MLSIM_REQUIRE(nx % factor == 0 && ny % factor == 0, "`factor` must divide the grid (block_reduce of the reference raises)");
   MLSIM_REQUIRE(factor == 1 || ((ny % 4) == 0), "ny must be a multiple of 4");
   return launch_downsample_staggered(u, v, cu, cv, batch, nx, ny, factor, reinterpret_cast<cudaStream_t>(stream));
@@ -1044,6 +1059,7 @@ int mlsim_downsample_staggered(const float* u, const float* v, float* cu, float*
 int mlsim_datagen_pair(mlsim_plan* fine, mlsim_plan* coarse, float* u, float* v, float* cu, float* cv,
                        int32_t n_between, int32_t n_inner, void* stream) {
   if (!fine || !coarse) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_CUDA_CHECK(cudaSetDevice(fine->cfg.device));
   MLSIM_PLAIN_ONLY(fine);
   MLSIM_PLAIN_ONLY(coarse);
   int rc;
@@ -1061,11 +1077,38 @@ int mlsim_datagen_pair(mlsim_plan* fine, mlsim_plan* coarse, float* u, float* v,
   return run_steps(coarse, cu, cv, nullptr, 1, 0, 1.0, st, cc);
 }
 
+int mlsim_finite_check_enable(mlsim_plan* pl, int32_t every) {
+  MLSIM_ENTER(pl);
+  MLSIM_PLAIN_ONLY(pl);
+  MLSIM_REQUIRE(every >= 0, "every must be >= 0");
+  if (every > 0 && !pl->d_fcflag) {
+    int rc = dev_alloc(pl, &pl->d_fcflag, 1);
+    if (rc) return rc;
+    MLSIM_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&pl->h_fcflag), sizeof(unsigned long long), cudaHostAllocDefault));
+  }
+  if (pl->d_fcflag) {
+    MLSIM_CUDA_CHECK(cudaDeviceSynchronize());                 // set-up call: no check of an earlier run is in flight
+    MLSIM_CUDA_CHECK(cudaMemset(pl->d_fcflag, 0xff, sizeof(unsigned long long)));
+    *pl->h_fcflag = ~0ull;
+  }
+  pl->fc_every = every;
+  pl->fc_steps = 0;
+  return MLSIM_OK;
+}
+
+int mlsim_finite_check_read(mlsim_plan* pl, int64_t* first_bad_step, int64_t* steps_issued) {
+  if (!pl || !first_bad_step || !steps_issued) { set_error("null argument"); return MLSIM_EINVAL; }
+  const unsigned long long f = pl->h_fcflag ? *reinterpret_cast<volatile unsigned long long*>(pl->h_fcflag) : ~0ull;
+  *first_bad_step = (f == ~0ull) ? -1 : (int64_t)f;
+  *steps_issued = pl->fc_steps;
+  return MLSIM_OK;
+}
+
 int mlsim_launches_per_step(mlsim_plan* pl, int32_t apply_cnn) {
   if (!pl) return MLSIM_EINVAL;
   int n = pl->cluster_projection ? 8 : 16;   // 4 stages x (explicit + cluster projection | explicit, div+rfft, column solve, irfft+grad)
   if (pl->slab || pl->r0 > 1) n = 4 * 6;     // split x-transform: explicit, div+rfft, pass A, column solve, pass C, irfft+grad
-  if (!pl->slab) n *= solver_blocks(apply_cnn && pl->cnn_ready, pl->cfg.batch);   // one set of solver launches per batch block
+  if (!pl->slab) n *= solver_blocks(pl, apply_cnn && pl->cnn_ready, pl->cfg.batch);   // one set of solver launches per batch block
   if (apply_cnn && pl->cnn_ready) n += (int)pl->layers.size();
   return n;
 }
@@ -1088,7 +1131,7 @@ int mlsim_conv_debug(mlsim_plan* pl, double* out8) {
 }
 
 int mlsim_profile_enable(mlsim_plan* pl, int32_t kernel_class, int32_t max_samples) {
-  if (!pl) { set_error("null plan"); return MLSIM_EINVAL; }
+  MLSIM_ENTER(pl);
   MLSIM_REQUIRE(kernel_class >= -1 && kernel_class <= 7 && max_samples >= 0 && max_samples <= (1 << 20), "bad arguments");
   MLSIM_CUDA_CHECK(cudaSetDevice(pl->cfg.device));
   while ((int)pl->prof_events.size() < max_samples) {
@@ -1104,6 +1147,7 @@ int mlsim_profile_enable(mlsim_plan* pl, int32_t kernel_class, int32_t max_sampl
 
 int mlsim_profile_read(mlsim_plan* pl, float* total_ms, int32_t* count) {
   if (!pl || !total_ms || !count) { set_error("null argument"); return MLSIM_EINVAL; }
+  MLSIM_CUDA_CHECK(cudaSetDevice(pl->cfg.device));
   float tot = 0.f;
   for (size_t i = 0; i < pl->prof_used; ++i) {
     MLSIM_CUDA_CHECK(cudaEventSynchronize(pl->prof_events[i].second));
@@ -1119,6 +1163,7 @@ int mlsim_profile_read(mlsim_plan* pl, float* total_ms, int32_t* count) {
 
 int mlsim_time_kernel(mlsim_plan* pl, int32_t which, int32_t warmup, int32_t iters, float* ms_out, void* stream) {
   if (!pl || !ms_out) { set_error("null argument"); return MLSIM_EINVAL; }
+  MLSIM_CUDA_CHECK(cudaSetDevice(pl->cfg.device));
   MLSIM_PLAIN_ONLY(pl);
   MLSIM_REQUIRE(which >= 0 && which <= 7 && iters >= 1 && warmup >= 0, "bad arguments");
   if (which == 7 && !pl->cluster_projection) { set_error("cluster projection not available for this grid"); return MLSIM_EINVAL; }

@@ -25,6 +25,8 @@ int launch_normalize_speed(float* u, float* v, unsigned int* scratch, int batch,
                            cudaStream_t st);
 int launch_halo_push(const float* uv, float* up_uv, float* dn_uv, int images, int ext_rows, int ny, int nxl, int halo,
                      int lo, int hi, cudaStream_t st);
+int launch_finite_check(const float* u, const float* v, size_t n, unsigned long long step, unsigned long long* flag,
+                        cudaStream_t st);
 int launch_downsample_staggered(const float* u, const float* v, float* cu, float* cv, int batch, int nx, int ny, int f,
                                 cudaStream_t st);
 }  // namespace mlsim

@@ -44,7 +44,7 @@ def downsample_fields(u: torch.Tensor, v: torch.Tensor, factor: int) -> Tuple[to
     lib = _lib.load()
     with torch.cuda.device(u.device):
         _lib.check(lib.mlsim_downsample_staggered(u.data_ptr(), v.data_ptr(), cu.data_ptr(), cv.data_ptr(), b, nx, ny,
-                                                  int(factor), torch.cuda.current_stream().cuda_stream))
+                                                  int(factor), torch.cuda.current_stream(u.device).cuda_stream))
     return cu, cv
 
 
@@ -80,6 +80,7 @@ class PairGenerator:
         self.delta_t = stable_time_step(dx=min(self.coarse_grid.step), max_velocity=max_velocity,
                                         max_courant_number=cfl_safety_factor, viscosity=viscosity)     # :142-147
         self.inner_step = round(self.delta_t / self.dt)                                                 # :150
+        self.time_between_samples = float(time_between_samples)
         self.steps_between = round(time_between_samples / self.dt)                                      # :205
         common = dict(batch=batch_size, viscosity=viscosity, density=density, drag=drag,
                       forcing_wavenumber=int(peak_wavenumber), device=device)
@@ -147,7 +148,9 @@ def generate(path: str, sample_size: int = 1, pairs_per_sample: Optional[int] = 
             gen.reset(seed + i)
             n_pairs = pairs_per_sample
             if n_pairs is None:
-                n_pairs = round((simulation_time / 1.0) / gen.dt) // gen.inner_step                  # :203
+                # reference :203 -- round(((simulation_time/time_between_samples)/dt)//inner_step): floor-divide the
+                # float first, then round
+                n_pairs = round(((simulation_time / gen.time_between_samples) / gen.dt) // gen.inner_step)
             for _ in range(n_pairs):
                 (uf, vf), (uc, vc) = gen.next_pair()
                 dataset = pairs_to_dataset([((uf.clone(), vf.clone()), (uc, vc))])

@@ -9,6 +9,12 @@ class KolmogorovForcing:
                  swap_xy: bool = False, **_ignored):
         if swap_xy:
             raise NotImplementedError("swap_xy forcing is not on the hot path")
+        # The reference builds it with diam = 2*pi = the domain length (src/inference.py:61,81-82); only there do the
+        # candidate readings of the third-party formula ("sin(k y)" / "sin(2 pi k y / diam)") coincide, so any other
+        # diam is refused instead of guessed (the C ABI refuses ly != 2*pi with forcing for the same reason).
+        import math
+        if diam is not None and abs(float(diam) - 2 * math.pi) > 1e-9:
+            raise NotImplementedError("KolmogorovForcing is on the hot path for diam = 2*pi only")
         self.diam = diam
         self.wave_number = int(wave_number)
         self.grid = grid

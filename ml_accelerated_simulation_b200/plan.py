@@ -38,6 +38,9 @@ class PlanConfig:
     device: int = 0
     slab_rank: int = 0                   # slab decomposition along x (see slab.py); slab_world == 0: plain plan
     slab_world: int = 0
+    solver_blocks: int = 0               # execution tuning, 0 = measured default (see include/mlsim.h)
+    host_blocks: int = 0
+    cluster_projection: bool = False
 
     def resolved_dt(self) -> float:
         if self.dt is not None:
@@ -60,7 +63,8 @@ class Plan:
         self.dt = cfg.resolved_dt()
         c = _lib.MlsimConfig(cfg.nx, cfg.ny, cfg.batch, cfg.lx, cfg.ly, self.dt, cfg.viscosity, cfg.density,
                              cfg.drag, cfg.forcing_wavenumber, cfg.forcing_scale, ADVECTION[cfg.advection],
-                             cfg.lw_dt_scale, cfg.device, cfg.slab_rank, cfg.slab_world)
+                             cfg.lw_dt_scale, cfg.device, cfg.slab_rank, cfg.slab_world, cfg.solver_blocks,
+                             cfg.host_blocks, int(cfg.cluster_projection))
         h = C.c_void_p()
         _lib.check(self._lib.mlsim_plan_create(C.byref(c), C.byref(h)))
         self._h = h
@@ -91,9 +95,9 @@ class Plan:
     def new_field(self) -> torch.Tensor:
         return torch.empty(self.shape, dtype=torch.float32, device=self.device)
 
-    @staticmethod
-    def _stream() -> int:
-        return torch.cuda.current_stream().cuda_stream
+    def _stream(self) -> int:
+        # the current stream of the PLAN's device (not of whatever device happens to be current)
+        return torch.cuda.current_stream(self.device).cuda_stream
 
     # ------------------------------------------------------------------ correction network
     def set_cnn(self, layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], shortcuts=None, final_relu: bool = False):
@@ -129,6 +133,8 @@ class Plan:
         self._field(u, "u"); self._field(v, "v")
         if p is not None:
             self._field(p, "p")
+        if apply_cnn and self.has_cnn and self.cnn_out_channels != 2:
+            raise ValueError(f"v += model(v) needs a 2-channel network output, this one has {self.cnn_out_channels}")
         _lib.check(self._lib.mlsim_step(self._h, u.data_ptr(), v.data_ptr(), _ptr(p), nsteps, int(apply_cnn),
                                         float(input_scale), self._stream()))
 
@@ -189,6 +195,17 @@ class Plan:
     def cnn_correct(self, u, v, input_scale: float = 1.0):
         self._field(u, "u"); self._field(v, "v")
         _lib.check(self._lib.mlsim_cnn_correct(self._h, u.data_ptr(), v.data_ptr(), float(input_scale), self._stream()))
+
+    # ------------------------------------------------------------------ divergence guard
+    def finite_check_enable(self, every: int) -> None:
+        """Scan (u, v) for non-finite values after every `every`-th step on the device (0: off); no sync on the step path."""
+        _lib.check(self._lib.mlsim_finite_check_enable(self._h, int(every)))
+
+    def finite_check_read(self):
+        """(first_bad_step or -1, steps_issued) as published by the device so far; non-blocking."""
+        bad, done = C.c_int64(-1), C.c_int64(0)
+        _lib.check(self._lib.mlsim_finite_check_read(self._h, C.byref(bad), C.byref(done)))
+        return int(bad.value), int(done.value)
 
     # ------------------------------------------------------------------ introspection
     def launches_per_step(self, apply_cnn: bool) -> int:

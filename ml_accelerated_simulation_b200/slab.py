@@ -255,9 +255,8 @@ class CudaSlabBackend:
     def new_pressure(self) -> torch.Tensor:
         return torch.zeros((self.geom.batch, self.geom.nxl, self.geom.ny), dtype=torch.float32, device=self.device)
 
-    @staticmethod
-    def _st() -> int:
-        return torch.cuda.current_stream().cuda_stream
+    def _st(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
 
     @staticmethod
     def _p(t):

@@ -44,7 +44,7 @@ def test_plan_create_fails_loudly_without_a_gpu(built_lib):
         pytest.skip("GPU present")
     from ml_accelerated_simulation_b200 import _lib
     lib = _lib.load()
-    cfg = _lib.MlsimConfig(64, 64, 1, 6.28, 6.28, 1e-3, 1e-3, 1.0, 0.1, 4, 1.0, 0, 1.0, 0)
+    cfg = _lib.MlsimConfig(64, 64, 1, 2 * 3.141592653589793, 2 * 3.141592653589793, 1e-3, 1e-3, 1.0, 0.1, 4, 1.0, 0, 1.0, 0)
     h = C.c_void_p()
     rc = lib.mlsim_plan_create(C.byref(cfg), C.byref(h))
     assert rc != 0 and not h.value

@@ -324,6 +324,95 @@ def test_argument_errors_are_loud(mlsim):
         plan.step(good, good.clone(), apply_cnn=True)        # no network attached
     with pytest.raises(MlsimError):
         mlsim.Plan(mlsim.PlanConfig(nx=96, ny=64))
+    with pytest.raises(MlsimError):
+        mlsim.Plan(mlsim.PlanConfig(nx=64, ny=64, solver_blocks=9))
+    with pytest.raises(MlsimError):
+        mlsim.Plan(mlsim.PlanConfig(nx=64, ny=128, cluster_projection=True))      # square 64/128/256 only
+    with pytest.raises(MlsimError):                                                # forcing on a domain other than 2*pi: refused, not guessed
+        mlsim.Plan(mlsim.PlanConfig(nx=64, ny=64, lx=1.0, ly=1.0))
+    mlsim.Plan(mlsim.PlanConfig(nx=64, ny=64, lx=1.0, ly=1.0, forcing_scale=0.0)).close()
+    from ml_accelerated_simulation_b200.forcings import KolmogorovForcing
+    with pytest.raises(NotImplementedError):
+        KolmogorovForcing(diam=1.0, wave_number=4)
+    plan.close()
+
+
+def test_correction_add_needs_two_output_channels(mlsim):
+    """reference `v += model(v)` raises on a shape mismatch; so must the fused path (a 3-channel net used to be
+    accepted and its third channel silently dropped)."""
+    from ml_accelerated_simulation_b200._lib import MlsimError
+    plan = mlsim.Plan(mlsim.PlanConfig(nx=64, ny=64, batch=1))
+    g = torch.Generator().manual_seed(0)
+    layers = [(torch.randn(8, 2, 3, 3, generator=g) * 0.1, torch.zeros(8)), (torch.randn(3, 8, 3, 3, generator=g) * 0.1, torch.zeros(3))]
+    plan.set_cnn(layers)
+    u = plan.new_field().zero_()
+    v = plan.new_field().zero_()
+    assert plan.cnn_forward(u, v).shape == (1, 3, 64, 64)           # the forward itself is fine
+    with pytest.raises(ValueError):
+        plan.step(u, v, apply_cnn=True)
+    lib = plan._lib
+    assert lib.mlsim_step(plan._h, u.data_ptr(), v.data_ptr(), None, 1, 1, 1.0, None) == -1
+    assert b"2-channel" in lib.mlsim_last_error()
+    hu, hv = u.cpu(), v.cpu()
+    assert lib.mlsim_rollout_host(plan._h, hu.data_ptr(), hv.data_ptr(), None, 1, 1, 1.0) == -1
+    with pytest.raises(MlsimError):
+        plan.cnn_correct(u, v)
+    plan.close()
+
+
+@pytest.mark.parametrize("nx,batch", [(64, 6), (256, 5)])
+def test_execution_tuning_does_not_change_results(mlsim, mlacfd, nx, batch):
+    """mlsim_config.solver_blocks / host_blocks only change how launches overlap (bit-identical results);
+    cluster_projection is a different kernel for the same projection (fp32 round-off)."""
+    from ml_accelerated_simulation_b200 import models
+    cfgj, sd = mlacfd
+    model = models.buildModel(cfgj)
+    model.load_state_dict(sd)
+    cfg = S.SolverConfig(nx=nx, ny=nx)
+    u64, v64 = S.filtered_velocity_field(cfg, batch, seed=5, iterations=4)
+    ref = None
+    for kw in ({}, {"solver_blocks": 1}, {"solver_blocks": 3, "host_blocks": 1}, {"solver_blocks": 8, "host_blocks": 4}):
+        plan = mlsim.Plan(mlsim.PlanConfig(nx=nx, ny=nx, batch=batch, **kw))
+        model.attach(plan)
+        u, v = u64.float().to(DEV), v64.float().to(DEV)
+        plan.step(u, v, nsteps=3, apply_cnn=True)
+        hu, hv = u64.float().clone(), v64.float().clone()
+        plan.rollout_host(hu, hv, 3, apply_cnn=True)
+        assert torch.equal(hu, u.cpu()) and torch.equal(hv, v.cpu())
+        if ref is None:
+            ref = (u.clone(), v.clone())
+        else:
+            assert torch.equal(u, ref[0]) and torch.equal(v, ref[1]), kw
+        plan.close()
+    plan = mlsim.Plan(mlsim.PlanConfig(nx=nx, ny=nx, batch=batch, cluster_projection=True))
+    u, v = u64.float().to(DEV), v64.float().to(DEV)
+    plan.step(u, v, nsteps=3)
+    ou, ov, _ = OC.rollout(u64, v64, cfg, 3)
+    qu, qv, _ = OC.rollout(u64.float(), v64.float(), cfg, 3)
+    assert rel(u, ou) <= 4 * rel(qu, ou) + 2e-7 and rel(v, ov) <= 4 * rel(qv, ov) + 2e-7
+    plan.close()
+
+
+def test_device_side_finite_guard(mlsim):
+    """SURVEY section 5 / test/sim_test.py:82-87: the isnan test of the reference loop, on the device, without a sync."""
+    plan = mlsim.Plan(mlsim.PlanConfig(nx=64, ny=64, batch=2))
+    cfg = S.SolverConfig(nx=64, ny=64)
+    u64, v64 = S.filtered_velocity_field(cfg, 2, seed=1, iterations=4)
+    u, v = u64.float().to(DEV), v64.float().to(DEV)
+    plan.finite_check_enable(2)
+    plan.step(u, v, nsteps=6)
+    torch.cuda.synchronize()
+    assert plan.finite_check_read() == (-1, 6)
+    v[1, 3, 5] = float("inf")                   # poisons trajectory 1 (NaN after the first stage)
+    plan.step(u, v, nsteps=5)
+    torch.cuda.synchronize()
+    bad, done = plan.finite_check_read()
+    assert done == 11 and bad == 8              # first CHECKED step after the poison (checks at 8, 10)
+    assert torch.isfinite(u[0]).all() and not torch.isfinite(u[1]).all()
+    plan.finite_check_enable(0)
+    plan.step(u, v, nsteps=1)
+    torch.cuda.synchronize()
+    assert plan.finite_check_read() == (-1, 0)
     plan.close()
 
 

@@ -93,3 +93,33 @@ def test_initial_condition_contract():
     speed = torch.sqrt(u * u + v * v).amax(dim=(-2, -1))
     assert torch.allclose(speed, torch.full_like(speed, 7.0), rtol=1e-12)
     assert S.divergence(u, v, cfg).abs().max().item() < 1e-11
+
+
+def test_matches_torch_cfd():
+    """Consumes tests/golden/torchcfd_golden.safetensors when tests/golden/make_golden_torchcfd.py could produce it
+    (it needs the real torch_cfd package; see DESIGN.md section 2 for the dated outcome of the attempt).  Until then the
+    solver oracle is PARITY UNPINNED and this test skips -- it must never silently pass."""
+    import os
+    import safetensors.torch as st
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "torchcfd_golden.safetensors")
+    if not os.path.exists(path):
+        pytest.skip("no torch_cfd fixture (package unobtainable: parity unpinned)")
+    g = st.load_file(path)
+    cfg = S.SolverConfig()
+    u0, v0 = g["v0_u"], g["v0_v"]
+    dt = float(g["dt"][0])
+    assert dt == pytest.approx(cfg.dt, rel=1e-15)
+
+    def close(a, b):
+        return ((a - b).norm() / b.norm()).item() <= 1e-12
+    if "F_u" in g:
+        fu, fv = S.explicit_terms(u0, v0, cfg, dt)
+        assert close(fu, g["F_u"]) and close(fv, g["F_v"])
+    if "P_u" in g:
+        pu, pv, pp = S.pressure_projection(u0, v0, cfg)
+        assert close(pu, g["P_u"]) and close(pv, g["P_v"])
+    u, v, p = S.rk4_step(u0, v0, cfg, dt)
+    assert close(u, g["step1_u"]) and close(v, g["step1_v"])
+    for _ in range(9):
+        u, v, p = S.rk4_step(u, v, cfg, dt)
+    assert close(u, g["step10_u"]) and close(v, g["step10_v"])

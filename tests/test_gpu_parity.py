@@ -249,21 +249,23 @@ def test_buildmodel_dropin_and_checkpoint_roundtrip(mlsim, mlacfd, tmp_path):
 
 
 # --------------------------------------------------------------------------------------------- end to end
-@pytest.mark.parametrize("nx,ny,batch,nsteps", [(64, 64, 1, 100), (128, 128, 2, 10)])
-def test_rollout_solver_plus_correction(mlsim, mlacfd, nx, ny, batch, nsteps):
-    """The hot loop of reference src/inference.py:100-102 (BASELINE config 1 at 64^2, 100 steps)."""
+@pytest.mark.parametrize("nx,ny,batch,nsteps,scale", [(64, 64, 1, 100, 1.0), (128, 128, 2, 10, 1.0), (64, 64, 2, 100, 1.0 / 7.0),
+                                                       (128, 256, 1, 10, 1.0 / 7.0)])
+def test_rollout_solver_plus_correction(mlsim, mlacfd, nx, ny, batch, nsteps, scale):
+    """The hot loop of reference src/inference.py:100-102 (BASELINE config 1 at 64^2, 100 steps), with the literal
+    input (scale 1) and with the training contract's input scaling (1/7, src/data/dataloader.py:66-80)."""
     from ml_accelerated_simulation_b200 import models
     from ml_accelerated_simulation_b200.rollout import Rollout
     cfgj, sd = mlacfd
     model = models.buildModel(cfgj)
     model.load_state_dict(sd)
     cfg, u64, v64 = _ic(nx, ny, batch)
-    ro = Rollout(mlsim.PlanConfig(nx=nx, ny=ny, batch=batch), model, input_scale=1.0)
+    ro = Rollout(mlsim.PlanConfig(nx=nx, ny=ny, batch=batch), model, input_scale=scale)
     u, v = u64.float().to(DEV), v64.float().to(DEV)
     ro.step(u, v, nsteps)
-    ou, ov, _ = OC.rollout(u64, v64, cfg, nsteps, cfgj, sd, 1.0)                      # fp64 reference semantics
-    bu, bv, _ = OC.rollout(u64, v64, cfg, nsteps, cfgj, sd, 1.0, round_bf16=True)     # fp64 solver, bf16-storage CNN
-    qu, qv, _ = OC.rollout(u64.float(), v64.float(), cfg, nsteps, cfgj, sd, 1.0)      # plain fp32 evaluation
+    ou, ov, _ = OC.rollout(u64, v64, cfg, nsteps, cfgj, sd, scale)                      # fp64 reference semantics
+    bu, bv, _ = OC.rollout(u64, v64, cfg, nsteps, cfgj, sd, scale, round_bf16=True)     # fp64 solver, bf16-storage CNN
+    qu, qv, _ = OC.rollout(u64.float(), v64.float(), cfg, nsteps, cfgj, sd, scale)      # plain fp32 evaluation
     assert torch.isfinite(u).all()
     # kernels vs the oracle with the SAME storage precision in the CNN: fp32 round-off only
     assert rel(u, bu) <= 4 * rel(qu, ou) + 1e-6
@@ -362,7 +364,8 @@ def test_correction_add_needs_two_output_channels(mlsim):
 
 @pytest.mark.parametrize("nx,batch", [(64, 6), (256, 5)])
 def test_execution_tuning_does_not_change_results(mlsim, mlacfd, nx, batch):
-    """mlsim_config.solver_blocks / host_blocks only change how launches overlap (bit-identical results);
+    """mlsim_config.solver_blocks / host_blocks only change how launches overlap: the solver part is bit-identical,
+    the network to fp32 round-off (the accumulation order of an output row depends on which persistent CTA gets it);
     cluster_projection is a different kernel for the same projection (fp32 round-off)."""
     from ml_accelerated_simulation_b200 import models
     cfgj, sd = mlacfd
@@ -378,11 +381,14 @@ def test_execution_tuning_does_not_change_results(mlsim, mlacfd, nx, batch):
         plan.step(u, v, nsteps=3, apply_cnn=True)
         hu, hv = u64.float().clone(), v64.float().clone()
         plan.rollout_host(hu, hv, 3, apply_cnn=True)
-        assert torch.equal(hu, u.cpu()) and torch.equal(hv, v.cpu())
+        assert rel(hu, u) < 1e-6 and rel(hv, v) < 1e-6
+        su, sv = u64.float().to(DEV), v64.float().to(DEV)
+        plan.step(su, sv, nsteps=3)
         if ref is None:
-            ref = (u.clone(), v.clone())
+            ref = (u.clone(), v.clone(), su.clone(), sv.clone())
         else:
-            assert torch.equal(u, ref[0]) and torch.equal(v, ref[1]), kw
+            assert rel(u, ref[0]) < 1e-6 and rel(v, ref[1]) < 1e-6, kw
+            assert torch.equal(su, ref[2]) and torch.equal(sv, ref[3]), kw
         plan.close()
     plan = mlsim.Plan(mlsim.PlanConfig(nx=nx, ny=nx, batch=batch, cluster_projection=True))
     u, v = u64.float().to(DEV), v64.float().to(DEV)
@@ -572,3 +578,101 @@ def test_spectral_multiply_and_initial_condition(mlsim, nx, ny, batch):
         assert rel(v0[0].data, ou) < 1e-4 and rel(v0[1].data, ov) < 1e-4
         speed = torch.sqrt(v0[0].data ** 2 + v0[1].data ** 2).amax(dim=(-2, -1))
         assert torch.allclose(speed.cpu(), torch.full((batch,), 7.0), atol=1e-4)
+
+
+# --------------------------------------------------------------------------------------------- config 3 full step
+def test_config3_full_step_1024(mlsim, mlacfd):
+    """BASELINE configs[2] grid (1024 x 1024), one trajectory: ONE whole step -- RK4 with four projections, then the
+    seven-layer correction with the fused add -- against the oracle (fp64 solver, bf16-storage CNN)."""
+    from ml_accelerated_simulation_b200 import models
+    cfgj, sd = mlacfd
+    model = models.buildModel(cfgj)
+    model.load_state_dict(sd)
+    cfg = S.SolverConfig(nx=1024, ny=1024)
+    u64, v64 = S.filtered_velocity_field(cfg, 1, seed=3, iterations=2)
+    plan = mlsim.Plan(mlsim.PlanConfig(nx=1024, ny=1024, batch=1))
+    model.attach(plan)
+    u, v = u64.float().to(DEV), v64.float().to(DEV)
+    p = plan.new_field()
+    plan.step(u, v, nsteps=1, apply_cnn=True, p=p)
+    with torch.inference_mode():
+        bu, bv, bp = OC.rollout(u64, v64, cfg, 1, cfgj, sd, 1.0, round_bf16=True)
+        ou, ov, _ = OC.rollout(u64, v64, cfg, 1)
+        qu, qv, _ = OC.rollout(u64.float(), v64.float(), cfg, 1)
+    assert rel(u, bu) <= 4 * rel(qu, ou) + 1e-6, (rel(u, bu), rel(qu, ou))
+    assert rel(v, bv) <= 4 * rel(qv, ov) + 1e-6, (rel(v, bv), rel(qv, ov))
+    assert rel(p, bp) <= 1e-4
+    plan.close()
+
+
+# --------------------------------------------------------------------------------------------- long rollouts: spectra
+def _shell_spectra(u, v, cfg):
+    """Kinetic-energy and enstrophy shell spectra E(k), Z(k), k = 1 .. n/3, of a [batch, n, n] velocity field (fp64).
+    Vorticity by the staggered difference w = d+x v - d+y u (the curl that is natural on the MAC grid)."""
+    u, v = u.double().cpu(), v.double().cpu()
+    n = cfg.nx
+    w = (torch.roll(v, -1, -2) - v) / cfg.hx - (torch.roll(u, -1, -1) - u) / cfg.hy
+    k1 = torch.fft.fftfreq(n, 1.0 / n)
+    kk = torch.sqrt(k1[:, None] ** 2 + k1[None, :] ** 2)
+    shell = torch.round(kk).long().clamp(max=n)
+    uh, vh, wh = (torch.fft.fft2(t) / (n * n) for t in (u, v, w))
+    e = 0.5 * (uh.abs() ** 2 + vh.abs() ** 2).mean(0)
+    z = 0.5 * (wh.abs() ** 2).mean(0)
+    E = torch.zeros(n + 1, dtype=torch.float64).index_add_(0, shell.flatten(), e.flatten())
+    Z = torch.zeros(n + 1, dtype=torch.float64).index_add_(0, shell.flatten(), z.flatten())
+    return E[1:n // 3 + 1], Z[1:n // 3 + 1]
+
+
+def _spectra_report(u, v, ou, ov, cfg):
+    E, Z = _shell_spectra(u, v, cfg)
+    Eo, Zo = _shell_spectra(ou, ov, cfg)
+    lo = slice(0, 16)                                # shells 1..16 carry > 99 % of the energy (forcing at k = 4)
+    return {"dE_total": abs(E.sum() / Eo.sum() - 1).item(), "dZ_total": abs(Z.sum() / Zo.sum() - 1).item(),
+            "dE_low": (E[lo] / Eo[lo] - 1).abs().max().item(), "dZ_low": (Z[lo] / Zo[lo] - 1).abs().max().item(),
+            "dE_all": (torch.log(E / Eo)).abs().max().item(), "dZ_all": (torch.log(Z / Zo)).abs().max().item()}
+
+
+def test_long_rollout_spectra_config2_grid(mlsim):
+    """beyond ~100 steps trajectories of a chaotic flow separate, so a 1000-step rollout on the
+    configs[1] grid (256 x 256, 2 trajectories) is compared through its kinetic-energy and enstrophy shell spectra:
+    kernels (fp32) against the fp32 oracle.  Stated band: totals within 1 %, every shell k <= 16 within 5 %, every shell
+    up to n/3 within a factor e^0.5 (the dissipation range is the most sensitive to the separation of trajectories)."""
+    cfg, u64, v64 = _ic(256, 256, 2, seed=7)
+    plan = mlsim.Plan(mlsim.PlanConfig(nx=256, ny=256, batch=2))
+    u, v = u64.float().to(DEV), v64.float().to(DEV)
+    plan.finite_check_enable(100)
+    plan.step(u, v, nsteps=1000)
+    torch.cuda.synchronize()
+    assert plan.finite_check_read() == (-1, 1000)
+    with torch.inference_mode():
+        ou, ov, _ = OC.rollout(u64.float(), v64.float(), cfg, 1000)
+    r = _spectra_report(u, v, ou, ov, cfg)
+    print("spectra 256^2 x 2, 1000 steps:", r, "trajectory relL2:", rel(u, ou))
+    assert r["dE_total"] < 0.01 and r["dZ_total"] < 0.01, r
+    assert r["dE_low"] < 0.05 and r["dZ_low"] < 0.05, r
+    assert r["dE_all"] < 0.5 and r["dZ_all"] < 0.5, r
+    plan.close()
+
+
+def test_long_rollout_spectra_with_correction(mlsim, mlacfd):
+    """The same comparison with the correction network in the loop (configs[0] grid, 64 x 64, 400 steps): kernels
+    (fp32 solver, bf16-storage CNN) against the plain fp32 oracle.  Same stated band."""
+    from ml_accelerated_simulation_b200 import models
+    cfgj, sd = mlacfd
+    model = models.buildModel(cfgj)
+    model.load_state_dict(sd)
+    cfg, u64, v64 = _ic(64, 64, 1, seed=8)
+    plan = mlsim.Plan(mlsim.PlanConfig(nx=64, ny=64, batch=1))
+    model.attach(plan)
+    u, v = u64.float().to(DEV), v64.float().to(DEV)
+    plan.step(u, v, nsteps=400, apply_cnn=True)
+    sd32 = {k: (t.float() if t.dtype.is_floating_point else t) for k, t in sd.items()}
+    with torch.inference_mode():
+        ou, ov, _ = OC.rollout(u64.float(), v64.float(), cfg, 400, cfgj, sd32, 1.0)
+    r = _spectra_report(u, v, ou, ov, cfg)
+    print("spectra 64^2 + CNN, 400 steps:", r, "trajectory relL2:", rel(u, ou))
+    assert torch.isfinite(u).all()
+    assert r["dE_total"] < 0.01 and r["dZ_total"] < 0.01, r
+    assert r["dE_low"] < 0.05 and r["dZ_low"] < 0.05, r
+    assert r["dE_all"] < 0.5 and r["dZ_all"] < 0.5, r
+    plan.close()

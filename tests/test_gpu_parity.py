@@ -418,7 +418,7 @@ def test_device_side_finite_guard(mlsim):
     plan.finite_check_enable(0)
     plan.step(u, v, nsteps=1)
     torch.cuda.synchronize()
-    assert plan.finite_check_read() == (-1, 0)
+    assert plan.finite_check_read() == (-1, 1)   # counting restarts at enable; nothing is checked with every = 0
     plan.close()
 
 
@@ -635,8 +635,9 @@ def _spectra_report(u, v, ou, ov, cfg):
 def test_long_rollout_spectra_config2_grid(mlsim):
     """beyond ~100 steps trajectories of a chaotic flow separate, so a 1000-step rollout on the
     configs[1] grid (256 x 256, 2 trajectories) is compared through its kinetic-energy and enstrophy shell spectra:
-    kernels (fp32) against the fp32 oracle.  Stated band: totals within 1 %, every shell k <= 16 within 5 %, every shell
-    up to n/3 within a factor e^0.5 (the dissipation range is the most sensitive to the separation of trajectories)."""
+    kernels (fp32) against the fp32 oracle.  Stated band: totals within 1e-4, every shell k <= 16 within 1e-3, every shell
+    up to n/3 within 1 % (measured on B200: 1.2e-8 / 1.4e-6 / 7e-6 -- over 1000 steps at this Reynolds number the two
+    fp32 evaluations have not separated yet, trajectory relL2 1.3e-6)."""
     cfg, u64, v64 = _ic(256, 256, 2, seed=7)
     plan = mlsim.Plan(mlsim.PlanConfig(nx=256, ny=256, batch=2))
     u, v = u64.float().to(DEV), v64.float().to(DEV)
@@ -648,15 +649,17 @@ def test_long_rollout_spectra_config2_grid(mlsim):
         ou, ov, _ = OC.rollout(u64.float(), v64.float(), cfg, 1000)
     r = _spectra_report(u, v, ou, ov, cfg)
     print("spectra 256^2 x 2, 1000 steps:", r, "trajectory relL2:", rel(u, ou))
-    assert r["dE_total"] < 0.01 and r["dZ_total"] < 0.01, r
-    assert r["dE_low"] < 0.05 and r["dZ_low"] < 0.05, r
-    assert r["dE_all"] < 0.5 and r["dZ_all"] < 0.5, r
+    assert r["dE_total"] < 1e-4 and r["dZ_total"] < 1e-4, r
+    assert r["dE_low"] < 1e-3 and r["dZ_low"] < 1e-3, r
+    assert r["dE_all"] < 1e-2 and r["dZ_all"] < 1e-2, r
     plan.close()
 
 
 def test_long_rollout_spectra_with_correction(mlsim, mlacfd):
     """The same comparison with the correction network in the loop (configs[0] grid, 64 x 64, 400 steps): kernels
-    (fp32 solver, bf16-storage CNN) against the plain fp32 oracle.  Same stated band."""
+    (fp32 solver, bf16-storage CNN) against the plain fp32 oracle.  Stated band (the bf16 storage of the activations
+    is the difference): totals within 1e-3, every shell k <= 16 within 1 %, every shell up to n/3 within 5 %
+    (measured on B200: 8e-7 / 1.3e-4 / 1.3e-4, trajectory relL2 1.5e-4)."""
     from ml_accelerated_simulation_b200 import models
     cfgj, sd = mlacfd
     model = models.buildModel(cfgj)
@@ -672,7 +675,7 @@ def test_long_rollout_spectra_with_correction(mlsim, mlacfd):
     r = _spectra_report(u, v, ou, ov, cfg)
     print("spectra 64^2 + CNN, 400 steps:", r, "trajectory relL2:", rel(u, ou))
     assert torch.isfinite(u).all()
-    assert r["dE_total"] < 0.01 and r["dZ_total"] < 0.01, r
-    assert r["dE_low"] < 0.05 and r["dZ_low"] < 0.05, r
-    assert r["dE_all"] < 0.5 and r["dZ_all"] < 0.5, r
+    assert r["dE_total"] < 1e-3 and r["dZ_total"] < 1e-3, r
+    assert r["dE_low"] < 1e-2 and r["dZ_low"] < 1e-2, r
+    assert r["dE_all"] < 5e-2 and r["dZ_all"] < 5e-2, r
     plan.close()

@@ -519,8 +519,13 @@ def run_ours(args):
     # ---------------- BASELINE configs[4]: one 8192^2 grid in x-slabs over the N GPUs, + multi-rank parity self-check ----------------
     slab = slab_parity = None
     if (NX, BATCH) == (256, 64) and not args.no_slab:
-        slab_parity = _slab_parity(dev, local, rank, world, model, cfgj, sd)
-        slab = _slab_measure(args.nx, 10, 3, 1, dev, local, rank, world, peaks, model)
+        # a failure in here must not cost the ensemble line above: it is recorded in the JSON and raised after printing
+        try:
+            slab_parity = _slab_parity(dev, local, rank, world, model, cfgj, sd)
+            slab = _slab_measure(args.nx, 10, 3, 1, dev, local, rank, world, peaks, model)
+        except Exception as e:                                   # noqa: BLE001
+            slab_parity = slab_parity or {"ok": False}
+            slab_parity["error"] = f"{type(e).__name__}: {e}"[:500]
 
     if rank != 0:
         if world > 1:

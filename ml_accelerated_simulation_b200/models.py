@@ -7,8 +7,9 @@ so ``load_state_dict`` / ``safetensors.torch.save_model`` / ``load_model`` inter
 checkpoints.  Parameters are created with the same ``nn.Conv2d`` / ``nn.BatchNorm2d`` constructors in the
 same order, so a given ``torch.manual_seed`` yields the reference's initial weights.
 
-Only the CNN block family on the hot path is implemented: 3x3 / stride 1 / padding 1 / groups 1, ReLU,
-dropout inactive (eval), optional BatchNorm (folded), in_channels = 2, hidden <= 64, out_channels <= 16.
+On the hot path: the CNN block family (3x3 / stride 1 / padding 1 / groups 1, ReLU, dropout inactive (eval), optional
+BatchNorm (folded), in_channels = 2, hidden <= 64, out_channels <= 16) and chains of ResNet basic / bottleneck and
+ResNeXt blocks (1x1 and 3x3, grouped or dense, BatchNorm folded, shortcuts fused into the layer epilogues).
 Anything else raises -- there is no PyTorch fallback.
 """
 from __future__ import annotations
@@ -87,12 +88,37 @@ class CNN(nn.Module):
 
 
 _RESNET_NAMES = ("RESNETBLOCK", "RESNETBASICBLOCK", "RESNETBOTTLENECKBLOCK")     # reference src/models/tools.py:93-95
+_RESNEXT_NAMES = ("RESNEXTBLOCK",)                                                 # reference src/models/tools.py:96-98
+
+
+def _fold_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Eval-mode BatchNorm folded into the preceding convolution, fp64."""
+    w = conv.weight.detach().double().cpu()
+    b = conv.bias.detach().double().cpu()
+    scale = bn.weight.detach().double().cpu() / torch.sqrt(bn.running_var.detach().double().cpu() + bn.eps)
+    return w * scale[:, None, None, None], (b - bn.running_mean.detach().double().cpu()) * scale + bn.bias.detach().double().cpu()
+
+
+def _dense3x3(w: torch.Tensor, groups: int) -> torch.Tensor:
+    """A 1x1 or 3x3, grouped or dense convolution weight [cout, cin/groups, k, k] as the dense 3x3 weight
+    [cout, cin, 3, 3] of the SAME linear map (zero padding of width (k-1)/2, stride 1): a 1x1 kernel sits in the
+    centre tap, a grouped kernel on the block diagonal.  The tensor-core layer kernel is a dense 64-channel 3x3
+    implicit GEMM, so the structural zeros ride along as zero weights -- exact, not an approximation."""
+    cout, cin_g, k, _ = w.shape
+    cin = cin_g * groups
+    out = torch.zeros(cout, cin, 3, 3, dtype=w.dtype)
+    og = cout // groups
+    lo = (3 - k) // 2
+    for g in range(groups):
+        out[g * og:(g + 1) * og, g * cin_g:(g + 1) * cin_g, lo:lo + k, lo:lo + k] = w[g * og:(g + 1) * og]
+    return out
 
 
 class ResNetBlock(nn.Module):
     """Parameter container with the reference ResNetBlock's layout (src/models/ResNet.py:26-39): every layer is
     ``Sequential(Conv2d, BatchNorm2d)``, optional 1x1 ``conv1`` on the block input; forward = ``act(x + y)`` (:41-50).
-    Only the basic-block shape is on the B200 path: 3x3 / stride 1 / padding 1 / groups 1, ReLU, two or more layers."""
+    On the B200 path: basic blocks (3x3, 3x3) and bottleneck blocks (1x1, 3x3, 1x1), stride 1, "same" padding, any
+    group count that divides the channels, ReLU, two or more layers, at most 64 channels."""
 
     def __init__(self, config: dict):
         super().__init__()
@@ -105,12 +131,14 @@ class ResNetBlock(nn.Module):
         self.dropouts = _as_list(config["dropouts"], n, "dropouts")
         if str(config["activation_func"]).lower() != "relu":
             raise NotImplementedError("only ReLU ResNet blocks are on the B200 hot path")
-        if any(k != 3 for k in ks) or any(s != 1 for s in st) or any(p != 1 for p in pd) or any(g != 1 for g in gr):
-            raise NotImplementedError("only 3x3 / stride 1 / padding 1 / groups 1 convolutions are on the B200 hot path")
+        if any(k not in (1, 3) for k in ks) or any(s != 1 for s in st) or any(2 * p != k - 1 for p, k in zip(pd, ks)):
+            raise NotImplementedError("only 1x1 / 3x3, stride 1, same-padding convolutions are on the B200 hot path")
         if n < 2:
             raise NotImplementedError("ResNet blocks on the B200 path need at least two conv layers")
         self.channels = chans
-        self.layers = nn.ModuleList([nn.Sequential(nn.Conv2d(chans[i], chans[i + 1], 3, 1, 1),
+        self.groups = [int(g) for g in gr]
+        self.layers = nn.ModuleList([nn.Sequential(nn.Conv2d(chans[i], chans[i + 1], kernel_size=ks[i], stride=1,
+                                                             padding=pd[i], groups=gr[i]),
                                                    nn.BatchNorm2d(chans[i + 1])) for i in range(n)])
         self.conv1 = nn.Conv2d(chans[0], chans[-1], kernel_size=1) if config.get("1x1_conv", False) else None
         if self.conv1 is None and chans[0] != chans[-1]:
@@ -118,14 +146,36 @@ class ResNetBlock(nn.Module):
 
     def folded_layers(self) -> List[Tuple[torch.Tensor, torch.Tensor]]:
         out = []
-        for layer in self.layers:
-            conv, bn = layer[0], layer[1]
-            w = conv.weight.detach().double().cpu()
-            b = conv.bias.detach().double().cpu()
-            scale = bn.weight.detach().double().cpu() / torch.sqrt(bn.running_var.detach().double().cpu() + bn.eps)
-            out.append(((w * scale[:, None, None, None]).contiguous(),
-                        ((b - bn.running_mean.detach().double().cpu()) * scale + bn.bias.detach().double().cpu()).contiguous()))
+        for layer, g in zip(self.layers, self.groups):
+            w, b = _fold_bn(layer[0], layer[1])
+            out.append((_dense3x3(w, g).contiguous(), b.contiguous()))
         return out
+
+    def shortcut_weights(self):
+        """(w1x1 [cout, cin, 1, 1], bias) of ``conv1`` in fp64, or None for the identity shortcut."""
+        if self.conv1 is None:
+            return None
+        return self.conv1.weight.detach().double().cpu(), self.conv1.bias.detach().double().cpu()
+
+
+class ResNeXtBlock(ResNetBlock):
+    """Reference ``ResNeXtBlock`` (src/models/ResNet.py:54-92): the layer stack of a ResNetBlock built from the same
+    config (:76 -- the reference constructs a whole ResNetBlock, including a ``conv1`` it then discards, and keeps its
+    ``layers``; the construction order is repeated here so a seed yields the reference's initial weights), and a
+    shortcut ``conv1 = Sequential(Conv2d 1x1, BatchNorm2d)`` (:78-80)."""
+
+    def __init__(self, config: dict):
+        super().__init__(config)                        # layers (+ the discarded plain conv1, in the reference's RNG order)
+        chans = self.channels
+        if config["1x1_conv"]:                          # the reference indexes the key directly (KeyError if absent)
+            self.conv1 = nn.Sequential(nn.Conv2d(chans[0], chans[-1], kernel_size=1), nn.BatchNorm2d(chans[-1]))
+        else:
+            self.conv1 = None
+
+    def shortcut_weights(self):
+        if self.conv1 is None:
+            return None
+        return _fold_bn(self.conv1[0], self.conv1[1])
 
 
 class buildModel(nn.Module):
@@ -138,18 +188,21 @@ class buildModel(nn.Module):
         if len(configs) == 1 and names[0] == "CNN":
             self.family = "cnn"
             self.models = nn.ModuleList([CNN(configs[0])])
-        elif configs and all(nm in _RESNET_NAMES for nm in names):
+        elif configs and all(nm in _RESNET_NAMES + _RESNEXT_NAMES for nm in names):
             self.family = "resnet"
             configs = [dict(c) for c in configs]
             for i in range(len(configs) - 1):             # the reference corrects mismatching channel counts (:12-15)
                 configs[i + 1]["structures"] = dict(configs[i + 1]["structures"])
                 configs[i + 1]["structures"]["in_channels"] = configs[i]["structures"]["out_channels"]
-            self.models = nn.ModuleList([ResNetBlock(c) for c in configs])
+            self.models = nn.ModuleList([(ResNeXtBlock if nm in _RESNEXT_NAMES else ResNetBlock)(c)
+                                         for nm, c in zip(names, configs)])
             ch = [b.channels for b in self.models]
             if ch[0][0] != 2 or ch[-1][-1] > 4 or any(c > 64 for b in ch for c in b[1:-1]) or any(b[-1] > 64 for b in ch[:-1]):
                 raise NotImplementedError("supported ResNet shapes: 2 -> (<=64)* -> (<=4) channels")
         else:
-            raise NotImplementedError("the B200 hot path covers buildModel([CNN block]) and chains of ResNet basic blocks")
+            raise NotImplementedError("the B200 hot path covers buildModel([CNN block]) and chains of ResNet (basic / "
+                                      "bottleneck) and ResNeXt blocks with at most 64 channels; the 128-channel "
+                                      "CHANNELAWARE net (smartConv.json) needs a K=128 / N=128 layer kernel that is not built")
         self.models_name = [c["name"] for c in configs]
         self.input_scale = 1.0
         self._plans: Dict[tuple, Tuple[Plan, tuple]] = {}
@@ -171,10 +224,8 @@ class buildModel(nn.Module):
             start = len(layers)
             layers += blk.folded_layers()
             end = len(layers) - 1
-            if blk.conv1 is None:
-                shortcuts[end] = (start - 1, None, None)
-            else:
-                shortcuts[end] = (start - 1, blk.conv1.weight.detach().double().cpu(), blk.conv1.bias.detach().double().cpu())
+            sc = blk.shortcut_weights()
+            shortcuts[end] = (start - 1, None, None) if sc is None else (start - 1, sc[0], sc[1])
         return layers, shortcuts, True
 
     def attach(self, plan) -> None:

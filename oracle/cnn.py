@@ -91,10 +91,12 @@ def cnn_block_forward(x: torch.Tensor, config: dict, sd: Dict[str, torch.Tensor]
 
 
 def resnet_block_forward(x: torch.Tensor, config: dict, sd: Dict[str, torch.Tensor], prefix: str,
-                         round_bf16: bool = False, last_block: bool = False) -> torch.Tensor:
+                         round_bf16: bool = False, last_block: bool = False, resnext: bool = False) -> torch.Tensor:
     """Eval-mode forward of one ``ResNetBlock`` (src/models/ResNet.py:26-50): every layer is Conv2d + BatchNorm2d
-    (:31), activation after every layer but the last (:44-46), optional 1x1 ``conv1`` on the block input (:33-39,
-    :48-49), output ``act(x + y)`` (:50).
+    (:31) with the block's kernel sizes / paddings / groups (basic: 3x3; bottleneck: 1x1, 3x3, 1x1), activation after
+    every layer but the last (:44-46), optional 1x1 ``conv1`` on the block input (:33-39, :48-49), output
+    ``act(x + y)`` (:50).  ``resnext``: the ``ResNeXtBlock`` variant (:54-92) -- the same layer stack (:76), ``conv1``
+    followed by its own BatchNorm (:78-80).
 
     ``round_bf16`` as in cnn_block_forward: conv weights (3x3 and 1x1) and every stored activation -- including each
     block's output, except the network's final output (``last_block``) -- are rounded to bf16; ``x`` must already be
@@ -123,7 +125,15 @@ def resnet_block_forward(x: torch.Tensor, config: dict, sd: Dict[str, torch.Tens
         if i < n - 1:
             y = q(act(y))
     if config.get("1x1_conv", False):
-        x = F.conv2d(x, q(sd[prefix + "conv1.weight"].to(x.dtype)), sd[prefix + "conv1.bias"].to(x.dtype))
+        if resnext:
+            # ResNeXtBlock (src/models/ResNet.py:78-80): conv1 = Sequential(Conv2d 1x1, BatchNorm2d), folded like the layers
+            w1, b1 = sd[prefix + "conv1.0.weight"].to(x.dtype), sd[prefix + "conv1.0.bias"].to(x.dtype)
+            g, beta = sd[prefix + "conv1.1.weight"].to(x.dtype), sd[prefix + "conv1.1.bias"].to(x.dtype)
+            mean, var = sd[prefix + "conv1.1.running_mean"].to(x.dtype), sd[prefix + "conv1.1.running_var"].to(x.dtype)
+            scale = g / torch.sqrt(var + 1e-5)
+            x = F.conv2d(x, q(w1 * scale[:, None, None, None]), (b1 - mean) * scale + beta)
+        else:
+            x = F.conv2d(x, q(sd[prefix + "conv1.weight"].to(x.dtype)), sd[prefix + "conv1.bias"].to(x.dtype))
     out = act(x + y)
     return out if last_block else q(out)
 
@@ -139,8 +149,13 @@ def model_forward(x: torch.Tensor, configs: Sequence[dict], sd: Dict[str, torch.
             if m == 0 and round_bf16:
                 x = x.to(torch.bfloat16).to(x.dtype)
             x = resnet_block_forward(x, config, sd, f"models.{m}.", round_bf16, last_block=(m == len(configs) - 1))
+        elif name == "RESNEXTBLOCK":                                                      # src/models/tools.py:96-98
+            if m == 0 and round_bf16:
+                x = x.to(torch.bfloat16).to(x.dtype)
+            x = resnet_block_forward(x, config, sd, f"models.{m}.", round_bf16, last_block=(m == len(configs) - 1),
+                                     resnext=True)
         else:
-            raise ValueError(f"oracle covers only CNN and ResNet blocks, got {config['name']}")
+            raise ValueError(f"oracle covers only CNN, ResNet and ResNeXt blocks, got {config['name']}")
     return x
 
 

@@ -259,3 +259,36 @@ def test_resnet_rollout_matches_oracle(mlsim, resnet, nx, ny, batch):
     assert torch.isfinite(u).all()
     assert rel(u, eu) <= 4 * rel(qu, eu) + 1e-5 and rel(v, ev) <= 4 * rel(qv, ev) + 1e-5, (rel(u, eu), rel(qu, eu))
     plan.close()
+
+
+@pytest.mark.parametrize("name,tag", [("basicBottleneck1", "bottleneck"), ("basicResNeXt1", "resnext")])
+def test_bottleneck_and_resnext_forward_match_reference_golden(mlsim, golden_dir, name, tag):
+    """8f f4: buildModel(basicBottleneck1.json / basicResNeXt1.json)(x) -- 18 layers, 1x1 and grouped layers carried as
+    dense 3x3 operands of the tcgen05 layer kernel, shortcuts in the epilogues -- against the reference's own fp64
+    forward.  Tolerance protocol of the basic-block test above (self-calibrated against the fp32 evaluation of the same
+    bf16-emulating oracle)."""
+    from ml_accelerated_simulation_b200 import models
+    cfg = json.load(open(os.path.join(golden_dir, f"{name}.json")))
+    sd = st.load_file(os.path.join(golden_dir, f"{tag}_weights.safetensors"))
+    g = st.load_file(os.path.join(golden_dir, f"{tag}_golden.safetensors"))
+    model = models.buildModel(cfg)
+    model.load_state_dict(sd)
+    y = model(g["x"].to(DEV))
+    emu = OC.model_forward(g["x"], cfg, sd, round_bf16=True)
+    sd32 = {k: (t.float() if t.dtype.is_floating_point else t) for k, t in sd.items()}
+    emu32 = OC.model_forward(g["x"].float(), cfg, sd32, round_bf16=True)
+    assert y.shape == g["y"].shape
+    assert rel(y, emu) <= 2 * rel(emu32, emu) + 2e-4, (rel(y, emu), rel(emu32, emu), rel(emu, g["y"]))
+    assert rel(y, g["y"]) <= 2 * rel(emu, g["y"]) + 1e-3
+    # and in the rollout loop (solver step + fused correction add), two steps
+    scfg = S.SolverConfig(nx=64, ny=64)
+    u64, v64 = S.filtered_velocity_field(scfg, 2, seed=21, iterations=4)
+    plan = mlsim.Plan(mlsim.PlanConfig(nx=64, ny=64, batch=2))
+    model.attach(plan)
+    u, v = u64.float().to(DEV), v64.float().to(DEV)
+    plan.step(u, v, nsteps=2, apply_cnn=True, input_scale=1.0 / 7.0)
+    eu, ev, _ = OC.rollout(u64, v64, scfg, 2, cfg, sd, 1.0 / 7.0, round_bf16=True)
+    qu, qv, _ = OC.rollout(u64.float(), v64.float(), scfg, 2, cfg, sd32, 1.0 / 7.0, round_bf16=True)
+    assert torch.isfinite(u).all()
+    assert rel(u, eu) <= 4 * rel(qu, eu) + 1e-5 and rel(v, ev) <= 4 * rel(qv, ev) + 1e-5, (rel(u, eu), rel(qu, eu))
+    plan.close()

@@ -104,3 +104,68 @@ def test_resnet_module_tree_loads_reference_checkpoint(golden_dir, built_lib):
     bn = "models.0.layers.0.1."
     scale = sd[bn + "weight"].double() / torch.sqrt(sd[bn + "running_var"].double() + 1e-5)
     assert torch.allclose(w, sd["models.0.layers.0.0.weight"].double() * scale[:, None, None, None], atol=1e-15)
+
+
+@pytest.mark.parametrize("name,tag", [("basicBottleneck1", "bottleneck"), ("basicResNeXt1", "resnext")])
+def test_bottleneck_and_resnext_oracle_match_reference_golden(golden_dir, name, tag):
+    """bottleneck (1x1 / 3x3 / 1x1, src/models/ResNet.py:26-50) and ResNeXt (groups = 2, conv1 with its
+    own BatchNorm, :54-92) chains: oracle vs the reference's own fp64 forward (tests/golden/make_golden_resnet.py)."""
+    import json
+    import os
+    import safetensors.torch as st
+    from oracle import cnn as OC
+    cfg = json.load(open(os.path.join(golden_dir, f"{name}.json")))
+    sd = st.load_file(os.path.join(golden_dir, f"{tag}_weights.safetensors"))
+    g = st.load_file(os.path.join(golden_dir, f"{tag}_golden.safetensors"))
+    y = OC.model_forward(g["x"], cfg, sd)
+    assert (y - g["y"]).abs().max().item() <= 1e-14
+    yb = OC.model_forward(g["x"], cfg, sd, round_bf16=True)
+    assert 1e-4 < ((yb - g["y"]).norm() / g["y"].norm()).item() < 3e-2
+
+
+@pytest.mark.parametrize("name,tag", [("basicBottleneck1", "bottleneck"), ("basicResNeXt1", "resnext")])
+def test_bottleneck_and_resnext_module_trees(golden_dir, built_lib, name, tag):
+    """models.buildModel has the reference's parameter names, the reference's initial weights under the same seed
+    (construction order), and its dense 3x3 embedding of the 1x1 / grouped layers is the same linear map."""
+    import json
+    import os
+    import safetensors.torch as st
+    import torch
+    import torch.nn.functional as F
+    from ml_accelerated_simulation_b200 import models
+    cfg = json.load(open(os.path.join(golden_dir, f"{name}.json")))
+    sd = st.load_file(os.path.join(golden_dir, f"{tag}_weights.safetensors"))
+    g = st.load_file(os.path.join(golden_dir, f"{tag}_golden.safetensors"))
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        torch.manual_seed(2025)                           # the seed of make_golden_resnet.py
+        fresh = models.buildModel(cfg)
+    finally:
+        torch.set_default_dtype(prev)
+    for k, t in fresh.state_dict().items():
+        if k.endswith(".0.weight") or k.endswith(".0.bias") or k.endswith("conv1.weight"):     # convolutions: untouched by the script
+            assert torch.equal(t.float(), sd[k]), k
+    model = models.buildModel(cfg)
+    missing, unexpected = model.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    layers, shortcuts, final_relu = model.flat_layers()
+    assert len(layers) == 18 and final_relu and sorted(shortcuts) == [2, 5, 8, 11, 14, 17]
+    assert all(tuple(w.shape[2:]) == (3, 3) for w, _ in layers)
+    x, acts = g["x"], {}
+    acts[-1] = x
+    for i, (w, b) in enumerate(layers):
+        y = F.conv2d(acts[i - 1], w, b, padding=1)
+        if i in shortcuts:
+            src, w1, b1 = shortcuts[i]
+            y = y + (acts[src] if w1 is None else F.conv2d(acts[src], w1.reshape(w1.shape[0], -1, 1, 1), b1))
+        acts[i] = torch.relu(y)
+    assert (acts[17] - g["y"]).abs().max().item() <= 1e-13
+
+
+def test_128_channel_net_is_refused_not_emulated(built_lib):
+    import pytest as _pt
+    from ml_accelerated_simulation_b200 import models
+    with _pt.raises(NotImplementedError):
+        models.buildModel([{"name": "CHANNELAWARE", "structures": {"vector_components": [2, 128, 128, 128],
+                                                                     "combined_cnn": [128, 128, 128, 64, 2]}}])

@@ -97,6 +97,14 @@ int64_t mlsim_cnn_pack_host(int32_t kind, int32_t cin, int32_t cout, const doubl
 int  mlsim_step(mlsim_plan* plan, float* u, float* v, float* p_or_null, int32_t nsteps,
                 int32_t apply_cnn, double cnn_input_scale, void* stream);
 
+/* The same loop for callers that hold their state in float64, as the reference scripts do
+ * (torch.set_default_dtype(torch.float64), src/inference.py:60; RKStepper.from_method(..., dtype=torch.float64), :64):
+ * DEVICE pointers to fp64 arrays [batch][nx][ny]; (u_in, v_in) are read, (u_out, v_out) and optionally p_out written
+ * (in == out is allowed).  The arithmetic is the fp32 path of mlsim_step -- one fused conversion pass on the way in
+ * and one on the way out, on plan-owned staging fields. */
+int  mlsim_step_f64(mlsim_plan* plan, const double* u_in, const double* v_in, double* u_out, double* v_out,
+                    double* p_out_or_null, int32_t nsteps, int32_t apply_cnn, double cnn_input_scale, void* stream);
+
 /* Same loop through HOST buffers (pinned or pageable): H2D of (u, v), nsteps, D2H of (u, v) and
  * optionally p, synchronised on return.  This is the end-to-end call bench.py times as `e2e`. */
 int  mlsim_rollout_host(mlsim_plan* plan, float* host_u, float* host_v, float* host_p_or_null,

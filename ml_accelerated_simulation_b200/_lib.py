@@ -45,6 +45,7 @@ _SIGNATURES = {
     "mlsim_cnn_pack_host": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "mlsim_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double,
                              C.c_void_p]),
+    "mlsim_step_f64": (C.c_int, [C.c_void_p] * 6 + [C.c_int32, C.c_int32, C.c_double, C.c_void_p]),
     "mlsim_rollout_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                      C.c_double]),
     "mlsim_explicit_terms": (C.c_int, [C.c_void_p] * 5 + [C.c_void_p]),

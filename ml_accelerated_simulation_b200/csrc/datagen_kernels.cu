@@ -179,4 +179,56 @@ int launch_finite_check(const float* u, const float* v, size_t n, unsigned long 
   return MLSIM_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// fp64 boundary of the drop-in route: the reference scripts hold their state in float64
+// (torch.set_default_dtype(torch.float64), src/inference.py:60); the step arithmetic is fp32.  One fused pass each
+// way instead of separate dtype casts, copies and allocations per field.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_cast_f64_to_f32(const double2* __restrict__ a, const double2* __restrict__ b, float2* __restrict__ oa,
+                  float2* __restrict__ ob, size_t n2) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n2; e += (size_t)gridDim.x * blockDim.x) {
+    const double2 x = __ldg(a + e), y = __ldg(b + e);
+    oa[e] = make_float2((float)x.x, (float)x.y);
+    ob[e] = make_float2((float)y.x, (float)y.y);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_cast_f32_to_f64(const float2* __restrict__ a, const float2* __restrict__ b, const float2* __restrict__ c,
+                  double2* __restrict__ oa, double2* __restrict__ ob, double2* __restrict__ oc, size_t n2) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n2; e += (size_t)gridDim.x * blockDim.x) {
+    const float2 x = a[e], y = b[e];
+    oa[e] = make_double2((double)x.x, (double)x.y);
+    ob[e] = make_double2((double)y.x, (double)y.y);
+    if (oc != nullptr) {
+      const float2 z = c[e];
+      oc[e] = make_double2((double)z.x, (double)z.y);
+    }
+  }
+}
+
+static int cast_grid(size_t n2) {
+  const size_t want = (n2 + 255) / 256;
+  return (int)(want < 148 * 8 ? (want ? want : 1) : 148 * 8);
+}
+int launch_cast_in(const double* a, const double* b, float* oa, float* ob, size_t n, cudaStream_t st) {
+  MLSIM_CUDA_CHECK(launch_pdl(k_cast_f64_to_f32, dim3(cast_grid(n / 2)), dim3(256), 0, st,
+                              reinterpret_cast<const double2*>(a), reinterpret_cast<const double2*>(b),
+                              reinterpret_cast<float2*>(oa), reinterpret_cast<float2*>(ob), n / 2));
+  return MLSIM_OK;
+}
+int launch_cast_out(const float* a, const float* b, const float* c, double* oa, double* ob, double* oc, size_t n,
+                    cudaStream_t st) {
+  MLSIM_CUDA_CHECK(launch_pdl(k_cast_f32_to_f64, dim3(cast_grid(n / 2)), dim3(256), 0, st,
+                              reinterpret_cast<const float2*>(a), reinterpret_cast<const float2*>(b),
+                              reinterpret_cast<const float2*>(c), reinterpret_cast<double2*>(oa),
+                              reinterpret_cast<double2*>(ob), reinterpret_cast<double2*>(oc), n / 2));
+  return MLSIM_OK;
+}
+
 }  // namespace mlsim

@@ -87,6 +87,8 @@ struct mlsim_plan {
   size_t act_bytes = 0;
   int rs = 32;
   bool cluster_projection = false;      // single-kernel projection (thread-block cluster per image)
+  // fp32 staging of the fp64 entry point (mlsim_step_f64)
+  float* d_fu = nullptr; float* d_fv = nullptr; float* d_fp = nullptr;
   // host-rollout staging
   float* d_hu = nullptr; float* d_hv = nullptr; float* d_hp = nullptr;
   cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
@@ -495,7 +497,7 @@ int mlsim_plan_destroy(mlsim_plan* pl) {
   cudaSetDevice(pl->cfg.device);
   cudaDeviceSynchronize();
   void* ptrs[] = {pl->d_forcing, pl->d_inv_eig, pl->d_twx, pl->d_twy, pl->d_w1u, pl->d_w1v, pl->d_w2u, pl->d_w2v,
-                  pl->d_accu, pl->d_accv, pl->d_spec, pl->d_tw_n2, pl->d_split, pl->d_filt, pl->d_smax, pl->d_act[0], pl->d_act[1], pl->d_act[2], pl->d_hu, pl->d_hv, pl->d_hp,
+                  pl->d_accu, pl->d_accv, pl->d_spec, pl->d_tw_n2, pl->d_split, pl->d_filt, pl->d_smax, pl->d_act[0], pl->d_act[1], pl->d_act[2], pl->d_hu, pl->d_hv, pl->d_hp, pl->d_fu, pl->d_fv, pl->d_fp,
                   pl->d_tu, pl->d_tv, pl->d_dbg};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (pl->d_fcflag) cudaFree(pl->d_fcflag);
@@ -726,6 +728,29 @@ int mlsim_step(mlsim_plan* pl, float* u, float* v, float* p_or_null, int32_t nst
   const int rc2 = run_steps(pl, u, v, p_or_null, nsteps, apply_cnn, cnn_input_scale, st, Chunk{0, pl->cfg.batch});
   if (!rc2) pl->fc_steps += nsteps;
   return rc2;
+}
+
+int mlsim_step_f64(mlsim_plan* pl, const double* u_in, const double* v_in, double* u_out, double* v_out, double* p_out,
+                   int32_t nsteps, int32_t apply_cnn, double cnn_input_scale, void* stream) {
+  MLSIM_ENTER(pl);
+  MLSIM_PLAIN_ONLY(pl);
+  int rc;
+  if ((rc = check_field(u_in, "u_in")) || (rc = check_field(v_in, "v_in")) || (rc = check_field(u_out, "u_out")) ||
+      (rc = check_field(v_out, "v_out"))) return rc;
+  if (p_out && (rc = check_field(p_out, "p_out"))) return rc;
+  MLSIM_REQUIRE(nsteps >= 0, "nsteps must be >= 0");
+  if (apply_cnn && !pl->cnn_ready) { set_error("apply_cnn set but the correction network is not finalised"); return MLSIM_ESTATE; }
+  if (apply_cnn) MLSIM_REQUIRE(pl->layers.back().cout == 2, "v += model(v) needs a 2-channel network output (u, v)");
+  const size_t n = pl->field_elems;
+  if (!pl->d_fu) {
+    if ((rc = dev_alloc(pl, &pl->d_fu, n)) || (rc = dev_alloc(pl, &pl->d_fv, n)) || (rc = dev_alloc(pl, &pl->d_fp, n))) return rc;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if ((rc = launch_cast_in(u_in, v_in, pl->d_fu, pl->d_fv, n, st))) return rc;
+  if ((rc = run_steps(pl, pl->d_fu, pl->d_fv, p_out ? pl->d_fp : nullptr, nsteps, apply_cnn, cnn_input_scale, st,
+                      Chunk{0, pl->cfg.batch}))) return rc;
+  pl->fc_steps += nsteps;
+  return launch_cast_out(pl->d_fu, pl->d_fv, pl->d_fp, u_out, v_out, p_out, n, st);
 }
 
 int mlsim_rollout_host(mlsim_plan* pl, float* hu, float* hv, float* hp, int32_t nsteps, int32_t apply_cnn,

@@ -27,6 +27,9 @@ int launch_halo_push(const float* uv, float* up_uv, float* dn_uv, int images, in
                      int lo, int hi, cudaStream_t st);
 int launch_finite_check(const float* u, const float* v, size_t n, unsigned long long step, unsigned long long* flag,
                         cudaStream_t st);
+int launch_cast_in(const double* a, const double* b, float* oa, float* ob, size_t n, cudaStream_t st);
+int launch_cast_out(const float* a, const float* b, const float* c, double* oa, double* ob, double* oc, size_t n,
+                    cudaStream_t st);
 int launch_downsample_staggered(const float* u, const float* v, float* cu, float* cv, int batch, int nx, int ny, int f,
                                 cudaStream_t st);
 }  // namespace mlsim

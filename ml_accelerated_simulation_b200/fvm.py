@@ -88,13 +88,21 @@ class RKStepper:
         squeeze = data.dim() == 2
         ud = u_var.data[None] if squeeze else u_var.data
         vd = v_var.data[None] if squeeze else v_var.data
-        plan = _plan_for(grid, ud, dt, equation)
-        uf = ud.to(torch.float32, copy=True).contiguous()
-        vf = vd.to(torch.float32, copy=True).contiguous()
-        p = plan.new_field()
-        plan.step(uf, vf, nsteps=1, apply_cnn=False, p=p)
-        out_dtype = data.dtype
-        uo, vo, po = uf.to(out_dtype), vf.to(out_dtype), p.to(out_dtype)
+        # one plan per (equation, batch, dt, device), remembered on the equation object: no key building per step
+        cache = equation.__dict__.setdefault("_mlsim_plans", {})
+        ck = (ud.shape[0], float(dt), ud.device.index)
+        plan = cache.get(ck)
+        if plan is None:
+            plan = cache[ck] = _plan_for(grid, ud, dt, equation)
+        if data.dtype == torch.float64:
+            # the reference's dtype: fused fp64 <-> fp32 conversion inside the C ABI (mlsim_step_f64)
+            uo, vo, po = plan.step_f64(ud.contiguous(), vd.contiguous(), nsteps=1, want_p=True)
+        else:
+            uf = ud.to(torch.float32, copy=True).contiguous()
+            vf = vd.to(torch.float32, copy=True).contiguous()
+            p = plan.new_field()
+            plan.step(uf, vf, nsteps=1, apply_cnn=False, p=p)
+            uo, vo, po = uf.to(data.dtype), vf.to(data.dtype), p.to(data.dtype)
         if squeeze:
             uo, vo, po = uo[0], vo[0], po[0]
         vec = GridVariableVector((GridVariable(uo, u_var.offset, grid, u_var.bc),

@@ -63,6 +63,18 @@ class GridVariable:
     def to(self, *args, **kwargs):
         return GridVariable(self.data.to(*args, **kwargs), self.offset, self.grid, self.bc)
 
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        """torch functions applied to a GridVariable act on its array (``torch.linalg.norm(fdm.divergence(v0))``,
+        reference test/sim_test.py:45); the result is a plain tensor."""
+        def unwrap(x):
+            if isinstance(x, GridVariable):
+                return x.data
+            if isinstance(x, (list, tuple)) and not isinstance(x, GridVariableVector):
+                return type(x)(unwrap(y) for y in x)
+            return x
+        return func(*[unwrap(a) for a in args], **{k: unwrap(v) for k, v in (kwargs or {}).items()})
+
 
 class GridVariableVector(tuple):
     """Tuple of GridVariables (the velocity vector)."""

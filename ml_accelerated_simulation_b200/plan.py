@@ -138,6 +138,22 @@ class Plan:
         _lib.check(self._lib.mlsim_step(self._h, u.data_ptr(), v.data_ptr(), _ptr(p), nsteps, int(apply_cnn),
                                         float(input_scale), self._stream()))
 
+    def step_f64(self, u: torch.Tensor, v: torch.Tensor, nsteps: int = 1, apply_cnn: bool = False,
+                 input_scale: float = 1.0, want_p: bool = True, inplace: bool = False):
+        """The same loop for float64 state (what the reference scripts hold): returns (u, v, p) as NEW float64 tensors
+        (or updates u, v in place with ``inplace``); fp32 arithmetic, one fused conversion pass each way."""
+        for t, name in ((u, "u"), (v, "v")):
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == self.shape
+                    and t.device.index == self.cfg.device):
+                raise ValueError(f"{name} must be a contiguous float64 CUDA tensor of shape {self.shape} on cuda:{self.cfg.device}")
+        if apply_cnn and self.has_cnn and self.cnn_out_channels != 2:
+            raise ValueError(f"v += model(v) needs a 2-channel network output, this one has {self.cnn_out_channels}")
+        uo, vo = (u, v) if inplace else (torch.empty_like(u), torch.empty_like(v))
+        p = torch.empty_like(u) if want_p else None
+        _lib.check(self._lib.mlsim_step_f64(self._h, u.data_ptr(), v.data_ptr(), uo.data_ptr(), vo.data_ptr(), _ptr(p),
+                                            nsteps, int(apply_cnn), float(input_scale), self._stream()))
+        return uo, vo, p
+
     def rollout_host(self, hu: torch.Tensor, hv: torch.Tensor, nsteps: int, apply_cnn: bool = False,
                      input_scale: float = 1.0, hp: Optional[torch.Tensor] = None):
         """Same loop through host tensors (H2D, nsteps, D2H inside); in place on hu, hv."""

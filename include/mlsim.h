@@ -54,7 +54,7 @@ typedef struct {
    * independent, so the block structure only changes how launches overlap. */
   int32_t solver_blocks;          /* 1..8: independent batch blocks whose solver steps run on separate streams
                                    * (default: 2 when the correction network follows every step, 4 for bare solver rollouts) */
-  int32_t host_blocks;            /* 1..4: equal batch blocks of the H2D | step | D2H pipeline of mlsim_rollout_host
+  int32_t host_blocks;            /* 1..8: equal batch blocks of the H2D | step | D2H pipeline of mlsim_rollout_host
                                    * (default: sized in whole rounds of the persistent conv grid) */
   int32_t cluster_projection;     /* 1: single-kernel projection (thread-block cluster per image, half spectrum in
                                    * distributed shared memory); plain square 64 / 128 / 256 grids only.  Measured slower
@@ -109,6 +109,10 @@ int  mlsim_step_f64(mlsim_plan* plan, const double* u_in, const double* v_in, do
  * optionally p, synchronised on return.  This is the end-to-end call bench.py times as `e2e`. */
 int  mlsim_rollout_host(mlsim_plan* plan, float* host_u, float* host_v, float* host_p_or_null,
                         int32_t nsteps, int32_t apply_cnn, double cnn_input_scale);
+
+/* Explicit block sizes of the H2D | step | D2H pipeline of mlsim_rollout_host: n <= 8 blocks of trajectories whose sizes
+ * add up to the batch (sizes == NULL or n == 0: back to the automatic choice).  Results do not depend on it. */
+int  mlsim_set_host_blocks(mlsim_plan* plan, const int32_t* sizes, int32_t n);
 
 /* ---- pieces of the step, exposed for parity tests ---- */
 /* F(u,v;dt): NavierStokes2DFVMProjection.explicit_terms */

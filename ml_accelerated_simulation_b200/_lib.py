@@ -48,6 +48,7 @@ _SIGNATURES = {
     "mlsim_step_f64": (C.c_int, [C.c_void_p] * 6 + [C.c_int32, C.c_int32, C.c_double, C.c_void_p]),
     "mlsim_rollout_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                      C.c_double]),
+    "mlsim_set_host_blocks": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32]),
     "mlsim_explicit_terms": (C.c_int, [C.c_void_p] * 5 + [C.c_void_p]),
     "mlsim_project": (C.c_int, [C.c_void_p] * 4 + [C.c_void_p]),
     "mlsim_spectral_multiply": (C.c_int, [C.c_void_p] * 4 + [C.c_void_p]),

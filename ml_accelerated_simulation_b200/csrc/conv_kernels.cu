@@ -207,11 +207,15 @@ k_conv_first(ConvFirstArgs a) {
 // =============================================================================================
 // Mid / last layers: 64 -> NB channels per dx block (NB = 64 mid, 16 last).
 // Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer, warps 2.. = epilogue (mid layers: 8 warps,
-// two per TMEM lane quarter, each draining one 32-column half of the slot; last layer: 4 warps).
+// two per TMEM lane quarter, each draining one 32-column half of the slot; last layer: 4 warps), last warp = gate
+// (accumulator-slot bookkeeping, see below).
 // =============================================================================================
-constexpr int CM_THREADS_MID = 64 + 8 * 32;       // producer + MMA + 8 epilogue warps
-constexpr int CM_THREADS_LAST = 64 + 4 * 32;
-constexpr int CM_STAGES_MID = 6;                 // smem input-row ring depth, mid layers (1 CTA/SM)
+constexpr int CM_THREADS_MID = 64 + 8 * 32 + 32;  // producer + MMA + 8 epilogue warps + gate
+constexpr int CM_THREADS_LAST = 64 + 4 * 32 + 32;
+#ifndef MLSIM_CM_STAGES_MID
+#define MLSIM_CM_STAGES_MID 8
+#endif
+constexpr int CM_STAGES_MID = MLSIM_CM_STAGES_MID;   // smem input-row ring depth, mid layers (1 CTA/SM): 8 x 16.6 KB + 74 KB of weights
 constexpr int CM_STAGES_LAST = 5;                // last layer: 2 CTAs/SM (issue-bound N=48 MMAs), 101.6 KB each
 constexpr int CM_NPX = 130;
 constexpr int CM_PLANE = CM_NPX * 16;            // 2080 B: LBO of the A operand
@@ -257,7 +261,8 @@ k_conv_mid(ConvMidArgs a) {
   constexpr uint32_t TMEM_COLS = (NB * CM_SLOTS < 32) ? 32 : NB * CM_SLOTS;
 
   if (tid == 0) {
-    for (int s = 0; s < CM_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    // full[s]: one arrival from the producer (with the byte count of the row's bulk copies) + one from the gate
+    for (int s = 0; s < CM_STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
     for (int s = 0; s < CM_SLOTS; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EPI_WARPS); }
     mbar_init(wbar, 1);
     fence_mbar_init();
@@ -298,13 +303,10 @@ k_conv_mid(ConvMidArgs a) {
   //  * every slot is zero when a row starts using it (the epilogue re-zeroes after draining): all MMAs accumulate.
   if (warp == 0) {
     // ------------------------------ producer (one thread) ------------------------------
-    // Also owns the "accumulator slot is free" check: input row X is only staged once the slot(s) of the output
-    // row that STARTS accumulating with it (row X+1; and row 0 of the image) have been drained and re-zeroed
-    // (tempty[q] phase u = ring position q ready for its u-th use, phase 0 = initial zero fill).  The MMA warp
-    // then has a single barrier to wait for per input row (full[stage]), keeping its inter-row gap short.
+    // Stages input rows as fast as shared-memory stages are released, up to CM_STAGES rows ahead of the MMA warp
+    // (HBM latency under load is 2-3 rows of tensor time).
     if (lane == 0) {
       uint32_t stage = 0, empty_parity = 1;          // fresh barrier: waiting on parity 1 passes immediately
-      uint32_t qn = 0, ready_par = 0;
       for (int it_ = blockIdx.x; it_ < nitems; it_ += gridDim.x) {
         const int item = a.reverse ? (nitems - 1 - it_) : it_;
         const int yt = item % nyt;
@@ -319,18 +321,42 @@ k_conv_mid(ConvMidArgs a) {
         const uint8_t* src = reinterpret_cast<const uint8_t*>(a.in) +
                              ((((size_t)b * a.nx + xlo) * 8) * plane + (size_t)y0) * 16;
         for (int X = xlo; X <= xhi; ++X) {
-          const int nnew = ((X + 1 <= x1 - 1) ? 1 : 0) + ((X == 0) ? 1 : 0);
-          for (int k = 0; k < nnew; ++k) {
-            mbar_wait(&tempty[qn], (ready_par >> qn) & 1u);
-            ready_par ^= 1u << qn;
-            qn = (qn + 1 == CM_RING) ? 0 : qn + 1;
-          }
           mbar_wait(&empty[stage], empty_parity);
           mbar_arrive_expect_tx(&full[stage], 8 * bytes);
           uint8_t* dst = sStage + stage * CM_STAGE_BYTES;
 #pragma unroll
           for (int c = 0; c < 8; ++c) bulk_g2s(dst + c * CM_PLANE, src + (size_t)c * plane * 16, bytes, &full[stage]);
           src += (size_t)8 * plane * 16;
+          if (++stage == CM_STAGES) { stage = 0; empty_parity ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2 + EPI_WARPS) {
+    // ------------------------------ gate (one thread) ------------------------------
+    // Owns the "accumulator slot is free" check: input row X may only be consumed once the slot(s) of the output row
+    // that STARTS accumulating with it (row X+1; and row 0 of the image) have been drained and re-zeroed (tempty[q]
+    // phase u = ring position q ready for its u-th use, phase 0 = initial zero fill).  It contributes the second
+    // arrival of full[stage], so the MMA warp still has a single barrier to wait for per input row, while the
+    // producer's loads no longer queue behind the epilogue.  (With both checks in the producer thread the loads ran at
+    // most ~4 rows ahead and the MMA warp waited 298 of 1498 clk per row for its input; mlsim_conv_debug.)
+    if (lane == 0) {
+      uint32_t stage = 0, empty_parity = 1;
+      uint32_t qn = 0, ready_par = 0;
+      for (int it_ = blockIdx.x; it_ < nitems; it_ += gridDim.x) {
+        const int item = a.reverse ? (nitems - 1 - it_) : it_;
+        const int strip = (item / nyt) % nstrips;
+        const int x0 = strip * a.rs;
+        const int x1 = min(x0 + a.rs, a.nx);
+        const int xlo = max(x0 - 1, 0), xhi = min(x1, a.nx - 1);
+        for (int X = xlo; X <= xhi; ++X) {
+          const int nnew = ((X + 1 <= x1 - 1) ? 1 : 0) + ((X == 0) ? 1 : 0);
+          for (int k = 0; k < nnew; ++k) {
+            mbar_wait(&tempty[qn], (ready_par >> qn) & 1u);
+            ready_par ^= 1u << qn;
+            qn = (qn + 1 == CM_RING) ? 0 : qn + 1;
+          }
+          mbar_wait(&empty[stage], empty_parity);      // the stage's previous phase is over: this arrival counts for the new one
+          mbar_arrive(&full[stage]);
           if (++stage == CM_STAGES) { stage = 0; empty_parity ^= 1; }
         }
       }

@@ -163,6 +163,14 @@ class Plan:
         _lib.check(self._lib.mlsim_rollout_host(self._h, hu.data_ptr(), hv.data_ptr(), _ptr(hp), nsteps,
                                                 int(apply_cnn), float(input_scale)))
 
+    def set_host_blocks(self, sizes=None) -> None:
+        """Explicit block sizes of rollout_host's H2D | step | D2H pipeline (None: automatic)."""
+        if not sizes:
+            _lib.check(self._lib.mlsim_set_host_blocks(self._h, None, 0))
+        else:
+            arr = (C.c_int32 * len(sizes))(*[int(x) for x in sizes])
+            _lib.check(self._lib.mlsim_set_host_blocks(self._h, arr, len(sizes)))
+
     # ------------------------------------------------------------------ pieces (parity hooks)
     def explicit_terms(self, u, v):
         self._field(u, "u"); self._field(v, "v")

@@ -382,6 +382,13 @@ def test_execution_tuning_does_not_change_results(mlsim, mlacfd, nx, batch):
         hu, hv = u64.float().clone(), v64.float().clone()
         plan.rollout_host(hu, hv, 3, apply_cnn=True)
         assert rel(hu, u) < 1e-6 and rel(hv, v) < 1e-6
+        plan.set_host_blocks([1, batch - 3, 2])              # explicit pipeline blocks (mlsim_set_host_blocks)
+        hu2, hv2 = u64.float().clone(), v64.float().clone()
+        plan.rollout_host(hu2, hv2, 3, apply_cnn=True)
+        assert rel(hu2, u) < 1e-6 and rel(hv2, v) < 1e-6
+        with pytest.raises(Exception):
+            plan.set_host_blocks([1, 1])                     # must add up to the batch
+        plan.set_host_blocks(None)
         su, sv = u64.float().to(DEV), v64.float().to(DEV)
         plan.step(su, sv, nsteps=3)
         if ref is None:

@@ -36,20 +36,46 @@ __device__ __forceinline__ void dft_level(float2 (&a)[R]) {
   for (int b = 0; b < R; b += LEN) {
 #pragma unroll
     for (int k = 0; k < LEN / 2; ++k) {
-      const int ti = k * (16 / LEN);            // twiddle angle 2*pi*ti/16
+      constexpr int UNIT = 32 / LEN;
+      const int ti = k * UNIT;                  // twiddle angle 2*pi*ti/32, ti < 16
       const float2 x = a[b + k + LEN / 2];
       float2 t;
       if (ti == 0) {
         t = x;
-      } else if (ti == 4) {                      // w = SIGN * i
+      } else if (ti == 8) {                      // w = SIGN * i
         t = (SIGN > 0) ? make_float2(-x.y, x.x) : make_float2(x.y, -x.x);
       } else {
-        const float c = (ti == 1) ? 0.92387953251128674f : (ti == 2) ? 0.70710678118654752f
-                      : (ti == 3) ? 0.38268343236508977f : (ti == 5) ? -0.38268343236508977f
-                      : (ti == 6) ? -0.70710678118654752f : -0.92387953251128674f;
-        const float sa = (ti == 1) ? 0.38268343236508977f : (ti == 2) ? 0.70710678118654752f
-                       : (ti == 3) ? 0.92387953251128674f : (ti == 5) ? 0.92387953251128674f
-                       : (ti == 6) ? 0.70710678118654752f : 0.38268343236508977f;
+        // literal ternary chains: after unrolling `ti` is a constant and the chain folds to one immediate
+        const float c = (ti == 1) ? 0.98078528040323043f
+                      : (ti == 2) ? 0.92387953251128674f
+                      : (ti == 3) ? 0.83146961230254524f
+                      : (ti == 4) ? 0.70710678118654757f
+                      : (ti == 5) ? 0.55557023301960229f
+                      : (ti == 6) ? 0.38268343236508984f
+                      : (ti == 7) ? 0.19509032201612833f
+                      : (ti == 9) ? -0.19509032201612819f
+                      : (ti == 10) ? -0.38268343236508973f
+                      : (ti == 11) ? -0.55557023301960196f
+                      : (ti == 12) ? -0.70710678118654746f
+                      : (ti == 13) ? -0.83146961230254535f
+                      : (ti == 14) ? -0.92387953251128674f
+                      : (ti == 15) ? -0.98078528040323043f
+                      : 0.0f;
+        const float sa = (ti == 1) ? 0.19509032201612825f
+                      : (ti == 2) ? 0.38268343236508978f
+                      : (ti == 3) ? 0.55557023301960218f
+                      : (ti == 4) ? 0.70710678118654746f
+                      : (ti == 5) ? 0.83146961230254524f
+                      : (ti == 6) ? 0.92387953251128674f
+                      : (ti == 7) ? 0.98078528040323043f
+                      : (ti == 9) ? 0.98078528040323043f
+                      : (ti == 10) ? 0.92387953251128674f
+                      : (ti == 11) ? 0.83146961230254546f
+                      : (ti == 12) ? 0.70710678118654757f
+                      : (ti == 13) ? 0.55557023301960218f
+                      : (ti == 14) ? 0.38268343236508989f
+                      : (ti == 15) ? 0.19509032201612861f
+                      : 0.0f;
         const float s = (SIGN > 0) ? sa : -sa;
         t = make_float2(x.x * c - x.y * s, x.x * s + x.y * c);
       }
@@ -60,11 +86,11 @@ __device__ __forceinline__ void dft_level(float2 (&a)[R]) {
   }
 }
 
-// Natural-order in, natural-order out DFT of R in {2,4,8,16} points held in registers.
+// Natural-order in, natural-order out DFT of R in {2,4,8,16,32} points held in registers.
 // SIGN = -1 forward, +1 inverse (unnormalised).
 template <int R, int SIGN>
 __device__ __forceinline__ void dft_regs(float2 (&v)[R]) {
-  static_assert(R == 2 || R == 4 || R == 8 || R == 16, "radix");
+  static_assert(R == 2 || R == 4 || R == 8 || R == 16 || R == 32, "radix");
   constexpr int BITS = clog2(R);
   float2 a[R];
 #pragma unroll
@@ -73,6 +99,7 @@ __device__ __forceinline__ void dft_regs(float2 (&v)[R]) {
   if constexpr (R >= 4) dft_level<R, SIGN, 4>(a);
   if constexpr (R >= 8) dft_level<R, SIGN, 8>(a);
   if constexpr (R >= 16) dft_level<R, SIGN, 16>(a);
+  if constexpr (R >= 32) dft_level<R, SIGN, 32>(a);
 #pragma unroll
   for (int i = 0; i < R; ++i) v[i] = a[i];
 }
@@ -133,6 +160,38 @@ __device__ __forceinline__ void stage_smem(float2* buf, int c, int j, bool activ
   __syncthreads();
 }
 
+// The same stage with an explicit number of threads per line (TPL): a stage of radix R has N/R butterflies per line, so
+// each thread runs BPT = ceil((N/R)/TPL) of them -- all loads of the stage before its first store (in-place update).
+// Fewer threads per line means smaller CTAs, hence more CTAs per SM whose load / transform / store phases overlap.
+template <int N, int R, int NS, int SIGN, int Q, int TPL>
+__device__ __forceinline__ void stage_smem_t(float2* buf, int c, int j, const float2* __restrict__ tw) {
+  constexpr int NB = N / R;
+  constexpr int BPT = (NB + TPL - 1) / TPL;
+  constexpr bool FULL = (NB % TPL) == 0;
+  float2 v[BPT][R];
+#pragma unroll
+  for (int b = 0; b < BPT; ++b) {
+    const int jj = j + b * TPL;
+    if (FULL || jj < NB) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[b][r] = buf[fidx<Q>(jj + r * NB, c)];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int b = 0; b < BPT; ++b) {
+    const int jj = j + b * TPL;
+    if (FULL || jj < NB) {
+      stage_twiddle<N, R, NS, SIGN>(v[b], jj, tw);
+      dft_regs<R, SIGN>(v[b]);
+      const int j0 = stage_out_base<R, NS>(jj);
+#pragma unroll
+      for (int q = 0; q < R; ++q) buf[fidx<Q>(j0 + q * NS, c)] = v[b][q];
+    }
+  }
+  __syncthreads();
+}
+
 // Radix plans per transform length (R3 == 1 / R4 == 1 mean fewer stages).  R1*R2*R3*R4 == N.
 template <int N> struct FftPlan;
 template <> struct FftPlan<64>   { static constexpr int R1 = 8,  R2 = 8,  R3 = 1,  R4 = 1; };
@@ -144,6 +203,18 @@ template <> struct FftPlan<2048> { static constexpr int R1 = 8,  R2 = 16, R3 = 1
 template <> struct FftPlan<4096> { static constexpr int R1 = 16, R2 = 16, R3 = 16, R4 = 1; };
 template <> struct FftPlan<8192> { static constexpr int R1 = 8,  R2 = 8,  R3 = 8,  R4 = 16; };
 
+// Radix plan of the column solve (K3).  Measured on B200 at 1024^2 x 16 (scripts/ab_solver.py): radix-32 butterflies
+// (64 data registers, two shared-memory exchanges per direction instead of three) take K3 from 64 to 55 us; the same
+// plan makes the row kernels slower (K4 84 -> 128 us: their I/O phases want many threads per line), and at 512 the
+// (32, 16) plan loses to (8, 8, 8) (60 vs 54 us), so only the 1024-point column transform uses it.
+template <int N> struct FftColPlan : FftPlan<N> {};
+template <> struct FftColPlan<1024> { static constexpr int R1 = 32, R2 = 32, R3 = 1, R4 = 1; };
+template <int N> struct FftColMinRadix {
+  using P = FftColPlan<N>;
+  static constexpr int a = P::R1 < P::R2 ? P::R1 : P::R2;
+  static constexpr int value = (P::R3 > 1 && P::R3 < a) ? P::R3 : a;
+};
+
 template <int N> struct FftMinRadix {
   using P = FftPlan<N>;
   static constexpr int a = P::R1 < P::R2 ? P::R1 : P::R2;
@@ -151,30 +222,31 @@ template <int N> struct FftMinRadix {
   static constexpr int value = (P::R4 > 1 && P::R4 < b) ? P::R4 : b;
 };
 
-// All forward stages (R1, R2, R3, R4) / all inverse stages (reversed radix order) of a Q-line bundle in shared memory.
-template <int N, int Q>
+// All forward stages (R1, R2, R3, R4) / all inverse stages (reversed radix order) of a Q-line bundle in shared memory,
+// TPL threads per line (thread j of line c).
+template <int N, int Q, int TPL>
 __device__ __forceinline__ void fft_lines_forward(float2* buf, int c, int j, const float2* __restrict__ tw) {
   using P = FftPlan<N>;
-  stage_smem<N, P::R1, 1, -1, Q>(buf, c, j, true, tw);
-  stage_smem<N, P::R2, P::R1, -1, Q>(buf, c, j, true, tw);
-  if constexpr (P::R3 > 1) stage_smem<N, P::R3, P::R1 * P::R2, -1, Q>(buf, c, j, true, tw);
-  if constexpr (P::R4 > 1) stage_smem<N, P::R4, P::R1 * P::R2 * P::R3, -1, Q>(buf, c, j, true, tw);
+  stage_smem_t<N, P::R1, 1, -1, Q, TPL>(buf, c, j, tw);
+  stage_smem_t<N, P::R2, P::R1, -1, Q, TPL>(buf, c, j, tw);
+  if constexpr (P::R3 > 1) stage_smem_t<N, P::R3, P::R1 * P::R2, -1, Q, TPL>(buf, c, j, tw);
+  if constexpr (P::R4 > 1) stage_smem_t<N, P::R4, P::R1 * P::R2 * P::R3, -1, Q, TPL>(buf, c, j, tw);
 }
-template <int N, int Q>
+template <int N, int Q, int TPL>
 __device__ __forceinline__ void fft_lines_inverse(float2* buf, int c, int j, const float2* __restrict__ tw) {
   using P = FftPlan<N>;
   if constexpr (P::R4 > 1) {
-    stage_smem<N, P::R4, 1, +1, Q>(buf, c, j, true, tw);
-    stage_smem<N, P::R3, P::R4, +1, Q>(buf, c, j, true, tw);
-    stage_smem<N, P::R2, P::R4 * P::R3, +1, Q>(buf, c, j, true, tw);
-    stage_smem<N, P::R1, P::R4 * P::R3 * P::R2, +1, Q>(buf, c, j, true, tw);
+    stage_smem_t<N, P::R4, 1, +1, Q, TPL>(buf, c, j, tw);
+    stage_smem_t<N, P::R3, P::R4, +1, Q, TPL>(buf, c, j, tw);
+    stage_smem_t<N, P::R2, P::R4 * P::R3, +1, Q, TPL>(buf, c, j, tw);
+    stage_smem_t<N, P::R1, P::R4 * P::R3 * P::R2, +1, Q, TPL>(buf, c, j, tw);
   } else if constexpr (P::R3 > 1) {
-    stage_smem<N, P::R3, 1, +1, Q>(buf, c, j, true, tw);
-    stage_smem<N, P::R2, P::R3, +1, Q>(buf, c, j, true, tw);
-    stage_smem<N, P::R1, P::R3 * P::R2, +1, Q>(buf, c, j, true, tw);
+    stage_smem_t<N, P::R3, 1, +1, Q, TPL>(buf, c, j, tw);
+    stage_smem_t<N, P::R2, P::R3, +1, Q, TPL>(buf, c, j, tw);
+    stage_smem_t<N, P::R1, P::R3 * P::R2, +1, Q, TPL>(buf, c, j, tw);
   } else {
-    stage_smem<N, P::R2, 1, +1, Q>(buf, c, j, true, tw);
-    stage_smem<N, P::R1, P::R2, +1, Q>(buf, c, j, true, tw);
+    stage_smem_t<N, P::R2, 1, +1, Q, TPL>(buf, c, j, tw);
+    stage_smem_t<N, P::R1, P::R2, +1, Q, TPL>(buf, c, j, tw);
   }
 }
 

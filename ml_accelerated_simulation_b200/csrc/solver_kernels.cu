@@ -318,7 +318,30 @@ template <int N> struct RowCfg {
 #define MLSIM_C2048 4
 #endif
   static constexpr int Q = (N <= 256) ? 16 : (N == 512 ? MLSIM_Q512 : (N == 1024 ? MLSIM_Q1024 : (N == 2048 ? MLSIM_Q2048 : (N <= 4096 ? 2 : 1))));
-  static constexpr int THREADS = Q * N / RMIN;
+  // threads per line: N / (smallest radix) runs one butterfly per thread in the narrowest stage; long lines use fewer
+  // threads with two butterflies each (smaller CTAs -> more of them per SM, their phases overlap)
+#ifndef MLSIM_TPLF_1024
+// measured on B200 (scripts/ab_solver.py; us per launch at 1024^2 x 16 / 8192^2 x 1): K2 with 64 instead of 128 threads
+// per 1024-point line 70 -> 54, with 512 instead of 1024 per 8192-point line 437 -> 352; K4 gets SLOWER with fewer
+// threads (84 -> 112, 1039 -> 1196: its gradient phase is pure I/O) and keeps one butterfly per thread; the 2048-point
+// column transform with 128 instead of 256 threads per column takes the 8192^2 x-solve from 637 to 511
+#define MLSIM_TPLF_1024 64
+#define MLSIM_TPLF_2048 128
+#define MLSIM_TPLF_4096 256
+#define MLSIM_TPLF_8192 512
+#define MLSIM_TPLI_1024 128
+#define MLSIM_TPLI_2048 256
+#define MLSIM_TPLI_4096 256
+#define MLSIM_TPLI_8192 1024
+#define MLSIM_TPL_COL_1024 32
+#define MLSIM_TPL_COL_2048 128
+#endif
+  // forward (K2) and inverse (K4) row kernels are tuned separately
+  static constexpr int TPLF = (N == 1024) ? MLSIM_TPLF_1024 : (N == 2048) ? MLSIM_TPLF_2048 : (N == 4096) ? MLSIM_TPLF_4096
+                            : (N == 8192) ? MLSIM_TPLF_8192 : N / RMIN;
+  static constexpr int TPLI = (N == 1024) ? MLSIM_TPLI_1024 : (N == 2048) ? MLSIM_TPLI_2048 : (N == 4096) ? MLSIM_TPLI_4096
+                            : (N == 8192) ? MLSIM_TPLI_8192 : N / RMIN;
+  static constexpr int THREADS_F = Q * TPLF, THREADS_I = Q * TPLI;
   static constexpr size_t SMEM = fft_buf_elems<N, Q>() * sizeof(float2);
 };
 
@@ -357,11 +380,11 @@ struct SpecWalk {
 };
 
 template <int N, bool SLAB>
-__global__ void __launch_bounds__(RowCfg<N>::THREADS)
+__global__ void __launch_bounds__(RowCfg<N>::THREADS_F)
 k_div_rfft(const float* __restrict__ u, const float* __restrict__ v, float2* __restrict__ S, SpecPeers peers,
            const float2* __restrict__ tw, SolverParams p) {
   using C = RowCfg<N>;
-  constexpr int Q = C::Q, NT = C::THREADS;
+  constexpr int Q = C::Q, NT = C::THREADS_F;
   constexpr int TPL = NT / Q;                       // threads per line in the I/O phases (k / y fastest)
   extern __shared__ float4 smem4[];
   float2* buf = reinterpret_cast<float2*>(smem4);
@@ -398,7 +421,7 @@ k_div_rfft(const float* __restrict__ u, const float* __restrict__ v, float2* __r
   __syncthreads();
 
   const int c = threadIdx.x % Q, j = threadIdx.x / Q;
-  fft_lines_forward<N, Q>(buf, c, j, tw);
+  fft_lines_forward<N, Q, C::TPLF>(buf, c, j, tw);
 
   // untangle the two real rows of line ql and store their half spectra
   constexpr int nyc = N / 2 + 1;
@@ -420,12 +443,12 @@ k_div_rfft(const float* __restrict__ u, const float* __restrict__ v, float2* __r
 //     u -= d+x p, v -= d+y p  for the first 2Q-1 rows (the last row is the x-halo of p).
 // ---------------------------------------------------------------------------------------------
 template <int N, bool SLAB>
-__global__ void __launch_bounds__(RowCfg<N>::THREADS)
+__global__ void __launch_bounds__(RowCfg<N>::THREADS_I)
 k_irfft_grad(const float2* __restrict__ S, SpecPeers peers, const float* uin, const float* vin,   // uin may alias uout
              float* uout, float* vout, float* __restrict__ pout,                                    // (in-place update)
              const float2* __restrict__ tw, SolverParams p) {
   using C = RowCfg<N>;
-  constexpr int Q = C::Q, NT = C::THREADS;
+  constexpr int Q = C::Q, NT = C::THREADS_I;
   constexpr int TPL = NT / Q;
   extern __shared__ float4 smem4[];
   float2* buf = reinterpret_cast<float2*>(smem4);
@@ -460,7 +483,7 @@ k_irfft_grad(const float2* __restrict__ S, SpecPeers peers, const float* uin, co
   __syncthreads();
 
   const int c = threadIdx.x % Q, j = threadIdx.x / Q;
-  fft_lines_inverse<N, Q>(buf, c, j, tw);
+  fft_lines_inverse<N, Q, C::TPLI>(buf, c, j, tw);
 
   // Gradient subtraction.  A thread owns a block of 4 consecutive rows and the columns t', t' + TPG, ...: in the
   // line-fastest layout the rows 2q, 2q+1 of one y are the two halves of one float2, so its pressure values are 3 + 2
@@ -527,17 +550,20 @@ k_irfft_grad(const float2* __restrict__ S, SpecPeers peers, const float* uin, co
 // of long / distributed grids runs R0 sub-transforms per image, each with its own slice of the spectrum).
 // ---------------------------------------------------------------------------------------------
 template <int N> struct ColCfg {
-  static constexpr int RMIN = FftMinRadix<N>::value;
+  static constexpr int RMIN = FftColMinRadix<N>::value;
   static constexpr int C = (N <= 256) ? 16 : (N == 512 ? MLSIM_C512 : (N == 1024 ? MLSIM_C1024 : MLSIM_C2048));
-  static constexpr int THREADS = C * N / RMIN;
+  static constexpr int TPL = (N == 1024) ? MLSIM_TPL_COL_1024 : (N == 2048) ? MLSIM_TPL_COL_2048 : N / RMIN;     // threads per column
+  static constexpr int THREADS = C * TPL;
+  // at least two CTAs per SM (their load / transform / store phases overlap): caps the registers of the radix-32 stages
+  static constexpr int MINB = (THREADS * 128 * 2 <= 65536) ? 2 : 1;
   static constexpr size_t SMEM = fft_buf_elems<N, C>() * sizeof(float2);
 };
 
 template <int N>
-__global__ void __launch_bounds__(ColCfg<N>::THREADS)
+__global__ void __launch_bounds__(ColCfg<N>::THREADS, ColCfg<N>::MINB)
 k_col_solve(float2* __restrict__ S, const float* __restrict__ inv_eig, const float2* __restrict__ tw,
             SolverParams p, int eig_images) {
-  using P = FftPlan<N>;
+  using P = FftColPlan<N>;
   using CC = ColCfg<N>;
   constexpr int C = CC::C;
   constexpr int RL = (P::R3 > 1) ? P::R3 : P::R2;        // radix of the last forward stage
@@ -554,61 +580,80 @@ k_col_solve(float2* __restrict__ S, const float* __restrict__ inv_eig, const flo
   float2* base = S + (size_t)blockIdx.y * N * p.nycp + ky;
   const float* __restrict__ eig = inv_eig + (size_t)(blockIdx.y % eig_images) * N * p.nyc;
 
+  constexpr int TPL = CC::TPL;
   // forward stage 1: global -> registers -> smem
   {
     constexpr int R = P::R1;
-    if (j < N / R) {
-      float2 v[R];
+    constexpr int NB = N / R, BPT = (NB + TPL - 1) / TPL;
 #pragma unroll
-      for (int r = 0; r < R; ++r)
-        v[r] = valid ? base[(size_t)(j + r * (N / R)) * p.nycp] : make_float2(0.f, 0.f);
-      dft_regs<R, -1>(v);
+    for (int bq = 0; bq < BPT; ++bq) {
+      const int jj = j + bq * TPL;
+      if (jj < NB) {
+        float2 v[R];
 #pragma unroll
-      for (int q = 0; q < R; ++q) buf[fidx<C>(j * R + q, c)] = v[q];
+        for (int r = 0; r < R; ++r)
+          v[r] = valid ? base[(size_t)(jj + r * NB) * p.nycp] : make_float2(0.f, 0.f);
+        dft_regs<R, -1>(v);
+#pragma unroll
+        for (int q = 0; q < R; ++q) buf[fidx<C>(jj * R + q, c)] = v[q];
+      }
     }
     __syncthreads();
   }
-  if constexpr (P::R3 > 1) stage_smem<N, P::R2, P::R1, -1, C>(buf, c, j, true, tw);
+  if constexpr (P::R3 > 1) stage_smem_t<N, P::R2, P::R1, -1, C, TPL>(buf, c, j, tw);
 
   // last forward stage -> scale -> first inverse stage, all in registers
   {
-    float2 v[RL];
-    const bool on = j < N / RL;
-    if (on) {
+    constexpr int NBL = N / RL, BPT = (NBL + TPL - 1) / TPL;
+    float2 v[BPT][RL];
 #pragma unroll
-      for (int r = 0; r < RL; ++r) v[r] = buf[fidx<C>(j + r * NSL, c)];
+    for (int bq = 0; bq < BPT; ++bq) {
+      const int jj = j + bq * TPL;
+      if (jj < NBL) {
+#pragma unroll
+        for (int r = 0; r < RL; ++r) v[bq][r] = buf[fidx<C>(jj + r * NSL, c)];
+      }
     }
     __syncthreads();
-    if (on) {
-      stage_twiddle<N, RL, NSL, -1>(v, j, tw);
-      dft_regs<RL, -1>(v);                                // X[kx = j + q*NSL]
 #pragma unroll
-      for (int q = 0; q < RL; ++q) {
-        const float s = valid ? __ldg(&eig[(size_t)(j + q * NSL) * p.nyc + ky]) : 0.f;
-        v[q].x *= s;
-        v[q].y *= s;
+    for (int bq = 0; bq < BPT; ++bq) {
+      const int jj = j + bq * TPL;
+      if (jj < NBL) {
+        stage_twiddle<N, RL, NSL, -1>(v[bq], jj, tw);
+        dft_regs<RL, -1>(v[bq]);                            // X[kx = jj + q*NSL]
+#pragma unroll
+        for (int q = 0; q < RL; ++q) {
+          const float sc = valid ? __ldg(&eig[(size_t)(jj + q * NSL) * p.nyc + ky]) : 0.f;
+          v[bq][q].x *= sc;
+          v[bq][q].y *= sc;
+        }
+        dft_regs<RL, +1>(v[bq]);                            // inverse stage 1: Ns = 1, no twiddle
+#pragma unroll
+        for (int q = 0; q < RL; ++q) buf[fidx<C>(jj * RL + q, c)] = v[bq][q];
       }
-      dft_regs<RL, +1>(v);                                // inverse stage 1: Ns = 1, no twiddle
-#pragma unroll
-      for (int q = 0; q < RL; ++q) buf[fidx<C>(j * RL + q, c)] = v[q];
     }
     __syncthreads();
   }
-  if constexpr (P::R3 > 1) stage_smem<N, P::R2, P::R3, +1, C>(buf, c, j, true, tw);
+  if constexpr (P::R3 > 1) stage_smem_t<N, P::R2, P::R3, +1, C, TPL>(buf, c, j, tw);
 
   // last inverse stage: smem -> registers -> global
   {
     constexpr int R = P::R1;
     constexpr int NS = N / R;
-    if (j < N / R) {
-      float2 v[R];
+    constexpr int BPT = (NS + TPL - 1) / TPL;
 #pragma unroll
-      for (int r = 0; r < R; ++r) v[r] = buf[fidx<C>(j + r * (N / R), c)];
-      stage_twiddle<N, R, NS, +1>(v, j, tw);
-      dft_regs<R, +1>(v);
-      if (valid) {
+    for (int bq = 0; bq < BPT; ++bq) {
+      const int jj = j + bq * TPL;
+      if (jj < NS) {
+        float2 v[R];
 #pragma unroll
-        for (int q = 0; q < R; ++q) base[(size_t)(j + q * NS) * p.nycp] = v[q];
+        for (int r = 0; r < R; ++r) v[r] = buf[fidx<C>(jj + r * NS, c)];
+        stage_twiddle<N, R, NS, +1>(v, jj, tw);
+        dft_regs<R, +1>(v);
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < R; ++q) base[(size_t)(jj + q * NS) * p.nycp] = v[q];
+        }
       }
     }
   }
@@ -942,7 +987,7 @@ static int launch_div_rfft_n(const float* u, const float* v, float2* S, const Sp
   using C = RowCfg<N>;
   MLSIM_SET_SMEM_ONCE((k_div_rfft<N, SLAB>), (int)C::SMEM);
   dim3 grid(p.nx / (2 * C::Q), p.batch);
-  MLSIM_CUDA_CHECK(launch_pdl(k_div_rfft<N, SLAB>, grid, dim3(C::THREADS), C::SMEM, st, u, v, S, peers, tw, p));
+  MLSIM_CUDA_CHECK(launch_pdl(k_div_rfft<N, SLAB>, grid, dim3(C::THREADS_F), C::SMEM, st, u, v, S, peers, tw, p));
   return MLSIM_OK;
 }
 
@@ -953,7 +998,7 @@ static int launch_irfft_grad_n(const float2* S, const SpecPeers& peers, const fl
   MLSIM_SET_SMEM_ONCE((k_irfft_grad<N, SLAB>), (int)C::SMEM);
   const int rows = 2 * C::Q - 1;
   dim3 grid((p.nx + rows - 1) / rows, p.batch);
-  MLSIM_CUDA_CHECK(launch_pdl(k_irfft_grad<N, SLAB>, grid, dim3(C::THREADS), C::SMEM, st, S, peers, uin, vin, uout, vout, pout, tw, p));
+  MLSIM_CUDA_CHECK(launch_pdl(k_irfft_grad<N, SLAB>, grid, dim3(C::THREADS_I), C::SMEM, st, S, peers, uin, vin, uout, vout, pout, tw, p));
   return MLSIM_OK;
 }
 

@@ -5,8 +5,8 @@ sys.path.insert(0, ROOT)
 import torch
 from ml_accelerated_simulation_b200 import Plan, PlanConfig, models
 
-nx, ny, batch, cnn = (int(x) for x in (sys.argv[1:5] + ["256", "256", "64", "0"][len(sys.argv) - 1:]))
-plan = Plan(PlanConfig(nx=nx, ny=ny, batch=batch))
+nx, ny, batch, cnn, blocks = (int(x) for x in (sys.argv[1:6] + ["256", "256", "64", "0", "0"][len(sys.argv) - 1:]))
+plan = Plan(PlanConfig(nx=nx, ny=ny, batch=batch, solver_blocks=blocks))
 if cnn:
     cfgj = json.load(open(os.path.join(ROOT, "tests/golden/MLACFD.json")))
     model = models.buildModel(cfgj); model.attach(plan)

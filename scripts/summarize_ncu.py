@@ -90,21 +90,25 @@ def summarize_launches(path, fh):
 
 
 def main():
+    """python scripts/summarize_ncu.py <tag> [launches.csv] [report.ncu-rep ...]  (paths under gpurun_out/)"""
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(OUT, exist_ok=True)
     g = os.path.join(ROOT, "gpurun_out")
+    files = sys.argv[2:]
+    lc = next((os.path.join(g, f) for f in files if f.endswith(".csv")), os.path.join(g, "launches.csv"))
+    reps = [os.path.join(g, f) for f in files if f.endswith(".ncu-rep")] or \
+           [os.path.join(g, f) for f in sorted(os.listdir(g)) if f.endswith(".ncu-rep")]
     with open(os.path.join(OUT, f"{tag}_ncu_summary.txt"), "w") as fh:
-        fh.write("ncu summaries of `python bench.py --steps 2 --warmup 1` (config 2: 256x256, batch 64) on one B200\n"
-                 "(the solver kernels are launched per batch block -- 2 blocks with the CNN, 4 for bare solver steps, on separate\n"
-                 " streams -- so their per-launch figures below are per block of 32 / 16 trajectories; the torch / cuFFT kernels in\n"
-                 " the launch list belong to the initial-condition generator, not to the step)\n\n")
-        lc = os.path.join(g, "launches.csv")
+        fh.write("ncu summaries on one B200.  Launch list: the first launches of `python bench.py --steps 2 --warmup 1 --no-slab`\n"
+                 "(config 2: 256x256, batch 64; set-up, warm-up, the timed steps and the per-class profiling passes).  The solver\n"
+                 "kernels are launched per batch block -- 2 blocks with the CNN, 4 for bare solver steps, on separate streams -- so\n"
+                 "their per-launch figures are per block of 32 / 16 trajectories.  Full captures: scripts/prof_step.py at the\n"
+                 "stated shape (conv kernels: 256 x 256 x 64; solver kernels: 1024 x 1024 x 16, one batch block).\n\n")
         if os.path.exists(lc):
             summarize_launches(lc, fh)
-        for f in sorted(os.listdir(g)):
-            if f.endswith(".ncu-rep"):
-                summarize_report(os.path.join(g, f), fh)
-    print(open(os.path.join(OUT, f"{tag}_ncu_summary.txt")).read()[:6000])
+        for rep in reps:
+            summarize_report(rep, fh)
+    print(open(os.path.join(OUT, f"{tag}_ncu_summary.txt")).read()[:9000])
 
 
 if __name__ == "__main__":

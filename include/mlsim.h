@@ -56,6 +56,8 @@ typedef struct {
                                    * (default: 2 when the correction network follows every step, 4 for bare solver rollouts) */
   int32_t host_blocks;            /* 1..8: equal batch blocks of the H2D | step | D2H pipeline of mlsim_rollout_host
                                    * (default: sized in whole rounds of the persistent conv grid) */
+  int32_t fuse_first_layer;       /* 1: the network's first layer (2 -> 64) is computed inside the first hidden layer's kernel,
+                                   * so its activations never reach HBM; 0: separate first-layer kernel */
   int32_t cluster_projection;     /* 1: single-kernel projection (thread-block cluster per image, half spectrum in
                                    * distributed shared memory); plain square 64 / 128 / 256 grids only.  Measured slower
                                    * than the three-kernel projection at every BASELINE config, hence off by default */
@@ -191,13 +193,18 @@ int  mlsim_launches_per_step(mlsim_plan* plan, int32_t apply_cnn);
 int64_t mlsim_workspace_bytes(mlsim_plan* plan);
 /* time one kernel class in isolation with CUDA events on `stream`: which = 0 explicit terms (stage 2
  * form), 1 div+row FFT, 2 column solve, 3 row iFFT+gradient, 4 first conv, 5 one mid conv layer,
- * 6 last conv + correction add, 7 single-kernel cluster projection (small square grids).  Runs `iters` launches after `warmup`, returns mean ms in *ms_out. */
+ * 6 last conv + correction add, 7 single-kernel cluster projection (small square grids), 8 first conv layer fused into
+ * the first hidden layer.  Runs `iters` launches after `warmup`, returns mean ms in *ms_out. */
 int  mlsim_time_kernel(mlsim_plan* plan, int32_t which, int32_t warmup, int32_t iters, float* ms_out, void* stream);
 
 /* Developer aid: mean per-CTA cycle counters of the last conv kernel run by mlsim_time_kernel(5|6):
  * out8 = {MMA-warp total, waiting for drained accumulators, waiting for staged input rows, issuing,
  * input rows, epilogue-warp total, epilogue waiting for finished accumulators, unused}.  Returns #CTAs. */
 int  mlsim_conv_debug(mlsim_plan* plan, double* out8);
+/* Same for the first-layer group of the fused kernel (mlsim_time_kernel(8)): out8 = {group total, waiting for a released
+ * stage, waiting for its accumulator, draining (TMEM -> ReLU -> bf16 -> stage), building the next A tile (incl. the
+ * row loads), rows, group barriers, unused}. */
+int  mlsim_conv_debug_first(mlsim_plan* plan, double* out8);
 
 /* In-step profiling: bracket every launch of one kernel class (numbering as in mlsim_time_kernel; -1 = off)
  * with CUDA events on the launching stream, for up to max_samples launches; mlsim_profile_read synchronises

@@ -24,7 +24,8 @@ class MlsimConfig(C.Structure):
         ("advection", C.c_int32), ("lw_dt_scale", C.c_double),
         ("device", C.c_int32),
         ("slab_rank", C.c_int32), ("slab_world", C.c_int32),
-        ("solver_blocks", C.c_int32), ("host_blocks", C.c_int32), ("cluster_projection", C.c_int32),
+        ("solver_blocks", C.c_int32), ("host_blocks", C.c_int32), ("fuse_first_layer", C.c_int32),
+        ("cluster_projection", C.c_int32),
     ]
 
 
@@ -72,6 +73,7 @@ _SIGNATURES = {
     "mlsim_workspace_bytes": (C.c_int64, [C.c_void_p]),
     "mlsim_time_kernel": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_void_p]),
     "mlsim_conv_debug": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "mlsim_conv_debug_first": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "mlsim_profile_enable": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "mlsim_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "mlsim_last_error": (C.c_char_p, []),

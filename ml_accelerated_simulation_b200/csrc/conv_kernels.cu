@@ -220,11 +220,21 @@ constexpr int CM_STAGES_LAST = 5;                // last layer: 2 CTAs/SM (issue
 constexpr int CM_NPX = 130;
 constexpr int CM_PLANE = CM_NPX * 16;            // 2080 B: LBO of the A operand
 constexpr int CM_STAGE_BYTES = 8 * CM_PLANE;     // 16640 B
-constexpr int CM_SLOTS = 8;                      // TMEM accumulator slots of NB columns
-constexpr int CM_RING = 6;                       // rows cycle with period 6; slots 6,7 mirror ring positions 0,1
+#ifndef MLSIM_CM_RING
+#define MLSIM_CM_RING 6
+#endif
+constexpr int CM_RING = MLSIM_CM_RING;          // rows cycle with period 6; two more slots mirror ring positions 0, 1
+// Fused first layer: four more warps compute the kernel's input rows (the first layer's output) on the fly; their two
+// 64-column accumulators take the place of two ring slots (ring 4 + 2 mirrors = 384 columns, first layer 384..511).
+constexpr int CM_L0_THREADS = 128;
+constexpr int CM_THREADS_FUSED = CM_THREADS_MID + CM_L0_THREADS;
+constexpr int CM_STAGES_FUSED = 6;
+constexpr int CM_RING_FUSED = 4;
 
-template <int NB> struct ConvMidSmem {
-  static constexpr int CM_STAGES = (NB == 64) ? CM_STAGES_MID : CM_STAGES_LAST;
+template <int NB, bool FIRST = false> struct ConvMidSmem {
+  static constexpr int CM_STAGES = FIRST ? CM_STAGES_FUSED : ((NB == 64) ? CM_STAGES_MID : CM_STAGES_LAST);
+  static constexpr int RING = FIRST ? CM_RING_FUSED : CM_RING;
+  static constexpr int SLOTS = RING + 2;
   static constexpr int LBO_B = 3 * NB * 16;
   static constexpr int WDY = 8 * LBO_B;
   static constexpr int WBYTES = 3 * WDY;
@@ -233,17 +243,282 @@ template <int NB> struct ConvMidSmem {
   static constexpr int EXTRA_BYTES = (NB == 64) ? 64 * 2 * 4 : 16 * 64 * 4;
   static constexpr int IMG_BYTES = EXTRA_OFF + EXTRA_BYTES;           // what the host packs and the CTA bulk-copies
   static constexpr int STAGE_OFF = ((IMG_BYTES + 127) / 128) * 128;
-  static constexpr int BAR_OFF = STAGE_OFF + CM_STAGES * CM_STAGE_BYTES;
-  static constexpr int NBARS = 2 * CM_STAGES + 2 * CM_SLOTS + 1;
+  // fused first layer: two im2col A tiles [4 k-chunks][128 px][8] bf16, the first layer's operand image, and the
+  // im2col rows of the two halo pixels (fp32, double buffered)
+  static constexpr int A0_OFF = STAGE_OFF + CM_STAGES * CM_STAGE_BYTES;
+  static constexpr int W0_OFF = A0_OFF + (FIRST ? 2 * 4 * CF_LBO_A : 0);
+  static constexpr int W0_BYTES = CF_WBYTES + 64 * 4;
+  static constexpr int HIN_OFF = W0_OFF + (FIRST ? W0_BYTES : 0);
+  static constexpr int BAR_OFF = HIN_OFF + (FIRST ? 2 * 2 * 20 * 4 + 64 : 0);
+  static constexpr int NBARS = 2 * CM_STAGES + 2 * SLOTS + 1 + (FIRST ? 4 : 0);
   static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
 };
 
-template <int NB, bool LAST>
-__global__ void __launch_bounds__(LAST ? CM_THREADS_LAST : CM_THREADS_MID, LAST ? 2 : 1)
-k_conv_mid(ConvMidArgs a) {
-  constexpr int EPI_WARPS = LAST ? 4 : 8;
-  using L = ConvMidSmem<NB>;
+// ---------------------------------------------------------------------------------------------------------------
+// Fused first layer.  For every input row X of the hidden layer the first layer's output row X -- relu(conv3x3(state)
+// + bias), 2 -> 64 channels -- is computed on the fly and written, as bf16, into the shared-memory stage in exactly the
+// layout the bulk copies of the unfused kernel produce (plane c8, pixel index p+1, 8 channels), so the hidden layer's
+// MMAs cannot tell the difference.  Pixels outside the image are written as zeros (the hidden layer's zero padding), rows
+// and columns outside it read as zeros (the first layer's zero padding).
+//
+//  * main group (4 warps, thread <-> one pixel of the 128-pixel row tile = its TMEM lane): keeps a 3 x 3 window of
+//    (u, v) around its pixel in registers and marches down the rows (one new row of 6 values per step, requested one row
+//    ahead); im2col row (K = 18 -> 32, bias in two spare K columns, as k_conv_first) -> A tile `buf`; later drains
+//    accumulator `buf`: tcgen05.ld -> ReLU -> bf16 -> stage.  No block-level barriers: every warp fences its own writes
+//    and arrives on the mbarriers itself (a0full[buf]: 4 arrivals; full[stage]: gate + 4 + halo warp).
+//  * the MMA warp issues the two M128 x N64 x K16 MMAs of row f+2 right behind the hidden layer's MMAs of row f, so they
+//    sit at a FIXED place in the tensor queue, one row of tensor time ahead of the row that needs their result, whatever
+//    the depth of that queue.  The group therefore builds A tiles two rows ahead of the row it drains:
+//    iteration r = [drain accumulator r -> stage][build A tile r+2].
+//  * halo warp (warp 0, idle otherwise in this mode): the two halo pixels of the 130-pixel stage row (tile columns -1
+//    and 128) on the CUDA cores: 12 lanes march the 2 x 3 columns x 2 fields down the rows, all 32 lanes then evaluate
+//    4 of the 2 x 64 outputs each from first-layer weights held in registers.
+// ---------------------------------------------------------------------------------------------------------------
+struct FirstRowWalk {                       // the (work item, input row) sequence of one CTA, shared by all roles
+  int it_, X, xhi, y0, b;
+  __device__ __forceinline__ void open(const ConvMidArgs& a, int it, int nyt, int nstrips, int nitems) {
+    const int item = a.reverse ? (nitems - 1 - it) : it;
+    const int yt = item % nyt;
+    const int strip = (item / nyt) % nstrips;
+    b = item / (nyt * nstrips);
+    const int x0 = strip * a.rs;
+    const int x1 = min(x0 + a.rs, a.nx);
+    it_ = it;
+    X = max(x0 - 1, 0);
+    xhi = min(x1, a.nx - 1);
+    y0 = yt * 128;
+  }
+};
+
+template <class L>
+__device__ __forceinline__ void conv_first_group(const ConvMidArgs& a, uint8_t* sStage, uint8_t* sA0, uint64_t* full,
+                                                 uint64_t* empty, uint64_t* l0full, uint64_t* a0full, uint32_t tmem_l0,
+                                                 int warp, int lane, int nyt, int nstrips, int nitems) {
   constexpr int CM_STAGES = L::CM_STAGES;
+  const int q4 = warp & 3;                       // TMEM lane quarter of this warp
+  const int t = q4 * 32 + lane;                  // pixel of the tile = TMEM lane
+
+  // the 4th K chunk (k = 24..31) of both A tiles is zero and never rewritten
+  *reinterpret_cast<uint4*>(sA0 + 0 * 4 * CF_LBO_A + 3 * CF_LBO_A + t * 16) = make_uint4(0u, 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(sA0 + 1 * 4 * CF_LBO_A + 3 * CF_LBO_A + t * 16) = make_uint4(0u, 0u, 0u, 0u);
+
+  struct Row { float u[3], v[3]; };
+  FirstRowWalk cu = {};
+  int py = 0;
+  bool ok[3] = {false, false, false};
+  const float* gu = a.fu; const float* gv = a.fv;
+  Row w0 = {}, w1 = {}, w2 = {}, pend = {};       // rows X-1, X, X+1 (scaled, bf16-exact) and the raw loads of row X+2
+  auto load_row = [&](int X) {
+    Row r;
+    const bool rok = X >= 0 && X < a.nx;
+    const float* pu = gu + (ptrdiff_t)X * a.ny;
+    const float* pv = gv + (ptrdiff_t)X * a.ny;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const bool in = rok && ok[j];
+      r.u[j] = in ? __ldg(pu + py - 1 + j) : 0.0f;
+      r.v[j] = in ? __ldg(pv + py - 1 + j) : 0.0f;
+    }
+    return r;
+  };
+  auto qrow = [&](Row r) {                         // scaled and rounded to bf16 exactly as k_conv_first does
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      r.u[j] = __bfloat162float(__float2bfloat16_rn(r.u[j] * a.fscale));
+      r.v[j] = __bfloat162float(__float2bfloat16_rn(r.v[j] * a.fscale));
+    }
+    return r;
+  };
+  auto open_item = [&](int it) {
+    cu.open(a, it, nyt, nstrips, nitems);
+    py = cu.y0 + t;                                // image column of this thread's pixel
+    ok[0] = py - 1 >= 0 && py - 1 < a.ny; ok[1] = py < a.ny; ok[2] = py + 1 < a.ny;
+    gu = a.fu + (size_t)cu.b * a.img_stride;
+    gv = a.fv + (size_t)cu.b * a.img_stride;
+    w0 = qrow(load_row(cu.X - 1)); w1 = qrow(load_row(cu.X)); w2 = qrow(load_row(cu.X + 1));
+    pend = load_row(cu.X + 2);
+  };
+  auto advance = [&]() -> bool {                   // next input row; false when this CTA's work is exhausted
+    if (cu.X < cu.xhi) {
+      ++cu.X;
+      w0 = w1; w1 = w2; w2 = qrow(pend);
+      pend = load_row(cu.X + 2);
+      return true;
+    }
+    if (cu.it_ + (int)gridDim.x >= nitems) return false;
+    open_item(cu.it_ + (int)gridDim.x);
+    return true;
+  };
+  auto build = [&](int buf) {                      // im2col row of this pixel -> A tile `buf`; k = (i*3 + j)*2 + ch
+    const Row* w[3] = {&w0, &w1, &w2};
+    uint32_t pk[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) pk[i * 3 + j] = pack_bf16(w[i]->u[j], w[i]->v[j]);     // values are bf16-exact
+    uint8_t* A = sA0 + buf * 4 * CF_LBO_A;
+    *reinterpret_cast<uint4*>(A + 0 * CF_LBO_A + t * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(A + 1 * CF_LBO_A + t * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    *reinterpret_cast<uint4*>(A + 2 * CF_LBO_A + t * 16) = make_uint4(pk[8], 0x3f803f80u, 0u, 0u);   // k = 18, 19: constant 1 (bias)
+    fence_proxy_async_smem();                      // generic-proxy writes of the A tile -> visible to the tensor core
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&a0full[buf]);
+  };
+
+  if ((int)blockIdx.x >= nitems) return;
+  uint32_t stage = 0, empty_parity = 1;
+  uint32_t l0par = 0;                              // bit b: parity to wait for on l0full[b]
+  long long g_empty = 0, g_acc = 0, g_drain = 0, g_build = 0, g_rows = 0;
+  const long long g_begin = clock64();
+  int py_even = 0, py_odd = 0;                     // pixel column of the rows whose A tiles are in flight (by row parity)
+  open_item(blockIdx.x);
+  py_even = py;
+  build(0);
+  bool more = advance();
+  if (more) { py_odd = py; build(1); }
+  for (int r = 0;; ++r) {
+    const int buf = r & 1;
+    const bool inside = (buf ? py_odd : py_even) < a.ny;
+    const bool have_next = more;                   // row r+1 exists (its A tile is already built)
+    // ---- the stage must have been released by the hidden layer's MMAs of its previous use ----
+    const long long c0 = clock64();
+    mbar_wait(&empty[stage], empty_parity);
+    uint8_t* dst = sStage + stage * CM_STAGE_BYTES;
+    // ---- accumulator -> ReLU -> bf16 -> stage (pixel index t + 1) ----
+    const long long c1 = clock64();
+    mbar_wait(&l0full[buf], (l0par >> buf) & 1u);
+    l0par ^= 1u << buf;
+    tc_fence_after();
+    const long long c2 = clock64();
+    const uint32_t taddr = tmem_l0 + ((uint32_t)(q4 * 32) << 16) + buf * 64;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      uint32_t rr[32];
+      tmem_ld32(taddr + hf * 32, rr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (inside) {
+          o.x = pack_bf16_relu(__uint_as_float(rr[c * 8 + 0]), __uint_as_float(rr[c * 8 + 1]));
+          o.y = pack_bf16_relu(__uint_as_float(rr[c * 8 + 2]), __uint_as_float(rr[c * 8 + 3]));
+          o.z = pack_bf16_relu(__uint_as_float(rr[c * 8 + 4]), __uint_as_float(rr[c * 8 + 5]));
+          o.w = pack_bf16_relu(__uint_as_float(rr[c * 8 + 6]), __uint_as_float(rr[c * 8 + 7]));
+        }
+        *reinterpret_cast<uint4*>(dst + (hf * 4 + c) * CM_PLANE + (t + 1) * 16) = o;
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();                      // stage writes -> visible to the hidden layer's MMAs
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&full[stage]);
+    const long long c3 = clock64();
+    if (++stage == CM_STAGES) { stage = 0; empty_parity ^= 1; }
+    g_empty += c1 - c0; g_acc += c2 - c1; g_drain += c3 - c2; ++g_rows;
+    if (!have_next) break;
+    // ---- A tile of row r+2 into the buffers row r has just released ----
+    more = advance();
+    if (more) { if (buf) py_odd = py; else py_even = py; build(buf); }
+    g_build += clock64() - c3;
+  }
+  if (a.dbg != nullptr && t == 0) {
+    unsigned long long* d = a.dbg + (size_t)(512 + blockIdx.x) * 8;
+    d[0] = (unsigned long long)(clock64() - g_begin);
+    d[1] = (unsigned long long)g_empty; d[2] = (unsigned long long)g_acc; d[3] = (unsigned long long)g_drain;
+    d[4] = (unsigned long long)g_build; d[5] = (unsigned long long)g_rows; d[6] = 0ull;
+  }
+}
+
+// Halo warp of the fused kernel: stage pixels 0 and 129 (tile columns -1 and 128) of every input row.
+template <class L>
+__device__ __forceinline__ void conv_first_halo(const ConvMidArgs& a, uint8_t* sStage, const uint8_t* sW0, float* sHin,
+                                                uint64_t* full, uint64_t* empty, uint64_t* wbar, int lane, int nyt,
+                                                int nstrips, int nitems) {
+  constexpr int CM_STAGES = L::CM_STAGES;
+  mbar_wait(wbar, 0);                            // the first layer's operand image has landed
+  // outputs of this lane: o = lane + 32*m, m = 0..3  ->  side = o >> 6 (0: column -1, 1: column 128), channel = o & 63.
+  // Weights bf16 -> fp32 (image layout [k >> 3][n][k & 7]), bias = its bf16 hi + lo parts, as the MMA adds them.
+  float wr[4][18], br[4];
+  {
+    const uint16_t* q = reinterpret_cast<const uint16_t*>(sW0);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int ch = (lane + 32 * m) & 63;
+      auto wq = [&](int k) { return __uint_as_float((uint32_t)q[((k >> 3) * 64 + ch) * 8 + (k & 7)] << 16); };
+#pragma unroll
+      for (int k = 0; k < 18; ++k) wr[m][k] = wq(k);
+      br[m] = wq(18) + wq(19);
+    }
+  }
+  // lanes 0..11 each march one (side, column j, field) down the rows: lane = (side*3 + j)*2 + field
+  const int mside = lane / 6, mj = (lane % 6) >> 1, mfield = lane & 1;
+  FirstRowWalk cu = {};
+  const float* g = nullptr;
+  int col = 0;
+  bool colok = false;
+  float x0 = 0.f, x1 = 0.f, x2 = 0.f, pend = 0.f;  // rows X-1, X, X+1 (scaled, bf16-exact), raw load of row X+2
+  auto load = [&](int X) { return (lane < 12 && colok && X >= 0 && X < a.nx) ? __ldg(g + (ptrdiff_t)X * a.ny + col) : 0.0f; };
+  auto quant = [&](float x) { return __bfloat162float(__float2bfloat16_rn(x * a.fscale)); };
+  auto open_item = [&](int it) {
+    cu.open(a, it, nyt, nstrips, nitems);
+    col = (mside == 0 ? cu.y0 - 1 : cu.y0 + 128) - 1 + mj;
+    colok = col >= 0 && col < a.ny;
+    g = (mfield ? a.fv : a.fu) + (size_t)cu.b * a.img_stride;
+    x0 = quant(load(cu.X - 1)); x1 = quant(load(cu.X)); x2 = quant(load(cu.X + 1));
+    pend = load(cu.X + 2);
+  };
+  if ((int)blockIdx.x >= nitems) return;
+  uint32_t stage = 0, empty_parity = 1;
+  open_item(blockIdx.x);
+  while (true) {
+    // im2col rows of the two halo pixels: h[side][k], k = (i*3 + j)*2 + field
+    if (lane < 12) {
+      float* h = sHin + mside * 20 + mj * 2 + mfield;
+      h[0] = x0; h[6] = x1; h[12] = x2;
+    }
+    __syncwarp();
+    float o[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int side = (lane + 32 * m) >> 6;
+      const float* h = sHin + side * 20;
+      float acc = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 18; ++k) acc = fmaf(wr[m][k], h[k], acc);
+      const int hy = side == 0 ? cu.y0 - 1 : cu.y0 + 128;
+      o[m] = (hy >= 0 && hy < a.ny) ? fmaxf(acc + br[m], 0.0f) : 0.0f;
+    }
+    mbar_wait(&empty[stage], empty_parity);      // the stage must have been released by the MMAs of its previous use
+    uint8_t* dst = sStage + stage * CM_STAGE_BYTES;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int oo = lane + 32 * m, side = oo >> 6, ch = oo & 63;
+      reinterpret_cast<__nv_bfloat16*>(dst + (ch >> 3) * CM_PLANE + (side ? 129 : 0) * 16)[ch & 7] = __float2bfloat16_rn(o[m]);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();                                // also: everybody has read sHin before the next row overwrites it
+    if (lane == 0) mbar_arrive(&full[stage]);
+    if (++stage == CM_STAGES) { stage = 0; empty_parity ^= 1; }
+    if (cu.X < cu.xhi) {
+      ++cu.X;
+      x0 = x1; x1 = x2; x2 = quant(pend);
+      pend = load(cu.X + 2);
+    } else {
+      if (cu.it_ + (int)gridDim.x >= nitems) break;
+      open_item(cu.it_ + (int)gridDim.x);
+    }
+  }
+}
+
+template <int NB, bool LAST, bool FIRST = false>
+__global__ void __launch_bounds__(LAST ? CM_THREADS_LAST : (FIRST ? CM_THREADS_FUSED : CM_THREADS_MID), LAST ? 2 : 1)
+k_conv_mid(ConvMidArgs a) {
+  static_assert(!(FIRST && LAST) && (!FIRST || NB == 64), "the fused first layer feeds a hidden layer");
+  constexpr int EPI_WARPS = LAST ? 4 : 8;
+  using L = ConvMidSmem<NB, FIRST>;
+  constexpr int CM_STAGES = L::CM_STAGES;
+  constexpr int RING = L::RING, SLOTS = L::SLOTS;
+  constexpr int GATE_WARP = 2 + EPI_WARPS;          // warps GATE_WARP+1 .. +4: first-layer group (FIRST)
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sW = smem;
   const float* sBias = reinterpret_cast<const float*>(smem + L::BIAS_OFF);
@@ -253,17 +528,27 @@ k_conv_mid(ConvMidArgs a) {
   uint64_t* full = bars;
   uint64_t* empty = bars + CM_STAGES;
   uint64_t* tfull = bars + 2 * CM_STAGES;
-  uint64_t* tempty = tfull + CM_SLOTS;
-  uint64_t* wbar = tempty + CM_SLOTS;
+  uint64_t* tempty = tfull + SLOTS;
+  uint64_t* wbar = tempty + SLOTS;
+  uint64_t* l0full = wbar + 1;                        // FIRST: first-layer accumulator `buf` complete
+  uint64_t* a0full = wbar + 3;                        // FIRST: first-layer A tile `buf` built
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + L::NBARS);
+  uint8_t* sA0 = smem + L::A0_OFF;
+  uint8_t* sW0 = smem + L::W0_OFF;
+  float* sHin = reinterpret_cast<float*>(smem + L::HIN_OFF);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr uint32_t TMEM_COLS = (NB * CM_SLOTS < 32) ? 32 : NB * CM_SLOTS;
+  constexpr uint32_t TMEM_WANT = FIRST ? 512u : (uint32_t)(NB * SLOTS);
+  constexpr uint32_t TMEM_COLS = TMEM_WANT <= 32 ? 32u : TMEM_WANT <= 64 ? 64u : TMEM_WANT <= 128 ? 128u : TMEM_WANT <= 256 ? 256u : 512u;   // power of two
+  constexpr uint32_t L0_COL = NB * SLOTS;             // FIRST: two 64-column first-layer accumulators behind the ring
 
   if (tid == 0) {
-    // full[s]: one arrival from the producer (with the byte count of the row's bulk copies) + one from the gate
-    for (int s = 0; s < CM_STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < CM_SLOTS; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EPI_WARPS); }
+    // full[s]: one arrival from the producer (with the byte count of the row's bulk copies; FIRST: from the first-layer
+    // group once the row is written) + one from the gate
+    // (FIRST: gate + the four warps of the first-layer group + the halo warp)
+    for (int s = 0; s < CM_STAGES; ++s) { mbar_init(&full[s], FIRST ? 6 : 2); mbar_init(&empty[s], 1); }
+    if constexpr (FIRST) { mbar_init(&l0full[0], 1); mbar_init(&l0full[1], 1); mbar_init(&a0full[0], 4); mbar_init(&a0full[1], 4); }
+    for (int s = 0; s < SLOTS; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EPI_WARPS); }
     mbar_init(wbar, 1);
     fence_mbar_init();
   }
@@ -278,7 +563,8 @@ k_conv_mid(ConvMidArgs a) {
   const uint32_t tmem = *tmem_slot;
   // the weight image does not depend on the previous kernel: start its bulk copy before waiting for that kernel
   if (tid == 0) {
-    mbar_arrive_expect_tx(wbar, (uint32_t)L::IMG_BYTES);
+    mbar_arrive_expect_tx(wbar, (uint32_t)L::IMG_BYTES + (FIRST ? (uint32_t)L::W0_BYTES : 0u));
+    if constexpr (FIRST) bulk_g2s(sW0, a.wimg0, (uint32_t)L::W0_BYTES, wbar);
     uint32_t off = 0;
     const uint32_t total = L::IMG_BYTES;
     while (off < total) {                       // weight image + bias, in pieces of at most 32 KB
@@ -304,8 +590,9 @@ k_conv_mid(ConvMidArgs a) {
   if (warp == 0) {
     // ------------------------------ producer (one thread) ------------------------------
     // Stages input rows as fast as shared-memory stages are released, up to CM_STAGES rows ahead of the MMA warp
-    // (HBM latency under load is 2-3 rows of tensor time).
-    if (lane == 0) {
+    // (HBM latency under load is 2-3 rows of tensor time).  FIRST: the first-layer group produces the rows instead.
+    if constexpr (FIRST) conv_first_halo<L>(a, sStage, sW0, sHin, full, empty, wbar, lane, nyt, nstrips, nitems);
+    if (!FIRST && lane == 0) {
       uint32_t stage = 0, empty_parity = 1;          // fresh barrier: waiting on parity 1 passes immediately
       for (int it_ = blockIdx.x; it_ < nitems; it_ += gridDim.x) {
         const int item = a.reverse ? (nitems - 1 - it_) : it_;
@@ -331,7 +618,9 @@ k_conv_mid(ConvMidArgs a) {
         }
       }
     }
-  } else if (warp == 2 + EPI_WARPS) {
+  } else if (FIRST && warp > GATE_WARP) {
+    if constexpr (FIRST) conv_first_group<L>(a, sStage, sA0, full, empty, l0full, a0full, tmem + L0_COL, warp, lane, nyt, nstrips, nitems);
+  } else if (warp == GATE_WARP) {
     // ------------------------------ gate (one thread) ------------------------------
     // Owns the "accumulator slot is free" check: input row X may only be consumed once the slot(s) of the output row
     // that STARTS accumulating with it (row X+1; and row 0 of the image) have been drained and re-zeroed (tempty[q]
@@ -353,7 +642,7 @@ k_conv_mid(ConvMidArgs a) {
           for (int k = 0; k < nnew; ++k) {
             mbar_wait(&tempty[qn], (ready_par >> qn) & 1u);
             ready_par ^= 1u << qn;
-            qn = (qn + 1 == CM_RING) ? 0 : qn + 1;
+            qn = (qn + 1 == RING) ? 0 : qn + 1;
           }
           mbar_wait(&empty[stage], empty_parity);      // the stage's previous phase is over: this arrival counts for the new one
           mbar_arrive(&full[stage]);
@@ -368,14 +657,50 @@ k_conv_mid(ConvMidArgs a) {
       tc_fence_after();
       constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
       constexpr int A_K16_STEP = (2 * CM_PLANE) / 16, B_STEP = (2 * L::LBO_B) / 16;
-      static_assert(CM_RING + 2 == CM_SLOTS, "window q0..q0+2 must fit the slots");
+      static_assert(RING + 2 == SLOTS, "window q0..q0+2 must fit the slots");
       static_assert(8 * L::LBO_B == L::WDY, "B offsets must be uniformly spaced over (dy, k16)");
       const uint64_t db0 = ((uint64_t)DESC_HI << 32) | (uint64_t)((smem_u32(sW) >> 4) | ((uint32_t)(L::LBO_B >> 4) << 16));
       const uint64_t da0 = ((uint64_t)DESC_HI << 32) | (uint64_t)((smem_u32(sStage) >> 4) | ((uint32_t)(CM_PLANE >> 4) << 16));
-      uint32_t stage = 0, full_parity = 0;
-      uint32_t qrow = 0;                                // ring position of output row x0 of the current item
       long long t_full = 0, t_issue = 0, t_rows = 0;
       const long long t_begin = clock64();
+      // FIRST: the first-layer MMAs (A tile `buf` x first-layer weights -> accumulator `buf`) are issued from here, for
+      // row f+2 right behind the hidden layer's MMAs of row f (rows counted over all of this CTA's work items)
+      int l0_total = 0, l0_f = 0;
+      uint32_t a0par = 0;
+      long long t_a0 = 0;
+      const uint64_t l0_da = umma_desc(smem_u32(sA0), CF_LBO_A, 128), l0_db = umma_desc(smem_u32(sW0), CF_LBO_B, 128);
+      auto issue_l0 = [&](int buf) {
+        const long long ta = clock64();
+        mbar_wait(&a0full[buf], (a0par >> buf) & 1u);
+        t_a0 += clock64() - ta;
+        a0par ^= 1u << buf;
+        tc_fence_after();
+        const uint64_t da = l0_da + (uint64_t)(buf * ((4 * CF_LBO_A) >> 4));
+        umma_bf16(tmem + L0_COL + buf * 64, da, l0_db, umma_idesc_bf16(64), 0u);
+        umma_bf16(tmem + L0_COL + buf * 64, da + (uint64_t)((2 * CF_LBO_A) >> 4), l0_db + (uint64_t)((2 * CF_LBO_B) >> 4), umma_idesc_bf16(64), 1u);
+        umma_commit(&l0full[buf]);
+      };
+      if constexpr (FIRST) {
+        for (int it_ = blockIdx.x; it_ < nitems; it_ += gridDim.x) {
+          const int item = a.reverse ? (nitems - 1 - it_) : it_;
+          const int x0 = ((item / nyt) % nstrips) * a.rs;
+          const int x1 = min(x0 + a.rs, a.nx);
+          l0_total += min(x1, a.nx - 1) - max(x0 - 1, 0) + 1;
+        }
+        if (l0_total > 0) issue_l0(0);
+        if (l0_total > 1) issue_l0(1);
+      }
+      // The tensor queue is shallow: every clock this thread spends on anything but issuing, with nothing queued, is a
+      // clock of idle tensor pipe (measured, scripts/umma_mix_bench.cu: tcgen05.commit 44 clk, mbarrier.try_wait 187 clk
+      // even on a complete phase -- hence the test_wait fast path of mbar_wait).  The commits of the PREVIOUS row
+      // therefore go behind this row's first four MMAs (its barriers fire four MMAs, ~0.4 us, later than strictly
+      // necessary), and in FIRST mode the first-layer MMAs of row f+2 are issued in the middle of row f.
+      // (Also tried: the next row's bookkeeping and a non-blocking test of its full barrier between the second and third
+      // group of four MMAs -- the 256 x 256 x 64 layer stayed at 1336 clk per row, HBM-bound, and the fused layer went
+      // from 1719 to 1943: too much scalar work between groups starves the queue.)
+      uint32_t stage = 0, full_parity = 0;
+      uint32_t qrow = 0;                                // ring position of output row x0 of the current item
+      int pend_stage = -1, pend_tf0 = -1, pend_tf1 = -1;     // commits owed for the previous row
       for (int it_ = blockIdx.x; it_ < nitems; it_ += gridDim.x) {
         const int item = a.reverse ? (nitems - 1 - it_) : it_;
         const int strip = (item / nyt) % nstrips;
@@ -383,8 +708,8 @@ k_conv_mid(ConvMidArgs a) {
         const int x1 = min(x0 + a.rs, a.nx);
         const int xlo = max(x0 - 1, 0), xhi = min(x1, a.nx - 1);
         // q0 = ring position of (virtual) row X-1 for the first input row of the item
-        uint32_t q0 = qrow + (uint32_t)(CM_RING + xlo - 1 - x0);
-        q0 = (q0 >= 2 * CM_RING) ? q0 - 2 * CM_RING : ((q0 >= CM_RING) ? q0 - CM_RING : q0);
+        uint32_t q0 = qrow + (uint32_t)(RING + xlo - 1 - x0);
+        q0 = (q0 >= 2 * RING) ? q0 - 2 * RING : ((q0 >= RING) ? q0 - RING : q0);
         for (int X = xlo; X <= xhi; ++X) {
           const int lo = max(X - 1, x0), hi = min(X + 1, x1 - 1);
           const int pos_lo = lo - (X - 1);                               // 0..2: window position of row lo
@@ -395,23 +720,42 @@ k_conv_mid(ConvMidArgs a) {
           const long long tc0 = clock64();
           const uint64_t da = da0 + (uint64_t)(stage * (CM_STAGE_BYTES >> 4));
           const uint64_t db = db0 + (uint64_t)(pos_lo * NB);
-          umma_bf16_row12<A_K16_STEP, B_STEP>(tmem + (q0 + (uint32_t)pos_lo) * NB, da, db, umma_idesc_bf16(nrows * NB));
-          umma_commit(&empty[stage]);                                  // smem stage free once the MMAs retire
-          if (X - 1 >= x0) umma_commit(&tfull[q0]);                    // output row X-1 complete
-          if (X == xhi && xhi == x1 - 1) umma_commit(&tfull[(q0 + 1 == CM_RING) ? 0 : q0 + 1]);   // image bottom: row X too
+          const uint32_t dcol = tmem + (q0 + (uint32_t)pos_lo) * NB;
+          const uint32_t idesc = umma_idesc_bf16(nrows * NB);
+          umma_bf16_rowpart<A_K16_STEP, B_STEP, 0, 4>(dcol, da, db, idesc);
+          if (pend_stage >= 0) {
+            umma_commit(&empty[pend_stage]);                            // smem stage free once the MMAs retire
+            if (pend_tf0 >= 0) umma_commit(&tfull[pend_tf0]);           // output row X-1 complete
+            if (pend_tf1 >= 0) umma_commit(&tfull[pend_tf1]);           // image bottom: row X too
+          }
+          umma_bf16_rowpart<A_K16_STEP, B_STEP, 4, 8>(dcol, da, db, idesc);
+          if constexpr (FIRST) {
+            // accumulator and A tile `f & 1` are free: row f was drained before this row's stage could be full
+            if (l0_f + 2 < l0_total) issue_l0(l0_f & 1);
+            ++l0_f;
+          }
+          umma_bf16_rowpart<A_K16_STEP, B_STEP, 8, 12>(dcol, da, db, idesc);
+          pend_stage = (int)stage;
+          pend_tf0 = (X - 1 >= x0) ? (int)q0 : -1;
+          pend_tf1 = (X == xhi && xhi == x1 - 1) ? (int)((q0 + 1 == RING) ? 0 : q0 + 1) : -1;
           t_full += tc0 - tb;
           t_issue += clock64() - tc0;
           ++t_rows;
-          q0 = (q0 + 1 == CM_RING) ? 0 : q0 + 1;
+          q0 = (q0 + 1 == RING) ? 0 : q0 + 1;
           if (++stage == CM_STAGES) { stage = 0; full_parity ^= 1; }
         }
         qrow += (uint32_t)(x1 - x0);
-        while (qrow >= CM_RING) qrow -= CM_RING;
+        while (qrow >= RING) qrow -= RING;
+      }
+      if (pend_stage >= 0) {                                 // the last row's commits
+        umma_commit(&empty[pend_stage]);
+        if (pend_tf0 >= 0) umma_commit(&tfull[pend_tf0]);
+        if (pend_tf1 >= 0) umma_commit(&tfull[pend_tf1]);
       }
       if (a.dbg != nullptr) {
         unsigned long long* d = a.dbg + (size_t)blockIdx.x * 8;
         d[0] = (unsigned long long)(clock64() - t_begin);
-        d[1] = 0ull;
+        d[1] = (unsigned long long)t_a0;                 // FIRST: waiting for the first layer's A tiles (inside `issue`)
         d[2] = (unsigned long long)t_full;
         d[3] = (unsigned long long)t_issue;
         d[4] = (unsigned long long)t_rows;
@@ -426,14 +770,14 @@ k_conv_mid(ConvMidArgs a) {
       const uint32_t t0 = tmem + ((uint32_t)(quarter * 32) << 16);
       if constexpr (NB == 64) {
 #pragma unroll
-        for (int c = 0; c < 512; c += 64) tmem_st32_fill(t0 + c + half * 32, 0u);
+        for (int c = 0; c < NB * SLOTS; c += 64) tmem_st32_fill(t0 + c + half * 32, 0u);
       } else {
 #pragma unroll
-        for (int c = 0; c < NB * CM_SLOTS; c += 16) tmem_st16_fill(t0 + c, 0u);
+        for (int c = 0; c < NB * SLOTS; c += 16) tmem_st16_fill(t0 + c, 0u);
       }
       tmem_st_wait();
       tc_fence_before();
-      if (lane == 0) for (int sl = 0; sl < CM_SLOTS; ++sl) mbar_arrive(&tempty[sl]);
+      if (lane == 0) for (int sl = 0; sl < SLOTS; ++sl) mbar_arrive(&tempty[sl]);
     }
     mbar_wait(wbar, 0);                               // bias lives behind the weight image
     uint32_t slot = 0, done_par = 0;                  // ring position of the next row to drain; per-position phase parity
@@ -478,7 +822,7 @@ k_conv_mid(ConvMidArgs a) {
         done_par ^= 1u << slot;
         tc_fence_after();
         const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + slot * NB;
-        const uint32_t maddr = taddr + CM_RING * NB;         // mirror slot (meaningful when slot < 2)
+        const uint32_t maddr = taddr + RING * NB;         // mirror slot (meaningful when slot < 2)
         if constexpr (!LAST) {
           uint32_t r[32];
           const uint32_t hoff = (uint32_t)(half * 32);
@@ -582,7 +926,7 @@ k_conv_mid(ConvMidArgs a) {
             }
           }
         }
-        slot = (slot + 1 == CM_RING) ? 0 : slot + 1;
+        slot = (slot + 1 == RING) ? 0 : slot + 1;
       }
     }
     if (a.dbg != nullptr && warp == 2 && lane == 0) {
@@ -634,6 +978,16 @@ static int launch_conv_mid_t(const ConvMidArgs& a, int sm_count, cudaStream_t st
 
 int launch_conv_mid(const ConvMidArgs& a, int sm_count, cudaStream_t st) {
   return launch_conv_mid_t<64, false>(a, sm_count, st);
+}
+int launch_conv_mid_fused(const ConvMidArgs& a, int sm_count, cudaStream_t st) {
+  using L = ConvMidSmem<64, true>;
+  MLSIM_SET_SMEM_ONCE((k_conv_mid<64, false, true>), L::TOTAL);
+  const int nyt = (a.ny + 127) / 128;
+  const int nstrips = (a.nx + a.rs - 1) / a.rs;
+  const long nitems = (long)a.batch * nstrips * nyt;
+  const int grid = (int)(nitems < sm_count ? nitems : sm_count);
+  MLSIM_CUDA_CHECK(launch_pdl(k_conv_mid<64, false, true>, dim3(grid), dim3(CM_THREADS_FUSED), (size_t)L::TOTAL, st, a));
+  return MLSIM_OK;
 }
 int launch_conv_last(const ConvMidArgs& a, int sm_count, cudaStream_t st) {
   return launch_conv_mid_t<16, true>(a, sm_count, st);

@@ -36,10 +36,16 @@ struct ConvMidArgs {
   int res_mode;
   const __nv_bfloat16* res;
   float sscale;
+  // fused first layer (launch_conv_mid_fused): the kernel's input rows are not read from `in` but COMPUTED from the fp32
+  // state (fu, fv) * fscale by the first layer (2 -> 64, weights wimg0 = the first layer's operand image)
+  const float* fu; const float* fv;
+  const uint8_t* wimg0;
+  float fscale;
 };
 
 int launch_conv_first(const ConvFirstArgs& a, int sm_count, cudaStream_t st);
 int launch_conv_mid(const ConvMidArgs& a, int sm_count, cudaStream_t st);
+int launch_conv_mid_fused(const ConvMidArgs& a, int sm_count, cudaStream_t st);     // first layer + first hidden layer
 int launch_conv_last(const ConvMidArgs& a, int sm_count, cudaStream_t st);
 int conv_pick_strip(int nx, int ny, int batch, int sm_count);
 int conv_first_wimg_bytes();

@@ -82,6 +82,7 @@ struct mlsim_plan {
   // cnn
   std::vector<CnnLayer> layers;
   bool cnn_ready = false;
+  bool fuse_first = false;              // first layer computed inside the first hidden layer's kernel (finalize decides)
   __nv_bfloat16* d_act[3] = {nullptr, nullptr, nullptr};
   int nact = 2;
   size_t act_bytes = 0;
@@ -279,10 +280,16 @@ int run_cnn_layers(mlsim_plan* pl, const float* u_in, const float* v_in, float* 
   const int L = (int)pl->layers.size();
   int rc;
   __nv_bfloat16* act[3] = {pl->d_act[0] + aoff, pl->d_act[1] + aoff, pl->d_act[2] ? pl->d_act[2] + aoff : nullptr};
-  ConvFirstArgs f;
-  f.u = u_in; f.v = v_in; f.out = act[pl->layers[0].out_buf]; f.wimg = pl->layers[0].d_wimg; f.scale = (float)scale;
-  f.nx = rows; f.ny = c.ny; f.batch = batch; f.reverse = 0; f.img_stride = img_stride;
-  { ProfScope ps(pl, 4, st); if ((rc = launch_conv_first(f, pl->sm_count, st))) return rc; }
+  // The first layer (2 -> 64) is computed inside the first hidden layer's kernel (its 537 MB of activations at config 2
+  // never reach HBM) whenever nobody else needs its output and the hidden layer is a plain 64-channel one.
+  const bool fuse_first = pl->fuse_first;
+  if (!fuse_first) {
+    ConvFirstArgs f;
+    f.u = u_in; f.v = v_in; f.out = act[pl->layers[0].out_buf]; f.wimg = pl->layers[0].d_wimg; f.scale = (float)scale;
+    f.nx = rows; f.ny = c.ny; f.batch = batch; f.reverse = 0; f.img_stride = img_stride;
+    ProfScope ps(pl, 4, st);
+    if ((rc = launch_conv_first(f, pl->sm_count, st))) return rc;
+  }
   for (int l = 1; l < L; ++l) {
     const CnnLayer& ly = pl->layers[l];
     ConvMidArgs m;
@@ -294,7 +301,12 @@ int run_cnn_layers(mlsim_plan* pl, const float* u_in, const float* v_in, float* 
     m.reverse = l & 1;                  // layer 0 ascending, layer 1 descending, ...
     m.res_mode = ly.res_mode; m.res = ly.res_buf >= 0 ? act[ly.res_buf] : nullptr; m.sscale = (float)scale;
     if (ly.res_mode == 2) { m.u = const_cast<float*>(u_in); m.v = const_cast<float*>(v_in); }   // read-only here
-    if (l < L - 1) {
+    m.fu = u_in; m.fv = v_in; m.wimg0 = pl->layers[0].d_wimg; m.fscale = (float)scale;
+    if (l == 1 && fuse_first) {
+      m.reverse = 0;
+      ProfScope ps(pl, 5, st);
+      if ((rc = launch_conv_mid_fused(m, pl->sm_count, st))) return rc;
+    } else if (l < L - 1) {
       ProfScope ps(pl, 5, st);
       if ((rc = launch_conv_mid(m, pl->sm_count, st))) return rc;
     } else {
@@ -713,6 +725,13 @@ int mlsim_cnn_finalize(mlsim_plan* pl) {
       MLSIM_CUDA_CHECK(cudaMemset(p, 0, pl->act_bytes));     // zero halo columns yp = 0 and yp = ny+1
     }
     pl->rs = conv_pick_strip(act_rows, c.ny, c.batch, pl->sm_count);
+  }
+  // fused first layer: layer 1 must be a hidden layer fed by layer 0 alone, and no shortcut may read layer 0's output
+  {
+    bool ok = pl->cfg.fuse_first_layer != 0 && L >= 3;
+    for (int li = 1; li < L && ok; ++li)
+      if ((pl->layers[li].res_mode == 1 || pl->layers[li].res_mode == 3) && pl->layers[li].res_src == 0) ok = false;
+    pl->fuse_first = ok;
   }
   MLSIM_CUDA_CHECK(cudaDeviceSynchronize());
   pl->cnn_ready = true;
@@ -1155,19 +1174,19 @@ int mlsim_launches_per_step(mlsim_plan* pl, int32_t apply_cnn) {
   int n = pl->cluster_projection ? 8 : 16;   // 4 stages x (explicit + cluster projection | explicit, div+rfft, column solve, irfft+grad)
   if (pl->slab || pl->r0 > 1) n = 4 * 6;     // split x-transform: explicit, div+rfft, pass A, column solve, pass C, irfft+grad
   if (!pl->slab) n *= solver_blocks(pl, apply_cnn && pl->cnn_ready, pl->cfg.batch);   // one set of solver launches per batch block
-  if (apply_cnn && pl->cnn_ready) n += (int)pl->layers.size();
+  if (apply_cnn && pl->cnn_ready) n += (int)pl->layers.size() - (pl->fuse_first ? 1 : 0);
   return n;
 }
 
 int64_t mlsim_workspace_bytes(mlsim_plan* pl) { return pl ? pl->ws_bytes : 0; }
 
-int mlsim_conv_debug(mlsim_plan* pl, double* out8) {
-  if (!pl || !out8 || !pl->d_dbg) { set_error("no conv debug counters (run mlsim_time_kernel(5|6) first)"); return MLSIM_EINVAL; }
+static int conv_debug_read(mlsim_plan* pl, double* out8, int first_cta) {
+  if (!pl || !out8 || !pl->d_dbg) { set_error("no conv debug counters (run mlsim_time_kernel(5|6|8) first)"); return MLSIM_EINVAL; }
   std::vector<unsigned long long> h((size_t)1024 * 8);
   MLSIM_CUDA_CHECK(cudaMemcpy(h.data(), pl->d_dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   int n = 0;
   for (int k = 0; k < 8; ++k) out8[k] = 0.0;
-  for (int b = 0; b < 1024; ++b) {
+  for (int b = first_cta; b < first_cta + 512; ++b) {
     if (h[(size_t)b * 8] == 0) continue;
     ++n;
     for (int k = 0; k < 8; ++k) out8[k] += (double)h[(size_t)b * 8 + k];
@@ -1175,6 +1194,8 @@ int mlsim_conv_debug(mlsim_plan* pl, double* out8) {
   for (int k = 0; k < 8; ++k) out8[k] /= (n ? n : 1);
   return n;
 }
+int mlsim_conv_debug(mlsim_plan* pl, double* out8) { return conv_debug_read(pl, out8, 0); }
+int mlsim_conv_debug_first(mlsim_plan* pl, double* out8) { return conv_debug_read(pl, out8, 512); }
 
 int mlsim_profile_enable(mlsim_plan* pl, int32_t kernel_class, int32_t max_samples) {
   MLSIM_ENTER(pl);
@@ -1211,7 +1232,7 @@ int mlsim_time_kernel(mlsim_plan* pl, int32_t which, int32_t warmup, int32_t ite
   if (!pl || !ms_out) { set_error("null argument"); return MLSIM_EINVAL; }
   MLSIM_CUDA_CHECK(cudaSetDevice(pl->cfg.device));
   MLSIM_PLAIN_ONLY(pl);
-  MLSIM_REQUIRE(which >= 0 && which <= 7 && iters >= 1 && warmup >= 0, "bad arguments");
+  MLSIM_REQUIRE(which >= 0 && which <= 8 && iters >= 1 && warmup >= 0, "bad arguments");
   if (which == 7 && !pl->cluster_projection) { set_error("cluster projection not available for this grid"); return MLSIM_EINVAL; }
   if (which >= 4 && !pl->cnn_ready) { set_error("correction network not finalised"); return MLSIM_ESTATE; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1247,13 +1268,15 @@ int mlsim_time_kernel(mlsim_plan* pl, int32_t which, int32_t warmup, int32_t ite
       }
       default: {
         const int L = (int)pl->layers.size();
-        const int l = (which == 5) ? 1 : L - 1;
-        if (which == 5 && L < 3) { set_error("no mid layer in this network"); return MLSIM_EINVAL; }
+        const int l = (which == 5 || which == 8) ? 1 : L - 1;
+        if ((which == 5 || which == 8) && L < 3) { set_error("no mid layer in this network"); return MLSIM_EINVAL; }
         ConvMidArgs m;
         m.in = pl->d_act[0]; m.out = pl->d_act[1]; m.u = pl->d_w1u; m.v = pl->d_w1v; m.y_nchw = nullptr;
         m.wimg = pl->layers[l].d_wimg; m.nx = c.nx; m.ny = c.ny; m.batch = c.batch; m.rs = pl->rs;
         m.img_stride = (long long)c.nx * c.ny; m.res_mode = 0; m.res = nullptr; m.sscale = 1.0f;
         m.cout = pl->layers[l].cout; m.relu = pl->layers[l].relu; m.dbg = pl->d_dbg; m.reverse = 0;
+        m.fu = pl->d_tu; m.fv = pl->d_tv; m.wimg0 = pl->layers[0].d_wimg; m.fscale = 1.0f;
+        if (which == 8) return launch_conv_mid_fused(m, pl->sm_count, st);
         return (which == 5) ? launch_conv_mid(m, pl->sm_count, st) : launch_conv_last(m, pl->sm_count, st);
       }
     }

@@ -50,8 +50,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Fast path first: measured on B200 (scripts/umma_mix_bench.cu), mbarrier.test_wait on a completed phase returns in 13
+// clocks, mbarrier.try_wait in 187 (it is a potentially-suspending instruction).  In steady state the barriers of the conv
+// pipelines are complete when their waiter arrives, and the tensor queue is shallow: every clock the MMA-issuing thread
+// spends in a wait is a clock of idle tensor pipe.  Only a barrier that is NOT ready falls through to try_wait.
 // Bounded spin: a protocol bug becomes a trap (reported as a launch failure) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_test_wait(bar, parity)) return;
 #ifndef MLSIM_NO_WATCHDOG
 #pragma unroll 1
   for (uint32_t it = 0; it < (1u << 26); ++it) {
@@ -206,6 +224,25 @@ __device__ __forceinline__ void umma_bf16_row12(uint32_t tmem_d, uint64_t desc_a
 #undef MLSIM_MMA
 #undef MLSIM_NEXT_K
 #undef MLSIM_NEXT_DY
+}
+
+// MMAs [I0, I1) of the same 12 (index i: dy = i / 4, K16 slice = i % 4): lets the issuing thread put its bookkeeping
+// (commits of the previous row) between two groups of MMAs, where the tensor queue hides it.
+template <int A_K16, int B_STEP, int I0, int I1>
+__device__ __forceinline__ void umma_bf16_rowpart(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+#pragma unroll
+  for (int i = I0; i < I1; ++i) {
+    const uint64_t da = desc_a + (uint64_t)((i & 3) * A_K16 + (i >> 2));
+    const uint64_t db = desc_b + (uint64_t)(i * B_STEP);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.eq.u32 p, 1, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc)
+        : "memory");
+  }
 }
 
 // Make `bar` track completion of all tcgen05 async ops issued so far by this thread.

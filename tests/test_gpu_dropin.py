@@ -115,3 +115,40 @@ def test_step_f64_equals_step(built_lib):
     with pytest.raises(ValueError):
         plan.step_f64(u, v)
     plan.close()
+
+
+def test_two_plans_on_two_devices_in_one_process(built_lib):
+    """One plan == one device, but one process may own several plans (mlsim_config.device): the per-device kernel
+    attributes (dynamic shared memory) and the current-device switch of every entry point must follow the plan."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import json
+    import safetensors.torch as st
+    from ml_accelerated_simulation_b200 import Plan, PlanConfig, models
+    g = os.path.join(ROOT, "tests", "golden")
+    cfgj = json.load(open(os.path.join(g, "MLACFD.json")))
+    sd = st.load_file(os.path.join(g, "mlacfd_weights.safetensors"))
+    model = models.buildModel(cfgj)
+    model.load_state_dict(sd)
+    gen = torch.Generator().manual_seed(3)
+    u0 = torch.randn(2, 128, 128, generator=gen)
+    v0 = torch.randn(2, 128, 128, generator=gen)
+    outs = []
+    plans = [Plan(PlanConfig(nx=128, ny=128, batch=2, device=d)) for d in (0, 1)]       # both alive at once
+    for d, plan in enumerate(plans):
+        model.attach(plan)
+    torch.cuda.set_device(0)                                                             # current device != plan 1's device
+    for d, plan in enumerate(plans):
+        u, v = u0.to(f"cuda:{d}"), v0.to(f"cuda:{d}")
+        plan.project(u, v, want_p=False)
+        plan.step(u, v, nsteps=2, apply_cnn=True)
+        hu, hv = u0.clone(), v0.clone()
+        plan.rollout_host(hu, hv, 0)
+        torch.cuda.synchronize(d)
+        outs.append((u.cpu(), v.cpu()))
+    assert torch.isfinite(outs[0][0]).all()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    with pytest.raises(ValueError):
+        plans[1].step(u0.to("cuda:0"), v0.to("cuda:0"))                                  # a field on the wrong device is refused
+    for plan in plans:
+        plan.close()

@@ -686,3 +686,67 @@ def test_long_rollout_spectra_with_correction(mlsim, mlacfd):
     assert r["dE_low"] < 1e-2 and r["dZ_low"] < 1e-2, r
     assert r["dE_all"] < 5e-2 and r["dZ_all"] < 5e-2, r
     plan.close()
+
+
+# --------------------------------------------------------------------------------------------- fused first layer
+@pytest.mark.parametrize("nx,ny,batch,scale", [(64, 64, 3, 1.0), (96 + 32, 128, 2, 1.0 / 7), (64, 512, 1, 1.0), (256, 256, 2, 1.0),
+                                               (512, 1024, 1, 1.0)])
+def test_fused_first_layer(mlsim, mlacfd, golden_dir, nx, ny, batch, scale):
+    """mlsim_config.fuse_first_layer: the first layer (2 -> 64) computed inside the first hidden layer's kernel (its
+    activations never reach HBM) against the oracle and against the separate-kernel path -- partial tiles (ny = 64), a
+    single full tile (both halo pixels are padding), several tiles (halo pixels computed on the CUDA cores), the BN
+    network with ragged channel counts, and a ResNet whose first block's shortcut reads the network input."""
+    from ml_accelerated_simulation_b200 import models
+    cfgj, sd = mlacfd
+    model = models.buildModel(cfgj)
+    model.load_state_dict(sd)
+    g = torch.Generator().manual_seed(17)
+    u = (torch.randn(batch, nx, ny, generator=g) * 3).to(DEV)
+    v = (torch.randn(batch, nx, ny, generator=g) * 3).to(DEV)
+    x = torch.stack((u.cpu().double(), v.cpu().double()), 1) * scale
+    y_emu = OC.model_forward(x, cfgj, sd, round_bf16=True)
+    ys = {}
+    for fuse in (False, True):
+        plan = mlsim.Plan(mlsim.PlanConfig(nx=nx, ny=ny, batch=batch, fuse_first_layer=fuse))
+        model.attach(plan)
+        ys[("launches", fuse)] = plan.launches_per_step(True)
+        ys[fuse] = plan.cnn_forward(u, v, scale)
+        uu, vv = u.clone(), v.clone()
+        plan.cnn_correct(uu, vv, scale)
+        assert torch.allclose(uu, u + ys[fuse][:, 0], atol=1e-6) and torch.allclose(vv, v + ys[fuse][:, 1], atol=1e-6)
+        plan.close()
+    assert ys[("launches", True)] == ys[("launches", False)] - 1          # one kernel fewer per step
+    assert rel(ys[True], y_emu) <= 1e-3, (rel(ys[True], y_emu), rel(ys[False], y_emu))
+    assert rel(ys[True], ys[False]) <= 3e-4
+    yc = ys[True].double().cpu()
+    for sl in ((..., 0, slice(None)), (..., -1, slice(None)), (..., slice(None), 0), (..., slice(None), -1)):
+        assert ((yc[sl] - y_emu[sl]).norm() / y_emu[sl].norm()).item() <= 2e-3
+    if ny > 128:      # tile seams: the columns either side of every 128-pixel tile boundary
+        for c in range(128, ny, 128):
+            sl = (..., slice(c - 2, c + 2))
+            assert ((yc[sl] - y_emu[sl]).norm() / y_emu[sl].norm()).item() <= 2e-3
+
+
+def test_fused_first_layer_other_networks(mlsim, golden_dir):
+    from ml_accelerated_simulation_b200 import models
+    g = torch.Generator().manual_seed(5)
+    for cfg_name, w_name in (("cnn1.json", "cnn1_bn_weights.safetensors"), ("basicResnet1.json", "resnet_weights.safetensors"),
+                             ("basicBottleneck1.json", "bottleneck_weights.safetensors")):
+        cfgj = json.load(open(os.path.join(golden_dir, cfg_name)))
+        sd = st.load_file(os.path.join(golden_dir, w_name))
+        model = models.buildModel(cfgj)
+        model.load_state_dict(sd)
+        u = torch.randn(2, 64, 256, generator=g).to(DEV)
+        v = torch.randn(2, 64, 256, generator=g).to(DEV)
+        ys = {}
+        for fuse in (False, True):
+            plan = mlsim.Plan(mlsim.PlanConfig(nx=64, ny=256, batch=2, fuse_first_layer=fuse))
+            model.attach(plan)
+            ys[fuse] = plan.cnn_forward(u, v, 1.0)
+            plan.close()
+        x = torch.stack((u.cpu().double(), v.cpu().double()), 1)
+        y_emu = OC.model_forward(x, cfgj, sd, round_bf16=True)
+        y_ref = OC.model_forward(x, cfgj, sd)
+        # same rule as the separate-kernel path: inside half the bf16 storage error of the emulation itself
+        assert rel(ys[True], y_emu) <= max(1e-3, 0.5 * rel(y_emu, y_ref)), (cfg_name, rel(ys[True], y_emu), rel(ys[False], y_emu))
+        assert rel(ys[True], ys[False]) <= max(3e-4, 0.5 * rel(y_emu, y_ref)), cfg_name

@@ -56,8 +56,9 @@ typedef struct {
                                    * (default: 2 when the correction network follows every step, 4 for bare solver rollouts) */
   int32_t host_blocks;            /* 1..8: equal batch blocks of the H2D | step | D2H pipeline of mlsim_rollout_host
                                    * (default: sized in whole rounds of the persistent conv grid) */
-  int32_t fuse_first_layer;       /* 1: the network's first layer (2 -> 64) is computed inside the first hidden layer's kernel,
-                                   * so its activations never reach HBM; 0: separate first-layer kernel */
+  int32_t separate_first_layer;   /* 0 (default): the network's first layer (2 -> 64) is computed inside the first hidden
+                                   * layer's kernel whenever the network allows it, so its activations never reach HBM;
+                                   * 1: always a separate first-layer kernel (the round-1 path, kept for A/B and parity) */
   int32_t cluster_projection;     /* 1: single-kernel projection (thread-block cluster per image, half spectrum in
                                    * distributed shared memory); plain square 64 / 128 / 256 grids only.  Measured slower
                                    * than the three-kernel projection at every BASELINE config, hence off by default */

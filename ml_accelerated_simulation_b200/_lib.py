@@ -24,7 +24,7 @@ class MlsimConfig(C.Structure):
         ("advection", C.c_int32), ("lw_dt_scale", C.c_double),
         ("device", C.c_int32),
         ("slab_rank", C.c_int32), ("slab_world", C.c_int32),
-        ("solver_blocks", C.c_int32), ("host_blocks", C.c_int32), ("fuse_first_layer", C.c_int32),
+        ("solver_blocks", C.c_int32), ("host_blocks", C.c_int32), ("separate_first_layer", C.c_int32),
         ("cluster_projection", C.c_int32),
     ]
 

@@ -304,7 +304,7 @@ int run_cnn_layers(mlsim_plan* pl, const float* u_in, const float* v_in, float* 
     m.fu = u_in; m.fv = v_in; m.wimg0 = pl->layers[0].d_wimg; m.fscale = (float)scale;
     if (l == 1 && fuse_first) {
       m.reverse = 0;
-      ProfScope ps(pl, 5, st);
+      ProfScope ps(pl, 8, st);
       if ((rc = launch_conv_mid_fused(m, pl->sm_count, st))) return rc;
     } else if (l < L - 1) {
       ProfScope ps(pl, 5, st);
@@ -728,7 +728,7 @@ int mlsim_cnn_finalize(mlsim_plan* pl) {
   }
   // fused first layer: layer 1 must be a hidden layer fed by layer 0 alone, and no shortcut may read layer 0's output
   {
-    bool ok = pl->cfg.fuse_first_layer != 0 && L >= 3;
+    bool ok = pl->cfg.separate_first_layer == 0 && L >= 3;
     for (int li = 1; li < L && ok; ++li)
       if ((pl->layers[li].res_mode == 1 || pl->layers[li].res_mode == 3) && pl->layers[li].res_src == 0) ok = false;
     pl->fuse_first = ok;
@@ -1199,7 +1199,7 @@ int mlsim_conv_debug_first(mlsim_plan* pl, double* out8) { return conv_debug_rea
 
 int mlsim_profile_enable(mlsim_plan* pl, int32_t kernel_class, int32_t max_samples) {
   MLSIM_ENTER(pl);
-  MLSIM_REQUIRE(kernel_class >= -1 && kernel_class <= 7 && max_samples >= 0 && max_samples <= (1 << 20), "bad arguments");
+  MLSIM_REQUIRE(kernel_class >= -1 && kernel_class <= 8 && max_samples >= 0 && max_samples <= (1 << 20), "bad arguments");
   MLSIM_CUDA_CHECK(cudaSetDevice(pl->cfg.device));
   while ((int)pl->prof_events.size() < max_samples) {
     cudaEvent_t a, b;

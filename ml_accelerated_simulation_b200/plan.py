@@ -40,7 +40,7 @@ class PlanConfig:
     slab_world: int = 0
     solver_blocks: int = 0               # execution tuning, 0 = measured default (see include/mlsim.h)
     host_blocks: int = 0
-    fuse_first_layer: bool = False       # first conv layer computed inside the first hidden layer's kernel
+    fuse_first_layer: bool = True        # first conv layer computed inside the first hidden layer's kernel (when the net allows)
     cluster_projection: bool = False
 
     def resolved_dt(self) -> float:
@@ -65,7 +65,7 @@ class Plan:
         c = _lib.MlsimConfig(cfg.nx, cfg.ny, cfg.batch, cfg.lx, cfg.ly, self.dt, cfg.viscosity, cfg.density,
                              cfg.drag, cfg.forcing_wavenumber, cfg.forcing_scale, ADVECTION[cfg.advection],
                              cfg.lw_dt_scale, cfg.device, cfg.slab_rank, cfg.slab_world, cfg.solver_blocks,
-                             cfg.host_blocks, int(cfg.fuse_first_layer), int(cfg.cluster_projection))
+                             cfg.host_blocks, int(not cfg.fuse_first_layer), int(cfg.cluster_projection))
         h = C.c_void_p()
         _lib.check(self._lib.mlsim_plan_create(C.byref(c), C.byref(h)))
         self._h = h

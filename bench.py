@@ -361,7 +361,7 @@ def _slab_measure(n, K, W, p2p, dev, local, rank, world, peaks, model, want_cloc
            "solver_frac": SOLVER_BYTES_PER_CELL_STEP * solver_rate / world / 1e9 / peaks["hbm_gbs"],
            "solver_frac_note": f"{SOLVER_BYTES_PER_CELL_STEP} B/cell-step per GPU against the measured HBM copy peak; includes the exchanges",
            "phase_ms": phase, "mid_conv_avg_launch_ms": mid_avg, "mid_conv_tflops": mid_tflops,
-           "exchanges_per_step": 13, "gpu_launches_per_step": 24 + 7, "clocks": clocks}
+           "exchanges_per_step": 13, "gpu_launches_per_step": be.plan.launches_per_step(True), "clocks": clocks}
     be.close()
     del stp, be
     torch.cuda.empty_cache()
@@ -675,7 +675,7 @@ def run_slab(args):
                                 "achieved": SOLVER_BYTES_PER_CELL_STEP * solver_rate / world / 1e9, "peak": peaks["hbm_gbs"],
                                 "unit": "GB/s per GPU", "frac": m["solver_frac"], "phase_ms_per_launch": m["phase_ms"],
                                 "note": "296 B/cell-step algorithmic; includes the exchanges (4 halo + 8 spectral per step)"},
-            "cpu_baseline": None, "e2e": None, "gpu_launches": (24 + 7) * K, "clocks": m["clocks"],
+            "cpu_baseline": None, "e2e": None, "gpu_launches": m["gpu_launches_per_step"] * K, "clocks": m["clocks"],
         }
         print(json.dumps(line), flush=True)
     if world > 1:

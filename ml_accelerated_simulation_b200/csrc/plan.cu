@@ -310,6 +310,8 @@ int run_cnn_layers(mlsim_plan* pl, const float* u_in, const float* v_in, float* 
       ProfScope ps(pl, 5, st);
       if ((rc = launch_conv_mid(m, pl->sm_count, st))) return rc;
     } else {
+      // (strips of 16 instead of 32 rows for this layer -- better balance over its 296 CTAs, more halo rows -- were
+      //  measured: 0.137 -> 0.127 ms at 256^2 x 64, 0.461 -> 0.478 ms at 1024^2 x 16; not kept)
       ProfScope ps(pl, 6, st);
       if ((rc = launch_conv_last(m, pl->sm_count, st))) return rc;
     }

@@ -252,6 +252,13 @@ template <int NB, bool FIRST = false> struct ConvMidSmem {
   static constexpr int BAR_OFF = HIN_OFF + (FIRST ? 2 * 2 * 20 * 4 + 64 : 0);
   static constexpr int NBARS = 2 * CM_STAGES + 2 * SLOTS + 1 + (FIRST ? 4 : 0);
   static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
+  // compute-sanitizer is closed on this GPU pool: the bounds the roles rely on are checked here instead
+  static_assert(TOTAL <= 227 * 1024, "shared memory budget of one CTA");
+  static_assert(7 * CM_PLANE + 129 * 16 + 16 <= CM_STAGE_BYTES, "stage: plane 7, pixel 129 (right halo) ends inside the stage");
+  static_assert(3 * CF_LBO_A + 127 * 16 + 16 <= 4 * CF_LBO_A, "first-layer A tile: chunk 3, pixel 127 ends inside the tile");
+  static_assert((STAGE_OFF % 128) == 0 && (A0_OFF % 16) == 0 && (W0_OFF % 16) == 0 && (BAR_OFF % 8) == 0, "alignment of the regions");
+  static_assert(NB * SLOTS + (FIRST ? 128 : 0) <= 512, "TMEM columns: accumulator ring + mirrors (+ two first-layer accumulators)");
+  static_assert(20 + 2 * 2 + 1 + 12 < (FIRST ? (2 * 2 * 20 * 4 + 64) / 4 : 64), "halo im2col rows fit their region");
 };
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -750,3 +750,37 @@ def test_fused_first_layer_other_networks(mlsim, golden_dir):
         # same rule as the separate-kernel path: inside half the bf16 storage error of the emulation itself
         assert rel(ys[True], y_emu) <= max(1e-3, 0.5 * rel(y_emu, y_ref)), (cfg_name, rel(ys[True], y_emu), rel(ys[False], y_emu))
         assert rel(ys[True], ys[False]) <= max(3e-4, 0.5 * rel(y_emu, y_ref)), cfg_name
+
+
+def test_full_size_config4_shard(mlsim, mlacfd):
+    """BASELINE configs[3] as one GPU of eight sees it (128 x 128, 512 trajectories): two steps of solver + CNN; sampled
+    trajectories against the oracle, and against the same trajectories run as a batch of their own (independence of
+    trajectories is what lets the ensemble shard with no collective)."""
+    from ml_accelerated_simulation_b200 import models
+    cfgj, sd = mlacfd
+    model = models.buildModel(cfgj)
+    model.load_state_dict(sd)
+    cfg = S.SolverConfig(nx=128, ny=128)
+    B = 512
+    base_u, base_v = S.filtered_velocity_field(cfg, 8, seed=4, iterations=4)
+    g = torch.Generator().manual_seed(0)
+    amp = 0.5 + torch.rand(B, 1, 1, generator=g, dtype=torch.float64)
+    shift = torch.randint(0, 128, (B,), generator=g)
+    u64 = torch.stack([torch.roll(base_u[i % 8], int(shift[i]), 0) for i in range(B)]) * amp
+    v64 = torch.stack([torch.roll(base_v[i % 8], int(shift[i]), 0) for i in range(B)]) * amp
+    plan = mlsim.Plan(mlsim.PlanConfig(nx=128, ny=128, batch=B))
+    model.attach(plan)
+    u, v = u64.float().to(DEV), v64.float().to(DEV)
+    plan.step(u, v, nsteps=2, apply_cnn=True)
+    assert torch.isfinite(u).all() and torch.isfinite(v).all()
+    pick = [0, 137, 511]
+    ou, ov, _ = OC.rollout(u64[pick], v64[pick], cfg, 2, cfgj, sd, 1.0, round_bf16=True)
+    qu, qv, _ = OC.rollout(u64[pick].float(), v64[pick].float(), cfg, 2)
+    o64u, o64v, _ = OC.rollout(u64[pick], v64[pick], cfg, 2)
+    assert rel(u[pick], ou) <= 4 * rel(qu, o64u) + 1e-6 and rel(v[pick], ov) <= 4 * rel(qv, o64v) + 1e-6
+    small = mlsim.Plan(mlsim.PlanConfig(nx=128, ny=128, batch=3))
+    model.attach(small)
+    su, sv = u64[pick].float().to(DEV).contiguous(), v64[pick].float().to(DEV).contiguous()
+    small.step(su, sv, nsteps=2, apply_cnn=True)
+    assert rel(su, u[pick]) < 1e-6 and rel(sv, v[pick]) < 1e-6
+    plan.close(); small.close()

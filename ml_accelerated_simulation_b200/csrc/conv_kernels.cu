@@ -251,7 +251,8 @@ template <int NB, bool FIRST = false> struct ConvMidSmem {
   static constexpr int HIN_OFF = W0_OFF + (FIRST ? W0_BYTES : 0);
   static constexpr int BAR_OFF = HIN_OFF + (FIRST ? 2 * 2 * 20 * 4 + 64 : 0);
   static constexpr int NBARS = 2 * CM_STAGES + 2 * SLOTS + 1 + (FIRST ? 4 : 0);
-  static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
+  static constexpr int REC_OFF = ((BAR_OFF + NBARS * 8 + 16 + 15) / 16) * 16;   // one 32-byte row record per stage (gate -> MMA warp)
+  static constexpr int TOTAL = REC_OFF + CM_STAGES * 32;
   // compute-sanitizer is closed on this GPU pool: the bounds the roles rely on are checked here instead
   static_assert(TOTAL <= 227 * 1024, "shared memory budget of one CTA");
   static_assert(7 * CM_PLANE + 129 * 16 + 16 <= CM_STAGE_BYTES, "stage: plane 7, pixel 129 (right halo) ends inside the stage");
@@ -540,6 +541,7 @@ k_conv_mid(ConvMidArgs a) {
   uint64_t* l0full = wbar + 1;                        // FIRST: first-layer accumulator `buf` complete
   uint64_t* a0full = wbar + 3;                        // FIRST: first-layer A tile `buf` built
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + L::NBARS);
+  uint4* sRec = reinterpret_cast<uint4*>(smem + L::REC_OFF);
   uint8_t* sA0 = smem + L::A0_OFF;
   uint8_t* sW0 = smem + L::W0_OFF;
   float* sHin = reinterpret_cast<float*>(smem + L::HIN_OFF);
@@ -635,16 +637,45 @@ k_conv_mid(ConvMidArgs a) {
     // arrival of full[stage], so the MMA warp still has a single barrier to wait for per input row, while the
     // producer's loads no longer queue behind the epilogue.  (With both checks in the producer thread the loads ran at
     // most ~4 rows ahead and the MMA warp waited 298 of 1498 clk per row for its input; mlsim_conv_debug.)
+    // It also does the MMA warp's per-row bookkeeping: operand descriptors, accumulator column, instruction descriptor,
+    // which barriers to commit and (FIRST) which first-layer accumulator to issue -- one 32-byte record per stage, written
+    // before the arrival.  The issuing thread's ~50 dependent scalar instructions per row were not covered by the
+    // shallow tensor queue (~250 clk of idle pipe per row); it now loads 32 bytes instead.
     if (lane == 0) {
+      constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
+      const uint64_t db0 = ((uint64_t)DESC_HI << 32) | (uint64_t)((smem_u32(sW) >> 4) | ((uint32_t)(L::LBO_B >> 4) << 16));
+      const uint64_t da0 = ((uint64_t)DESC_HI << 32) | (uint64_t)((smem_u32(sStage) >> 4) | ((uint32_t)(CM_PLANE >> 4) << 16));
+      int total = 0, f = 0;
+      for (int it_ = blockIdx.x; it_ < nitems; it_ += gridDim.x) {
+        const int item = a.reverse ? (nitems - 1 - it_) : it_;
+        const int x0 = ((item / nyt) % nstrips) * a.rs;
+        const int x1 = min(x0 + a.rs, a.nx);
+        total += min(x1, a.nx - 1) - max(x0 - 1, 0) + 1;
+      }
       uint32_t stage = 0, empty_parity = 1;
       uint32_t qn = 0, ready_par = 0;
+      uint32_t qrow = 0;                                // ring position of output row x0 of the current item
       for (int it_ = blockIdx.x; it_ < nitems; it_ += gridDim.x) {
         const int item = a.reverse ? (nitems - 1 - it_) : it_;
         const int strip = (item / nyt) % nstrips;
         const int x0 = strip * a.rs;
         const int x1 = min(x0 + a.rs, a.nx);
         const int xlo = max(x0 - 1, 0), xhi = min(x1, a.nx - 1);
-        for (int X = xlo; X <= xhi; ++X) {
+        // q0 = ring position of (virtual) row X-1 for the first input row of the item
+        uint32_t q0 = qrow + (uint32_t)(RING + xlo - 1 - x0);
+        q0 = (q0 >= 2 * RING) ? q0 - 2 * RING : ((q0 >= RING) ? q0 - RING : q0);
+        for (int X = xlo; X <= xhi; ++X, ++f) {
+          const int lo = max(X - 1, x0), hi = min(X + 1, x1 - 1);
+          const int pos_lo = lo - (X - 1);                               // 0..2: window position of row lo
+          const int nrows = hi - lo + 1;
+          const uint64_t da = da0 + (uint64_t)(stage * (CM_STAGE_BYTES >> 4));
+          const uint64_t db = db0 + (uint64_t)(pos_lo * NB);
+          const int tf0 = (X - 1 >= x0) ? (int)q0 : 0xffff;                                           // output row X-1 complete
+          const int tf1 = (X == xhi && xhi == x1 - 1) ? (int)((q0 + 1 == RING) ? 0 : q0 + 1) : 0xffff;    // image bottom: row X too
+          const int l0 = (FIRST && f + 2 < total) ? (f & 1) : -1;
+          const uint4 r0 = make_uint4((uint32_t)da, (uint32_t)(da >> 32), (uint32_t)db, (uint32_t)(db >> 32));
+          const uint4 r1 = make_uint4(tmem + (q0 + (uint32_t)pos_lo) * NB, umma_idesc_bf16(nrows * NB),
+                                      (uint32_t)tf0 | ((uint32_t)tf1 << 16), (uint32_t)l0);
           const int nnew = ((X + 1 <= x1 - 1) ? 1 : 0) + ((X == 0) ? 1 : 0);
           for (int k = 0; k < nnew; ++k) {
             mbar_wait(&tempty[qn], (ready_par >> qn) & 1u);
@@ -652,9 +683,14 @@ k_conv_mid(ConvMidArgs a) {
             qn = (qn + 1 == RING) ? 0 : qn + 1;
           }
           mbar_wait(&empty[stage], empty_parity);      // the stage's previous phase is over: this arrival counts for the new one
-          mbar_arrive(&full[stage]);
+          sRec[2 * stage] = r0;
+          sRec[2 * stage + 1] = r1;
+          mbar_arrive(&full[stage]);                   // (release: the record is visible to whoever sees the phase complete)
+          q0 = (q0 + 1 == RING) ? 0 : q0 + 1;
           if (++stage == CM_STAGES) { stage = 0; empty_parity ^= 1; }
         }
+        qrow += (uint32_t)(x1 - x0);
+        while (qrow >= RING) qrow -= RING;
       }
     }
   } else if (warp == 1) {
@@ -672,7 +708,7 @@ k_conv_mid(ConvMidArgs a) {
       const long long t_begin = clock64();
       // FIRST: the first-layer MMAs (A tile `buf` x first-layer weights -> accumulator `buf`) are issued from here, for
       // row f+2 right behind the hidden layer's MMAs of row f (rows counted over all of this CTA's work items)
-      int l0_total = 0, l0_f = 0;
+      int l0_total = 0;
       uint32_t a0par = 0;
       long long t_a0 = 0;
       const uint64_t l0_da = umma_desc(smem_u32(sA0), CF_LBO_A, 128), l0_db = umma_desc(smem_u32(sW0), CF_LBO_B, 128);
@@ -706,58 +742,49 @@ k_conv_mid(ConvMidArgs a) {
       // group of four MMAs -- the 256 x 256 x 64 layer stayed at 1336 clk per row, HBM-bound, and the fused layer went
       // from 1719 to 1943: too much scalar work between groups starves the queue.)
       uint32_t stage = 0, full_parity = 0;
-      uint32_t qrow = 0;                                // ring position of output row x0 of the current item
-      int pend_stage = -1, pend_tf0 = -1, pend_tf1 = -1;     // commits owed for the previous row
-      for (int it_ = blockIdx.x; it_ < nitems; it_ += gridDim.x) {
-        const int item = a.reverse ? (nitems - 1 - it_) : it_;
-        const int strip = (item / nyt) % nstrips;
-        const int x0 = strip * a.rs;
-        const int x1 = min(x0 + a.rs, a.nx);
-        const int xlo = max(x0 - 1, 0), xhi = min(x1, a.nx - 1);
-        // q0 = ring position of (virtual) row X-1 for the first input row of the item
-        uint32_t q0 = qrow + (uint32_t)(RING + xlo - 1 - x0);
-        q0 = (q0 >= 2 * RING) ? q0 - 2 * RING : ((q0 >= RING) ? q0 - RING : q0);
-        for (int X = xlo; X <= xhi; ++X) {
-          const int lo = max(X - 1, x0), hi = min(X + 1, x1 - 1);
-          const int pos_lo = lo - (X - 1);                               // 0..2: window position of row lo
-          const int nrows = hi - lo + 1;
-          const long long tb = clock64();
-          mbar_wait(&full[stage], full_parity);
-          tc_fence_after();
-          const long long tc0 = clock64();
-          const uint64_t da = da0 + (uint64_t)(stage * (CM_STAGE_BYTES >> 4));
-          const uint64_t db = db0 + (uint64_t)(pos_lo * NB);
-          const uint32_t dcol = tmem + (q0 + (uint32_t)pos_lo) * NB;
-          const uint32_t idesc = umma_idesc_bf16(nrows * NB);
-          umma_bf16_rowpart<A_K16_STEP, B_STEP, 0, 4>(dcol, da, db, idesc);
-          if (pend_stage >= 0) {
-            umma_commit(&empty[pend_stage]);                            // smem stage free once the MMAs retire
-            if (pend_tf0 >= 0) umma_commit(&tfull[pend_tf0]);           // output row X-1 complete
-            if (pend_tf1 >= 0) umma_commit(&tfull[pend_tf1]);           // image bottom: row X too
-          }
-          umma_bf16_rowpart<A_K16_STEP, B_STEP, 4, 8>(dcol, da, db, idesc);
-          if constexpr (FIRST) {
-            // accumulator and A tile `f & 1` are free: row f was drained before this row's stage could be full
-            if (l0_f + 2 < l0_total) issue_l0(l0_f & 1);
-            ++l0_f;
-          }
-          umma_bf16_rowpart<A_K16_STEP, B_STEP, 8, 12>(dcol, da, db, idesc);
-          pend_stage = (int)stage;
-          pend_tf0 = (X - 1 >= x0) ? (int)q0 : -1;
-          pend_tf1 = (X == xhi && xhi == x1 - 1) ? (int)((q0 + 1 == RING) ? 0 : q0 + 1) : -1;
-          t_full += tc0 - tb;
-          t_issue += clock64() - tc0;
-          ++t_rows;
-          q0 = (q0 + 1 == RING) ? 0 : q0 + 1;
-          if (++stage == CM_STAGES) { stage = 0; full_parity ^= 1; }
+      int pend_stage = -1, pend_tf0 = 0xffff, pend_tf1 = 0xffff;     // commits owed for the previous row
+      int total = l0_total;
+      if constexpr (!FIRST) {
+        for (int it_ = blockIdx.x; it_ < nitems; it_ += gridDim.x) {
+          const int item = a.reverse ? (nitems - 1 - it_) : it_;
+          const int x0 = ((item / nyt) % nstrips) * a.rs;
+          const int x1 = min(x0 + a.rs, a.nx);
+          total += min(x1, a.nx - 1) - max(x0 - 1, 0) + 1;
         }
-        qrow += (uint32_t)(x1 - x0);
-        while (qrow >= RING) qrow -= RING;
+      }
+      for (int f = 0; f < total; ++f) {
+        const long long tb = clock64();
+        mbar_wait(&full[stage], full_parity);
+        tc_fence_after();
+        const long long tc0 = clock64();
+        const uint4 r0 = sRec[2 * stage], r1 = sRec[2 * stage + 1];      // this row's record, prepared by the gate warp
+        const uint64_t da = (uint64_t)r0.x | ((uint64_t)r0.y << 32);
+        const uint64_t db = (uint64_t)r0.z | ((uint64_t)r0.w << 32);
+        umma_bf16_rowpart<A_K16_STEP, B_STEP, 0, 4>(r1.x, da, db, r1.y);
+        if (pend_stage >= 0) {
+          umma_commit(&empty[pend_stage]);                            // smem stage free once the MMAs retire
+          if (pend_tf0 != 0xffff) umma_commit(&tfull[pend_tf0]);      // output row X-1 complete
+          if (pend_tf1 != 0xffff) umma_commit(&tfull[pend_tf1]);      // image bottom: row X too
+        }
+        umma_bf16_rowpart<A_K16_STEP, B_STEP, 4, 8>(r1.x, da, db, r1.y);
+        if constexpr (FIRST) {
+          // first-layer MMAs of row f+2: accumulator and A tile `f & 1` are free, row f was drained before this row's
+          // stage could be full
+          if ((int)r1.w >= 0) issue_l0((int)r1.w);
+        }
+        umma_bf16_rowpart<A_K16_STEP, B_STEP, 8, 12>(r1.x, da, db, r1.y);
+        pend_stage = (int)stage;
+        pend_tf0 = (int)(r1.z & 0xffffu);
+        pend_tf1 = (int)(r1.z >> 16);
+        t_full += tc0 - tb;
+        t_issue += clock64() - tc0;
+        ++t_rows;
+        if (++stage == CM_STAGES) { stage = 0; full_parity ^= 1; }
       }
       if (pend_stage >= 0) {                                 // the last row's commits
         umma_commit(&empty[pend_stage]);
-        if (pend_tf0 >= 0) umma_commit(&tfull[pend_tf0]);
-        if (pend_tf1 >= 0) umma_commit(&tfull[pend_tf1]);
+        if (pend_tf0 != 0xffff) umma_commit(&tfull[pend_tf0]);
+        if (pend_tf1 != 0xffff) umma_commit(&tfull[pend_tf1]);
       }
       if (a.dbg != nullptr) {
         unsigned long long* d = a.dbg + (size_t)blockIdx.x * 8;

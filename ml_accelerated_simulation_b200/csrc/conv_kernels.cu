@@ -23,6 +23,10 @@ namespace mlsim {
 
 using namespace tc;
 
+// cycle counters of the MMA-issuing thread: compiled in only for the instantiation mlsim_time_kernel launches (TIMED);
+// three clock reads per row on that thread's latency-critical path cost 0.5 % of the step
+#define MLSIM_MMA_CLOCK() (TIMED ? clock64() : 0ll)
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -518,7 +522,7 @@ __device__ __forceinline__ void conv_first_halo(const ConvMidArgs& a, uint8_t* s
   }
 }
 
-template <int NB, bool LAST, bool FIRST = false>
+template <int NB, bool LAST, bool FIRST = false, bool TIMED = false>
 __global__ void __launch_bounds__(LAST ? CM_THREADS_LAST : (FIRST ? CM_THREADS_FUSED : CM_THREADS_MID), LAST ? 2 : 1)
 k_conv_mid(ConvMidArgs a) {
   static_assert(!(FIRST && LAST) && (!FIRST || NB == 64), "the fused first layer feeds a hidden layer");
@@ -705,7 +709,7 @@ k_conv_mid(ConvMidArgs a) {
       const uint64_t db0 = ((uint64_t)DESC_HI << 32) | (uint64_t)((smem_u32(sW) >> 4) | ((uint32_t)(L::LBO_B >> 4) << 16));
       const uint64_t da0 = ((uint64_t)DESC_HI << 32) | (uint64_t)((smem_u32(sStage) >> 4) | ((uint32_t)(CM_PLANE >> 4) << 16));
       long long t_full = 0, t_issue = 0, t_rows = 0;
-      const long long t_begin = clock64();
+      const long long t_begin = MLSIM_MMA_CLOCK();
       // FIRST: the first-layer MMAs (A tile `buf` x first-layer weights -> accumulator `buf`) are issued from here, for
       // row f+2 right behind the hidden layer's MMAs of row f (rows counted over all of this CTA's work items)
       int l0_total = 0;
@@ -713,9 +717,9 @@ k_conv_mid(ConvMidArgs a) {
       long long t_a0 = 0;
       const uint64_t l0_da = umma_desc(smem_u32(sA0), CF_LBO_A, 128), l0_db = umma_desc(smem_u32(sW0), CF_LBO_B, 128);
       auto issue_l0 = [&](int buf) {
-        const long long ta = clock64();
+        const long long ta = MLSIM_MMA_CLOCK();
         mbar_wait(&a0full[buf], (a0par >> buf) & 1u);
-        t_a0 += clock64() - ta;
+        t_a0 += MLSIM_MMA_CLOCK() - ta;
         a0par ^= 1u << buf;
         tc_fence_after();
         const uint64_t da = l0_da + (uint64_t)(buf * ((4 * CF_LBO_A) >> 4));
@@ -753,10 +757,10 @@ k_conv_mid(ConvMidArgs a) {
         }
       }
       for (int f = 0; f < total; ++f) {
-        const long long tb = clock64();
+        const long long tb = MLSIM_MMA_CLOCK();
         mbar_wait(&full[stage], full_parity);
         tc_fence_after();
-        const long long tc0 = clock64();
+        const long long tc0 = MLSIM_MMA_CLOCK();
         const uint4 r0 = sRec[2 * stage], r1 = sRec[2 * stage + 1];      // this row's record, prepared by the gate warp
         const uint64_t da = (uint64_t)r0.x | ((uint64_t)r0.y << 32);
         const uint64_t db = (uint64_t)r0.z | ((uint64_t)r0.w << 32);
@@ -777,7 +781,7 @@ k_conv_mid(ConvMidArgs a) {
         pend_tf0 = (int)(r1.z & 0xffffu);
         pend_tf1 = (int)(r1.z >> 16);
         t_full += tc0 - tb;
-        t_issue += clock64() - tc0;
+        t_issue += MLSIM_MMA_CLOCK() - tc0;
         ++t_rows;
         if (++stage == CM_STAGES) { stage = 0; full_parity ^= 1; }
       }
@@ -788,7 +792,7 @@ k_conv_mid(ConvMidArgs a) {
       }
       if (a.dbg != nullptr) {
         unsigned long long* d = a.dbg + (size_t)blockIdx.x * 8;
-        d[0] = (unsigned long long)(clock64() - t_begin);
+        d[0] = (unsigned long long)(MLSIM_MMA_CLOCK() - t_begin);
         d[1] = (unsigned long long)t_a0;                 // FIRST: waiting for the first layer's A tiles (inside `issue`)
         d[2] = (unsigned long long)t_full;
         d[3] = (unsigned long long)t_issue;
@@ -1000,13 +1004,18 @@ int conv_pick_strip(int nx, int ny, int batch, int sm_count) {
 template <int NB, bool LAST>
 static int launch_conv_mid_t(const ConvMidArgs& a, int sm_count, cudaStream_t st) {
   using L = ConvMidSmem<NB>;
-  MLSIM_SET_SMEM_ONCE((k_conv_mid<NB, LAST>), L::TOTAL);
   const int nyt = (a.ny + 127) / 128;
   const int nstrips = (a.nx + a.rs - 1) / a.rs;
   const long nitems = (long)a.batch * nstrips * nyt;
   const long resident = (long)sm_count * (LAST ? 2 : 1);
   const int grid = (int)(nitems < resident ? nitems : resident);
-  MLSIM_CUDA_CHECK(launch_pdl(k_conv_mid<NB, LAST>, dim3(grid), dim3(LAST ? CM_THREADS_LAST : CM_THREADS_MID), (size_t)L::TOTAL, st, a));
+  if (a.dbg != nullptr) {      // mlsim_time_kernel: the instantiation that carries the MMA thread's cycle counters
+    MLSIM_SET_SMEM_ONCE((k_conv_mid<NB, LAST, false, true>), L::TOTAL);
+    MLSIM_CUDA_CHECK(launch_pdl(k_conv_mid<NB, LAST, false, true>, dim3(grid), dim3(LAST ? CM_THREADS_LAST : CM_THREADS_MID), (size_t)L::TOTAL, st, a));
+    return MLSIM_OK;
+  }
+  MLSIM_SET_SMEM_ONCE((k_conv_mid<NB, LAST, false, false>), L::TOTAL);
+  MLSIM_CUDA_CHECK(launch_pdl(k_conv_mid<NB, LAST, false, false>, dim3(grid), dim3(LAST ? CM_THREADS_LAST : CM_THREADS_MID), (size_t)L::TOTAL, st, a));
   return MLSIM_OK;
 }
 
@@ -1015,12 +1024,17 @@ int launch_conv_mid(const ConvMidArgs& a, int sm_count, cudaStream_t st) {
 }
 int launch_conv_mid_fused(const ConvMidArgs& a, int sm_count, cudaStream_t st) {
   using L = ConvMidSmem<64, true>;
-  MLSIM_SET_SMEM_ONCE((k_conv_mid<64, false, true>), L::TOTAL);
   const int nyt = (a.ny + 127) / 128;
   const int nstrips = (a.nx + a.rs - 1) / a.rs;
   const long nitems = (long)a.batch * nstrips * nyt;
   const int grid = (int)(nitems < sm_count ? nitems : sm_count);
-  MLSIM_CUDA_CHECK(launch_pdl(k_conv_mid<64, false, true>, dim3(grid), dim3(CM_THREADS_FUSED), (size_t)L::TOTAL, st, a));
+  if (a.dbg != nullptr) {
+    MLSIM_SET_SMEM_ONCE((k_conv_mid<64, false, true, true>), L::TOTAL);
+    MLSIM_CUDA_CHECK(launch_pdl(k_conv_mid<64, false, true, true>, dim3(grid), dim3(CM_THREADS_FUSED), (size_t)L::TOTAL, st, a));
+    return MLSIM_OK;
+  }
+  MLSIM_SET_SMEM_ONCE((k_conv_mid<64, false, true, false>), L::TOTAL);
+  MLSIM_CUDA_CHECK(launch_pdl(k_conv_mid<64, false, true, false>, dim3(grid), dim3(CM_THREADS_FUSED), (size_t)L::TOTAL, st, a));
   return MLSIM_OK;
 }
 int launch_conv_last(const ConvMidArgs& a, int sm_count, cudaStream_t st) {

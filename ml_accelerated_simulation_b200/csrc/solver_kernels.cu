@@ -313,26 +313,29 @@ template <int N> struct RowCfg {
 #define MLSIM_Q512 8
 #define MLSIM_Q1024 4
 #define MLSIM_Q2048 2
+#define MLSIM_Q8192 2
 #define MLSIM_C512 16
 #define MLSIM_C1024 8
 #define MLSIM_C2048 4
 #endif
-  static constexpr int Q = (N <= 256) ? 16 : (N == 512 ? MLSIM_Q512 : (N == 1024 ? MLSIM_Q1024 : (N == 2048 ? MLSIM_Q2048 : (N <= 4096 ? 2 : 1))));
+  static constexpr int Q = (N <= 256) ? 16 : (N == 512 ? MLSIM_Q512 : (N == 1024 ? MLSIM_Q1024 : (N == 2048 ? MLSIM_Q2048 : (N <= 4096 ? 2 : MLSIM_Q8192))));
   // threads per line: N / (smallest radix) runs one butterfly per thread in the narrowest stage; long lines use fewer
   // threads with two butterflies each (smaller CTAs -> more of them per SM, their phases overlap)
 #ifndef MLSIM_TPLF_1024
 // measured on B200 (scripts/ab_solver.py; us per launch at 1024^2 x 16 / 8192^2 x 1): K2 with 64 instead of 128 threads
 // per 1024-point line 70 -> 54, with 512 instead of 1024 per 8192-point line 437 -> 352; K4 gets SLOWER with fewer
 // threads (84 -> 112, 1039 -> 1196: its gradient phase is pure I/O) and keeps one butterfly per thread; the 2048-point
-// column transform with 128 instead of 256 threads per column takes the 8192^2 x-solve from 637 to 511
+// column transform with 128 instead of 256 threads per column takes the 8192^2 x-solve from 637 to 511.
+// 8192-point lines: TWO lines per CTA (K4 then updates three of the four rows it transforms instead of one of two) with
+// 512 threads per line: K4 1038 -> 489 us, K2 (256 threads per line) 352 -> 302 us, solver step 9.37 -> 7.02 ms at 8192^2
 #define MLSIM_TPLF_1024 64
 #define MLSIM_TPLF_2048 128
 #define MLSIM_TPLF_4096 256
-#define MLSIM_TPLF_8192 512
+#define MLSIM_TPLF_8192 256
 #define MLSIM_TPLI_1024 128
 #define MLSIM_TPLI_2048 256
 #define MLSIM_TPLI_4096 256
-#define MLSIM_TPLI_8192 1024
+#define MLSIM_TPLI_8192 512
 #define MLSIM_TPL_COL_1024 32
 #define MLSIM_TPL_COL_2048 128
 #endif

@@ -54,6 +54,13 @@ struct NvtxRange {                     // named ranges arou
 #define MLSIM_PLAIN_ONLY(pl) do { if ((pl)->slab) { set_error("this entry point needs a plain plan (slab_world == 0); use mlsim_slab_*"); return MLSIM_ESTATE; } } while (0)
 #define MLSIM_SLAB_ONLY(pl) do { if (!(pl)->slab) { set_error("this entry point needs a slab plan (slab_world >= 1)"); return MLSIM_ESTATE; } } while (0)
 
+// Length of the in-shared-memory column transforms the split x-transform of grids with nx > 2048 is built from
+// (nx = r0 * MLSIM_SPLIT_N2).  Measured at 8192^2 (scripts/ab_solver.py): 8 x 1024 (the radix-32 column kernel, two CTAs
+// per SM) takes the three x-solve kernels from 454 to 379 us against 4 x 2048.
+#ifndef MLSIM_SPLIT_N2
+#define MLSIM_SPLIT_N2 1024
+#endif
+
 struct mlsim_plan {
   mlsim_config cfg;
   SolverParams sp;
@@ -412,7 +419,8 @@ int mlsim_plan_create(const mlsim_config* cfg, mlsim_plan** out) {
   // readings of the third-party formula differ and neither can be checked here, so it is refused rather than guessed.
   MLSIM_REQUIRE(cfg->forcing_scale == 0.0 || fabs(cfg->ly - 2.0 * 3.14159265358979323846) < 1e-9,
                 "Kolmogorov forcing is defined here for ly = 2*pi only (set forcing_scale = 0 for other domains)");
-  MLSIM_REQUIRE((long)cfg->batch * (cfg->nx > 2048 ? cfg->nx / 2048 : 1) <= 65535, "batch * (nx/2048) must be <= 65535");
+  MLSIM_REQUIRE((long)cfg->batch * (cfg->nx > 2048 ? cfg->nx / MLSIM_SPLIT_N2 : 1) <= 65535,
+                "batch * (number of x sub-transforms) must be <= 65535");
   const bool slab = cfg->slab_world >= 1;
   if (slab) {
     const int W = cfg->slab_world;
@@ -443,7 +451,7 @@ int mlsim_plan_create(const mlsim_config* cfg, mlsim_plan** out) {
   const int nyc = cfg->ny / 2 + 1;
   pl->slab = slab;
   pl->nxg = cfg->nx;
-  pl->r0 = cfg->nx > 2048 ? cfg->nx / 2048 : 1;
+  pl->r0 = cfg->nx > 2048 ? cfg->nx / MLSIM_SPLIT_N2 : 1;
   pl->n2len = cfg->nx / pl->r0;
   if (slab) {
     const int W = cfg->slab_world;

@@ -316,7 +316,7 @@ template <int N> struct RowCfg {
 #define MLSIM_Q8192 2
 #define MLSIM_C512 16
 #define MLSIM_C1024 8
-#define MLSIM_C2048 4
+#define MLSIM_C2048 8
 #endif
   static constexpr int Q = (N <= 256) ? 16 : (N == 512 ? MLSIM_Q512 : (N == 1024 ? MLSIM_Q1024 : (N == 2048 ? MLSIM_Q2048 : (N <= 4096 ? 2 : MLSIM_Q8192))));
   // threads per line: N / (smallest radix) runs one butterfly per thread in the narrowest stage; long lines use fewer
@@ -325,7 +325,10 @@ template <int N> struct RowCfg {
 // measured on B200 (scripts/ab_solver.py; us per launch at 1024^2 x 16 / 8192^2 x 1): K2 with 64 instead of 128 threads
 // per 1024-point line 70 -> 54, with 512 instead of 1024 per 8192-point line 437 -> 352; K4 gets SLOWER with fewer
 // threads (84 -> 112, 1039 -> 1196: its gradient phase is pure I/O) and keeps one butterfly per thread; the 2048-point
-// column transform with 128 instead of 256 threads per column takes the 8192^2 x-solve from 637 to 511.
+// column transform with 128 instead of 256 threads per column takes the 8192^2 x-solve from 637 to 511; 64 threads per
+// column and 8 instead of 4 columns per CTA (64-byte row segments) 513 -> 454.
+// Tried and dropped: every K2 / K4 CTA issuing bulk L2 prefetches (cp.async.bulk.prefetch.L2) of the rows the CTA one
+// GPU-wide wave later will load -- K2 304 -> 334, K4 490 -> 550 us at 8192^2, 60 -> 63 / 85 -> 94 us at 1024^2 x 16.
 // 8192-point lines: TWO lines per CTA (K4 then updates three of the four rows it transforms instead of one of two) with
 // 512 threads per line: K4 1038 -> 489 us, K2 (256 threads per line) 352 -> 302 us, solver step 9.37 -> 7.02 ms at 8192^2
 #define MLSIM_TPLF_1024 64
@@ -337,7 +340,7 @@ template <int N> struct RowCfg {
 #define MLSIM_TPLI_4096 256
 #define MLSIM_TPLI_8192 512
 #define MLSIM_TPL_COL_1024 32
-#define MLSIM_TPL_COL_2048 128
+#define MLSIM_TPL_COL_2048 64
 #endif
   // forward (K2) and inverse (K4) row kernels are tuned separately
   static constexpr int TPLF = (N == 1024) ? MLSIM_TPLF_1024 : (N == 2048) ? MLSIM_TPLF_2048 : (N == 4096) ? MLSIM_TPLF_4096

@@ -37,7 +37,8 @@ HALO = 8          # halo rows on each side of a field buffer (MLSIM_SLAB_HALO)
 CNN_HALO = 7      # rows of state the 7-layer 3x3 network needs from each interior neighbour
 STAGE_HALO_LO = 3
 STAGE_HALO_HI = 2
-MAX_COL_FFT = 2048
+MAX_COL_FFT = 2048   # longest x-transform done inside shared memory by one column kernel
+SPLIT_N2 = 1024      # grids longer than that: nx = r0 * SPLIT_N2 (MLSIM_SPLIT_N2 in csrc/plan.cu)
 
 
 @dataclasses.dataclass(frozen=True)
@@ -89,7 +90,7 @@ class SlabGeometry:
 
     @property
     def r0(self) -> int:           # outer radix of the split x-transform
-        return max(1, self.nx // MAX_COL_FFT)
+        return self.nx // SPLIT_N2 if self.nx > MAX_COL_FFT else 1
 
     def field_shape(self):
         return (2, self.batch, self.ext_rows, self.ny)

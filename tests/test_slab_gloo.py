@@ -87,7 +87,7 @@ def test_multi_rank_gloo_slab_matches_oracle(tmp_path, world, nx, ny, r0, with_c
 
 def test_geometry_config5():
     g = SlabGeometry(nx=8192, ny=8192, batch=1, rank=7, world=8)
-    assert (g.nxl, g.ext_rows, g.nyc, g.kyw, g.kywp, g.ky0, g.kyv, g.r0) == (1024, 1040, 4097, 513, 516, 3591, 506, 4)
+    assert (g.nxl, g.ext_rows, g.nyc, g.kyw, g.kywp, g.ky0, g.kyv, g.r0) == (1024, 1040, 4097, 513, 516, 3591, 506, 8)
     assert sum(SlabGeometry(8192, 8192, 1, r, 8).kyv for r in range(8)) == 4097
     with pytest.raises(ValueError):
         SlabGeometry(nx=64, ny=64, batch=1, rank=0, world=4)         # 16 rows per rank

@@ -468,6 +468,14 @@ def run_ours(args):
     _, my_batch = ensemble.shard_batch(BATCH * world, rank, world)
     assert my_batch == BATCH
 
+    # ---------------- solver-only passes first, while the GPU is still at its boost clocks ----------------
+    # (scripts/solver_pass_probe.py: directly after ~100 CNN-heavy steps the power-capped clock state makes the same pass
+    # read 0.34 instead of 0.28-0.29 ms; that second reading is kept below as ms_per_step_after_cnn_passes)
+    solver_dram = _solver_dram_roofline(dev, local, peaks, ensemble) if (NX, BATCH) == (256, 64) else None
+    us, vs = u0.clone(), v0.clone()
+    plan.step(us, vs, nsteps=max(W, 3), apply_cnn=False)
+    solver_ms = _timed_steps(lambda: plan.step(us, vs, nsteps=K, apply_cnn=False), K, dev, ensemble)[0] / K
+
     # ---------------- device-resident throughput (value): production regime, no profiling events inside ----------------
     plan.step(u, v, nsteps=W, apply_cnn=True)
     ensemble.barrier(dev)
@@ -490,9 +498,9 @@ def run_ours(args):
     cnn_ms_per_step = sum(t for t, _ in conv.values()) / kp
 
     # ---------------- solver-only pass: HBM roofline of the stencil + projection (no correction add: 296 B) ----------------
-    us, vs = u0.clone(), v0.clone()
+    us.copy_(u0); vs.copy_(v0)
     plan.step(us, vs, nsteps=3, apply_cnn=False)
-    solver_ms = _timed_steps(lambda: plan.step(us, vs, nsteps=K, apply_cnn=False), K, dev, ensemble)[0] / K
+    solver_ms_hot = _timed_steps(lambda: plan.step(us, vs, nsteps=K, apply_cnn=False), K, dev, ensemble)[0] / K
 
     # ---------------- end to end through host buffers (e2e) ----------------
     hu, hv = u0.cpu().pin_memory(), v0.cpu().pin_memory()
@@ -512,9 +520,6 @@ def run_ours(args):
     plan.close()
     del plan, u, v, us, vs
     torch.cuda.empty_cache()
-
-    # ---------------- solver at a DRAM-resident size (configs[2]) ----------------
-    solver_dram = _solver_dram_roofline(dev, local, peaks, ensemble) if (NX, BATCH) == (256, 64) else None
 
     # ---------------- BASELINE configs[4]: one 8192^2 grid in x-slabs over the N GPUs, + multi-rank parity self-check ----------------
     slab = slab_parity = None
@@ -570,6 +575,9 @@ def run_ours(args):
                             "bytes_per_cell_step": SOLVER_BYTES_PER_CELL_STEP,
                             "achieved": solver_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s (algorithmic bytes / time)",
                             "frac": solver_gbs / peaks["hbm_gbs"],
+                            "timing": f"{K} steps before the CNN passes (boost clocks)",
+                            "ms_per_step_after_cnn_passes": solver_ms_hot,
+                            "frac_after_cnn_passes": SOLVER_BYTES_PER_CELL_STEP * cells / (solver_ms_hot * 1e-3) / 1e9 / peaks["hbm_gbs"],
                             "note": "algorithmic 296 B/cell-step against the HBM copy peak; the 33.5 MB state is L2-resident at "
                                     "this config, so this is an accounting unit -- see solver_roofline_dram for a DRAM-resident size"},
         "solver_roofline_dram": solver_dram,

@@ -351,6 +351,11 @@ int solver_blocks(const mlsim_plan* pl, int apply_cnn, int nb) {
     const long cells = (long)nb * pl->cfg.nx * pl->cfg.ny;
     const long cap = cells / 200000;
     if (ns > cap) ns = (int)(cap < 1 ? 1 : cap);
+    // Four blocks are 64 launches per bare solver step.  With blocks of ~1M cells (config 2: 256^2 x 16) the kernels are
+    // 5-10 us each and the launching thread becomes the limit (scripts/solver_pass_probe.py at 256^2 x 64: host enqueue
+    // 0.26-0.30 ms per step for 0.29-0.31 ms of device time with four blocks; 0.10 ms for 0.28-0.29 ms with two).  Four
+    // blocks only where a block keeps >= 2M cells (1024^2 x 16 and larger).
+    if (ns > 2 && cells / ns < 2000000) ns = 2;
   }
   if (ns > mlsim_plan::MAX_SPLIT) ns = mlsim_plan::MAX_SPLIT;
   if (ns > nb) ns = nb;

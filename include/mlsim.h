@@ -53,7 +53,7 @@ typedef struct {
   /* Execution tuning (0 = the measured default for the shape).  Results do not depend on these: trajectories are
    * independent, so the block structure only changes how launches overlap. */
   int32_t solver_blocks;          /* 1..8: independent batch blocks whose solver steps run on separate streams
-                                   * (default: 2 when the correction network follows every step, 4 for bare solver rollouts) */
+                                   * (default: 2; 4 for bare solver rollouts whose blocks keep >= 2M cells; 1 below 400k cells) */
   int32_t host_blocks;            /* 1..8: equal batch blocks of the H2D | step | D2H pipeline of mlsim_rollout_host
                                    * (default: sized in whole rounds of the persistent conv grid) */
   int32_t separate_first_layer;   /* 0 (default): the network's first layer (2 -> 64) is computed inside the first hidden
@@ -62,6 +62,11 @@ typedef struct {
   int32_t cluster_projection;     /* 1: single-kernel projection (thread-block cluster per image, half spectrum in
                                    * distributed shared memory); plain square 64 / 128 / 256 grids only.  Measured slower
                                    * than the three-kernel projection at every BASELINE config, hence off by default */
+  int32_t step_graph;             /* 1: mlsim_step / mlsim_step_f64 replay a captured CUDA graph of {solver step; correction}
+                                   * (the same kernels, arguments and order: results are bit-identical) once the same
+                                   * (u, v, p, apply_cnn, scale) has been stepped twice.  Saves host enqueue time only
+                                   * (device time unchanged, measured), hence 0 = eager launches by default.  Not used
+                                   * while in-step profiling or the finite guard are enabled */
 } mlsim_config;
 
 int  mlsim_plan_create (const mlsim_config* cfg, mlsim_plan** out);
@@ -190,6 +195,8 @@ int  mlsim_finite_check_read(mlsim_plan* plan, int64_t* first_bad_step, int64_t*
 /* ---- introspection ---- */
 /* number of kernel launches one mlsim_step(nsteps=1) issues (solver only, or solver + cnn) */
 int  mlsim_launches_per_step(mlsim_plan* plan, int32_t apply_cnn);
+/* number of cudaGraphLaunch calls mlsim_step / mlsim_step_f64 have issued so far (mlsim_config.step_graph); -1: null plan */
+int64_t mlsim_step_graph_launches(mlsim_plan* plan);
 /* bytes of device workspace owned by the plan */
 int64_t mlsim_workspace_bytes(mlsim_plan* plan);
 /* time one kernel class in isolation with CUDA events on `stream`: which = 0 explicit terms (stage 2

@@ -25,7 +25,7 @@ class MlsimConfig(C.Structure):
         ("device", C.c_int32),
         ("slab_rank", C.c_int32), ("slab_world", C.c_int32),
         ("solver_blocks", C.c_int32), ("host_blocks", C.c_int32), ("separate_first_layer", C.c_int32),
-        ("cluster_projection", C.c_int32),
+        ("cluster_projection", C.c_int32), ("step_graph", C.c_int32),
     ]
 
 
@@ -70,6 +70,7 @@ _SIGNATURES = {
     "mlsim_finite_check_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "mlsim_finite_check_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mlsim_launches_per_step": (C.c_int, [C.c_void_p, C.c_int32]),
+    "mlsim_step_graph_launches": (C.c_int64, [C.c_void_p]),
     "mlsim_workspace_bytes": (C.c_int64, [C.c_void_p]),
     "mlsim_time_kernel": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_void_p]),
     "mlsim_conv_debug": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),

@@ -42,6 +42,7 @@ class PlanConfig:
     host_blocks: int = 0
     fuse_first_layer: bool = True        # first conv layer computed inside the first hidden layer's kernel (when the net allows)
     cluster_projection: bool = False
+    step_graph: bool = False             # replay a captured CUDA graph of the step (saves host enqueue time only)
 
     def resolved_dt(self) -> float:
         if self.dt is not None:
@@ -65,7 +66,8 @@ class Plan:
         c = _lib.MlsimConfig(cfg.nx, cfg.ny, cfg.batch, cfg.lx, cfg.ly, self.dt, cfg.viscosity, cfg.density,
                              cfg.drag, cfg.forcing_wavenumber, cfg.forcing_scale, ADVECTION[cfg.advection],
                              cfg.lw_dt_scale, cfg.device, cfg.slab_rank, cfg.slab_world, cfg.solver_blocks,
-                             cfg.host_blocks, int(not cfg.fuse_first_layer), int(cfg.cluster_projection))
+                             cfg.host_blocks, int(not cfg.fuse_first_layer), int(cfg.cluster_projection),
+                             int(cfg.step_graph))
         h = C.c_void_p()
         _lib.check(self._lib.mlsim_plan_create(C.byref(c), C.byref(h)))
         self._h = h
@@ -235,6 +237,10 @@ class Plan:
     # ------------------------------------------------------------------ introspection
     def launches_per_step(self, apply_cnn: bool) -> int:
         return int(self._lib.mlsim_launches_per_step(self._h, int(apply_cnn)))
+
+    def step_graph_launches(self) -> int:
+        """cudaGraphLaunch calls issued by step / step_f64 so far (0 while the plan steps with eager launches)."""
+        return int(self._lib.mlsim_step_graph_launches(self._h))
 
     def workspace_bytes(self) -> int:
         return int(self._lib.mlsim_workspace_bytes(self._h))

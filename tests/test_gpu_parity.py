@@ -805,3 +805,48 @@ def test_rollout_is_deterministic(mlsim, mlacfd):
     assert torch.isfinite(outs[0][0]).all()
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     plan.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nx,batch,cnn", [(64, 1, True), (64, 1, False), (128, 4, True), (256, 16, True), (256, 16, False)])
+def test_step_graph_is_bit_identical_to_eager_launches(mlsim, mlacfd, nx, batch, cnn):
+    """mlsim_config.step_graph: the captured CUDA graph replays the same kernels with the same arguments, so a rollout
+    through it must equal the eager rollout bit for bit -- single steps, the 8-step unrolled graph, a pressure output and
+    a second (u, v) pair (second cache entry).  256^2 x 16 runs its solver part as two batch blocks on two streams, i.e.
+    a multi-stream capture."""
+    import torch
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(nx + batch)
+    u0 = torch.randn(batch, nx, nx, generator=g, device=dev)
+    v0 = torch.randn(batch, nx, nx, generator=g, device=dev)
+    model = None
+    if cnn:
+        from ml_accelerated_simulation_b200 import models
+        model = models.buildModel(mlacfd[0])
+        model.load_state_dict(mlacfd[1])
+    res = {}
+    for tag, sg in (("eager", False), ("graph", True)):
+        plan = mlsim.Plan(mlsim.PlanConfig(nx=nx, ny=nx, batch=batch, step_graph=sg))
+        if cnn:
+            model.attach(plan)
+        u, v = u0.clone(), v0.clone()
+        plan.project(u, v, want_p=False)
+        plan.normalize_speed(u, v, 3.0)
+        p = torch.empty_like(u)
+        for _ in range(3):
+            plan.step(u, v, nsteps=1, apply_cnn=cnn)                  # eager, capture, replay
+        plan.step(u, v, nsteps=19, apply_cnn=cnn)                     # 2 x 8-step graph + 3 x 1-step graph
+        plan.step(u, v, nsteps=1, apply_cnn=cnn, p=p)                   # new key (pressure requested): eager
+        plan.step(u, v, nsteps=2, apply_cnn=cnn, p=p)                   # captured with the pressure output
+        u2, v2 = u.clone() * 0.5, v.clone() * 0.5                     # another pair of buffers: second cache entry
+        for _ in range(3):
+            plan.step(u2, v2, nsteps=2, apply_cnn=cnn)
+        plan.step(u, v, nsteps=1, apply_cnn=cnn)                      # the first entry is still valid
+        torch.cuda.synchronize()
+        res[tag] = (u.clone(), v.clone(), p.clone(), u2.clone(), v2.clone(), plan.step_graph_launches())
+        plan.close()
+    assert res["eager"][5] == 0
+    assert res["graph"][5] == (2 + 5) + 2 + 4 + 1, res["graph"][5]
+    for a, b in zip(res["eager"][:5], res["graph"][:5]):
+        assert bool(torch.isfinite(a).all())
+        assert torch.equal(a, b)

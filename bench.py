@@ -369,7 +369,17 @@ def _slab_measure(n, K, W, p2p, dev, local, rank, world, peaks, model, want_cloc
 
 
 def _slab_parity(dev, local, rank, world, model, cfgj, sd):
-    """Self-check of the multi-rank slab paths on a small grid (512 x 256 over `world` ranks, 3 steps of solver + CNN):
+    """Two grids: 512 x 256 (x-solve inside one column kernel) and 4096 x 64 (split x-transform, the path the 8192^2
+    workload takes).  The top-level keys are the first case's; "long_grid" holds the second; "ok" covers both."""
+    res = _slab_parity_case(512, 256, dev, local, rank, world, model, cfgj, sd)
+    long_grid = _slab_parity_case(4096, 64, dev, local, rank, world, model, cfgj, sd)
+    res["long_grid"] = long_grid
+    res["ok"] = bool(res["ok"] and long_grid["ok"])
+    return res
+
+
+def _slab_parity_case(nx, ny, dev, local, rank, world, model, cfgj, sd):
+    """Self-check of the multi-rank slab paths on a small grid (nx x ny over `world` ranks, 3 steps of solver + CNN):
     both exchange modes (NCCL all-to-all / peer-memory stores) against (i) the single-GPU plain plan run on rank 0 on
     the same input and (ii) the bf16-emulating fp64 oracle on the host (the oracle is the CHECKER here, never timed).
     Tolerances as in tests/test_gpu_slab.py: relL2(slab, plain) <= 1e-6; relL2(slab, oracle) <= 4 relL2(O32, O64) + 1e-6."""
@@ -377,7 +387,7 @@ def _slab_parity(dev, local, rank, world, model, cfgj, sd):
     import torch.distributed as dist
     from ml_accelerated_simulation_b200 import Plan, PlanConfig
     from ml_accelerated_simulation_b200.slab import CudaSlabBackend, SlabComm, SlabGeometry, SlabStepper
-    nx, ny, steps = 512, 256, 3
+    steps = 3
 
     def rel(a, b):
         a, b = a.double().cpu(), b.double().cpu()

@@ -133,16 +133,18 @@ def test_slab_world1_matches_oracle(mlsim, mlacfd, nx, ny, batch):
 
 
 # ------------------------------------------------------------------------------------------ slab mode over NCCL
-@pytest.mark.parametrize("world,p2p", [(2, 0), (4, 0), (2, 1), (4, 1)])
-def test_slab_nccl_matches_single_gpu(built_lib, world, p2p, tmp_path):
-    """p2p = 0: spectral all-to-all over NCCL; p2p = 1: peer-memory stores from the producing kernels + barrier."""
+@pytest.mark.parametrize("world,p2p,nx,ny", [(2, 0, 256, 128), (4, 0, 256, 128), (2, 1, 256, 128), (4, 1, 256, 128),
+                                             (2, 0, 4096, 64), (2, 1, 4096, 64)])
+def test_slab_nccl_matches_single_gpu(built_lib, world, p2p, nx, ny, tmp_path):
+    """p2p = 0: spectral all-to-all over NCCL; p2p = 1: peer-memory stores from the producing kernels + barrier.
+    4096 x 64: the split x-transform (the path of the 8192^2 workload) across ranks."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     out = str(tmp_path / "slab.json")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world + 10 * p2p),
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world + 10 * p2p + (20 if nx > 2048 else 0)),
            os.path.join(ROOT, "tests", "slab_worker.py"),
-           "--nx", "256", "--ny", "128", "--steps", "3", "--out", out, "--p2p", str(p2p)]
+           "--nx", str(nx), "--ny", str(ny), "--steps", "3", "--out", out, "--p2p", str(p2p)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     res = json.load(open(out))

@@ -342,6 +342,10 @@ template <int N> struct RowCfg {
 #define MLSIM_TPL_COL_1024 32
 #define MLSIM_TPL_COL_2048 64
 #endif
+#ifndef MLSIM_K4_UB
+#define MLSIM_K4_UB 4      // K4: columns whose loads are issued together in the gradient phase / the spectrum load
+#define MLSIM_K4_UL 4
+#endif
   // forward (K2) and inverse (K4) row kernels are tuned separately
   static constexpr int TPLF = (N == 1024) ? MLSIM_TPLF_1024 : (N == 2048) ? MLSIM_TPLF_2048 : (N == 4096) ? MLSIM_TPLF_4096
                             : (N == 8192) ? MLSIM_TPLF_8192 : N / RMIN;
@@ -463,7 +467,6 @@ k_irfft_grad(const float2* __restrict__ S, SpecPeers peers, const float* uin, co
   pdl_wait();
   const int b = blockIdx.y;
   const int i0 = blockIdx.x * (2 * Q - 1);
-  constexpr int nyc = N / 2 + 1;
   const int ql = threadIdx.x / TPL, t = threadIdx.x % TPL;
 
   {
@@ -473,17 +476,35 @@ k_irfft_grad(const float2* __restrict__ S, SpecPeers peers, const float* uin, co
     SpecWalk<SLAB> wa, wb;
     wa.init(p, const_cast<float2*>(S), peers, b, ia, t, p.nx + 1);
     wb.init(p, const_cast<float2*>(S), peers, b, ib, t, p.nx + 1);
-    for (int k = t; k < nyc; k += TPL) {
+    // columns t, t + TPL, ... < N/2 in batches of UL: all global loads of a batch are in flight before the first of
+    // them is consumed (ncu, 8192^2: a quarter of the kernel's stall samples sat on the first use of A / B)
+    static_assert((N / 2) % TPL == 0, "threads per line must divide N/2");
+    constexpr int MAIN = (N / 2) / TPL;
+    constexpr int UL = (MAIN % MLSIM_K4_UL == 0) ? MLSIM_K4_UL : ((MAIN % 2 == 0) ? 2 : 1);
+    for (int it = 0; it < MAIN; it += UL) {
+      float2 A[UL], B[UL];
+#pragma unroll
+      for (int h = 0; h < UL; ++h) {
+        A[h] = __ldg(wa.ptr());
+        B[h] = __ldg(wb.ptr());
+        wa.advance(TPL, peers);
+        wb.advance(TPL, peers);
+      }
+#pragma unroll
+      for (int h = 0; h < UL; ++h) {
+        const int k = t + (it + h) * TPL;
+        if (k == 0) {
+          buf[fidx<Q>(0, ql)] = make_float2(A[h].x, B[h].x);          // c2r ignores Im of DC / Nyquist
+        } else {
+          buf[fidx<Q>(k, ql)] = make_float2(A[h].x - B[h].y, A[h].y + B[h].x);
+          buf[fidx<Q>(N - k, ql)] = make_float2(A[h].x + B[h].y, B[h].x - A[h].y);
+        }
+      }
+    }
+    if (t == 0) {                                                      // Nyquist column (the walkers stand on it now)
       const float2 A = __ldg(wa.ptr());
       const float2 B = __ldg(wb.ptr());
-      if (k == 0 || k == N / 2) {
-        buf[fidx<Q>(k, ql)] = make_float2(A.x, B.x);          // c2r ignores Im of DC / Nyquist
-      } else {
-        buf[fidx<Q>(k, ql)] = make_float2(A.x - B.y, A.y + B.x);
-        buf[fidx<Q>(N - k, ql)] = make_float2(A.x + B.y, B.x - A.y);
-      }
-      wa.advance(TPL, peers);
-      wb.advance(TPL, peers);
+      buf[fidx<Q>(N / 2, ql)] = make_float2(A.x, B.x);
     }
   }
   __syncthreads();
@@ -520,29 +541,43 @@ k_irfft_grad(const float2* __restrict__ S, SpecPeers peers, const float* uin, co
           if (on[k]) pp[k * N + y] = pr[k];
       }
     } else
-    for (int y = ty; y < N; y += TPG) {
-      float uo[4], vo[4];
+    {
+      // UB columns per pass: the (possibly in-place) stores of one column would otherwise fence the next column's loads
+      // behind them -- one exposed DRAM latency per column (ncu, 8192^2: 30 % of the stall samples on the first store)
+      constexpr int ITERS = N / TPG;
+      constexpr int UB = (ITERS % MLSIM_K4_UB == 0) ? MLSIM_K4_UB : ((ITERS % 2 == 0) ? 2 : 1);
+      for (int y0 = ty; y0 < N; y0 += UB * TPG) {
+        float uo[UB][4], vo[UB][4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (on[k]) {
-          uo[k] = pu[k * N + y];
-          vo[k] = pv[k * N + y];
+        for (int h = 0; h < UB; ++h) {
+          const int y = y0 + h * TPG;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (on[k]) {
+              uo[h][k] = pu[k * N + y];
+              vo[h][k] = pv[k * N + y];
+            }
+          }
         }
-      }
-      const int yn = (y + 1) & (N - 1);
-      const float2 A0 = buf[fidx<Q>(y, q0)];
-      const float2 A1 = (q0 + 1 < Q) ? buf[fidx<Q>(y, q0 + 1)] : make_float2(0.f, 0.f);
-      const float2 A2 = (q0 + 2 < Q) ? buf[fidx<Q>(y, q0 + 2)] : make_float2(0.f, 0.f);
-      const float2 B0 = buf[fidx<Q>(yn, q0)];
-      const float2 B1 = (q0 + 1 < Q) ? buf[fidx<Q>(yn, q0 + 1)] : make_float2(0.f, 0.f);
-      const float pr[5] = {A0.x, A0.y, A1.x, A1.y, A2.x};
-      const float py[4] = {B0.x, B0.y, B1.x, B1.y};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (!on[k]) continue;
-        ou[k * N + y] = uo[k] - (pr[k + 1] - pr[k]) * p.inv_hx;
-        ov[k * N + y] = vo[k] - (py[k] - pr[k]) * p.inv_hy;
-        if (pp) pp[k * N + y] = pr[k];
+        for (int h = 0; h < UB; ++h) {
+          const int y = y0 + h * TPG;
+          const int yn = (y + 1) & (N - 1);
+          const float2 A0 = buf[fidx<Q>(y, q0)];
+          const float2 A1 = (q0 + 1 < Q) ? buf[fidx<Q>(y, q0 + 1)] : make_float2(0.f, 0.f);
+          const float2 A2 = (q0 + 2 < Q) ? buf[fidx<Q>(y, q0 + 2)] : make_float2(0.f, 0.f);
+          const float2 B0 = buf[fidx<Q>(yn, q0)];
+          const float2 B1 = (q0 + 1 < Q) ? buf[fidx<Q>(yn, q0 + 1)] : make_float2(0.f, 0.f);
+          const float pr[5] = {A0.x, A0.y, A1.x, A1.y, A2.x};
+          const float py[4] = {B0.x, B0.y, B1.x, B1.y};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (!on[k]) continue;
+            ou[k * N + y] = uo[h][k] - (pr[k + 1] - pr[k]) * p.inv_hx;
+            ov[k * N + y] = vo[h][k] - (py[k] - pr[k]) * p.inv_hy;
+            if (pp) pp[k * N + y] = pr[k];
+          }
+        }
       }
     }
   }

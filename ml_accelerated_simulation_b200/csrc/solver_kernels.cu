@@ -92,14 +92,31 @@ k_explicit_rk(StageArgs a, SolverParams p, const float* __restrict__ forcing) {
   // ---- load the (TX+4) x (TY+8) halo tile, periodic wrap, float4 granules ----
   constexpr int W4 = SW / 4;
   const int ny4 = p.ny >> 2;
-  for (int idx = threadIdx.x; idx < SH * W4; idx += K1_THREADS) {
-    const int r = idx / W4, c4 = idx - r * W4;
-    const int gi = SLAB ? max(-p.halo, min(i0 - K1_HALO + r, p.nx + p.halo - 1)) : ((i0 - K1_HALO + r) & (p.nx - 1));
-    const int gc = ((j0 >> 2) - 1 + c4) & (ny4 - 1);
-    const float4 vu = __ldg(reinterpret_cast<const float4*>(gu + (ptrdiff_t)gi * p.ny) + gc);
-    const float4 vv = __ldg(reinterpret_cast<const float4*>(gv + (ptrdiff_t)gi * p.ny) + gc);
-    reinterpret_cast<float4*>(su + r * SW)[c4] = vu;
-    reinterpret_cast<float4*>(sv + r * SW)[c4] = vv;
+  // all of a thread's granules are requested before the first one is stored to shared memory (ncu at 1024^2 x 16: a
+  // quarter of K1's stall samples sat on the store that followed each pair of loads)
+  {
+    constexpr int NIT = (SH * W4 + K1_THREADS - 1) / K1_THREADS;
+    float4 tu[NIT], tv[NIT];
+#pragma unroll
+    for (int q = 0; q < NIT; ++q) {
+      const int idx = threadIdx.x + q * K1_THREADS;
+      if (idx < SH * W4) {
+        const int r = idx / W4, c4 = idx - r * W4;
+        const int gi = SLAB ? max(-p.halo, min(i0 - K1_HALO + r, p.nx + p.halo - 1)) : ((i0 - K1_HALO + r) & (p.nx - 1));
+        const int gc = ((j0 >> 2) - 1 + c4) & (ny4 - 1);
+        tu[q] = __ldg(reinterpret_cast<const float4*>(gu + (ptrdiff_t)gi * p.ny) + gc);
+        tv[q] = __ldg(reinterpret_cast<const float4*>(gv + (ptrdiff_t)gi * p.ny) + gc);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NIT; ++q) {
+      const int idx = threadIdx.x + q * K1_THREADS;
+      if (idx < SH * W4) {
+        const int r = idx / W4, c4 = idx - r * W4;
+        reinterpret_cast<float4*>(su + r * SW)[c4] = tu[q];
+        reinterpret_cast<float4*>(sv + r * SW)[c4] = tv[q];
+      }
+    }
   }
   __syncthreads();
 
@@ -342,6 +359,9 @@ template <int N> struct RowCfg {
 #define MLSIM_TPL_COL_1024 32
 #define MLSIM_TPL_COL_2048 64
 #endif
+#ifndef MLSIM_K2_UNROLL
+#define MLSIM_K2_UNROLL 8  // K2: columns of the divergence phase whose loads are in flight together
+#endif
 #ifndef MLSIM_K4_UB
 #define MLSIM_K4_UB 4      // K4: columns whose loads are issued together in the gradient phase / the spectrum load
 #define MLSIM_K4_UL 4
@@ -414,10 +434,11 @@ k_div_rfft(const float* __restrict__ u, const float* __restrict__ v, float2* __r
     const float* __restrict__ ru = u + (ptrdiff_t)b * p.img_stride + (ptrdiff_t)i * N;
     const float* __restrict__ rv = v + (ptrdiff_t)b * p.img_stride + (ptrdiff_t)i * N;
     const float* __restrict__ rum = u + (ptrdiff_t)b * p.img_stride + (ptrdiff_t)im * N;
+    constexpr int K2U = MLSIM_K2_UNROLL;
     if (p.raw) {                    // plain transform of the field itself (spectral filter path)
       for (int j = t; j < N; j += TPL) buf[fidx<Q>(j, ql)] = make_float2(ru[j], ru[N + j]);
     } else
-#pragma unroll 4
+#pragma unroll K2U
     for (int j = t; j < N; j += TPL) {
       const int jm = (j - 1) & (N - 1);
       const float um = rum[j];

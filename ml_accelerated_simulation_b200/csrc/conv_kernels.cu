@@ -522,6 +522,12 @@ __device__ __forceinline__ void conv_first_halo(const ConvMidArgs& a, uint8_t* s
   }
 }
 
+// rows ahead of the accumulator drain at which the last layer fetches the state it corrects (u, v)
+#ifndef MLSIM_LAST_AHEAD
+#define MLSIM_LAST_AHEAD 4
+#endif
+constexpr int LAST_AHEAD = MLSIM_LAST_AHEAD;
+
 template <int NB, bool LAST, bool FIRST = false, bool TIMED = false>
 __global__ void __launch_bounds__(LAST ? CM_THREADS_LAST : (FIRST ? CM_THREADS_FUSED : CM_THREADS_MID), LAST ? 2 : 1)
 k_conv_mid(ConvMidArgs a) {
@@ -829,18 +835,11 @@ k_conv_mid(ConvMidArgs a) {
       const int x0 = strip * a.rs;
       const int x1 = min(x0 + a.rs, a.nx);
       const int y = yt * 128 + quarter * 32 + lane;
-      for (int x = x0; x < x1; ++x) {
-        // last layer: fetch the state this row's correction is added to BEFORE waiting for the accumulator, so the
-        // global-load latency hides behind the wait instead of serialising the epilogue
-        float u_old = 0.0f, v_old = 0.0f;
+      // one output row: wait for its accumulator, drain it, write the row.  Last layer: (u_old, v_old) is the state the
+      // correction is added to, fetched by the caller several rows ahead.
+      auto drain_row = [&](const int x, float u_old, float v_old) {
         uint4 rres[LAST ? 1 : 4];                         // mid layers: shortcut operand, fetched before the accumulator wait
-        if constexpr (LAST) {
-          if (a.y_nchw == nullptr && y < a.ny) {
-            const size_t off0 = (size_t)b * a.img_stride + (size_t)x * a.ny + y;
-            u_old = a.u[off0];
-            v_old = a.v[off0];
-          }
-        } else {
+        if constexpr (!LAST) {
           if (a.res_mode == 1 && y < a.ny) {
             const uint8_t* rrow = reinterpret_cast<const uint8_t*>(a.res) +
                                   ((((size_t)b * a.nx + x) * 8 + (size_t)(half * 4)) * plane + (size_t)(y + 1)) * 16;
@@ -965,6 +964,38 @@ k_conv_mid(ConvMidArgs a) {
           }
         }
         slot = (slot + 1 == RING) ? 0 : slot + 1;
+      };
+      if constexpr (LAST) {
+        // The state rows are fetched LAST_AHEAD rows before they are added to.  Fetching a row at the top of its own
+        // iteration (round 1) left the load latency exposed whenever the accumulator was already waiting: ncu put 26 %
+        // of this kernel's stall samples on the correction add, and the epilogue, not the tensor pipe, set the row time.
+        constexpr int D = LAST_AHEAD;
+        const bool add = (a.y_nchw == nullptr) && (y < a.ny);
+        const float* pu = a.u + (size_t)b * a.img_stride + y;
+        const float* pv = a.v + (size_t)b * a.img_stride + y;
+        float uq[D], vq[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const bool on = add && (x0 + d < x1);
+          uq[d] = on ? pu[(size_t)(x0 + d) * a.ny] : 0.0f;
+          vq[d] = on ? pv[(size_t)(x0 + d) * a.ny] : 0.0f;
+        }
+        for (int xg = x0; xg < x1; xg += D) {
+          float un[D], vn[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            const bool on = add && (xg + D + d < x1);
+            un[d] = on ? pu[(size_t)(xg + D + d) * a.ny] : 0.0f;
+            vn[d] = on ? pv[(size_t)(xg + D + d) * a.ny] : 0.0f;
+          }
+#pragma unroll
+          for (int d = 0; d < D; ++d)
+            if (xg + d < x1) drain_row(xg + d, uq[d], vq[d]);
+#pragma unroll
+          for (int d = 0; d < D; ++d) { uq[d] = un[d]; vq[d] = vn[d]; }
+        }
+      } else {
+        for (int x = x0; x < x1; ++x) drain_row(x, 0.0f, 0.0f);
       }
     }
     if (a.dbg != nullptr && warp == 2 && lane == 0) {

@@ -932,10 +932,17 @@ int mlsim_rollout_host(mlsim_plan* pl, float* hu, float* hv, float* hp, int32_t 
     const int items_per_img = ((pl->cfg.nx + pl->rs - 1) / pl->rs) * ((pl->cfg.ny + 127) / 128);
     const double round_imgs = (double)pl->sm_count / (items_per_img > 0 ? items_per_img : 1);
     const int total = (int)ceil(B / round_imgs - 1e-9);
-    if (total >= 3) {                                   // [1 round | the bulk | ~a quarter]: measured best at config 2 (9, 37, 18)
-      int last = (total + 2) / 4;
+    if (total >= 3) {
+      // [head | the bulk | tail] in whole rounds.  The copy engines move a trajectory about twice as fast as the SMs
+      // step it, so the bulk's upload hides behind a head of half its size, and the tail's download is the only
+      // transfer left exposed at the end: for batches of 4-8 rounds [2 | bulk | 1] -- config 2: (18, 37, 9), measured
+      // 1.99 ms per step against 2.01-2.07 for (9, 37, 18) and 2.19 for (9, 46, 9) (scripts/e2e_blocks.py); larger
+      // batches keep [1 | bulk | a quarter].
+      const bool small = total >= 4 && total <= 8;
+      int last = small ? 1 : (total + 2) / 4;
       if (last < 1) last = 1;
-      const int e1 = (int)floor(1 * round_imgs + 1e-9), e2 = (int)floor((total - last) * round_imgs + 1e-9);
+      const int first = small ? 2 : 1;
+      const int e1 = (int)floor(first * round_imgs + 1e-9), e2 = (int)floor((total - last) * round_imgs + 1e-9);
       if (e1 >= 1 && e2 > e1 && e2 < B) { nchunks = 3; bounds[0] = 0; bounds[1] = e1; bounds[2] = e2; bounds[3] = B; }
     }
   }

@@ -89,3 +89,18 @@ def test_two_real_rows_in_one_complex_fft():
             zf[n - kk] = (A[kk].real + B[kk].imag) + 1j * (B[kk].real - A[kk].imag)
     back = np.fft.ifft(zf)
     assert np.abs(back.real - a).max() < 1e-12 and np.abs(back.imag - b).max() < 1e-12
+
+
+def test_split_length_is_mirrored_in_slab_py():
+    """slab.SlabGeometry.r0 must follow the rule csrc/plan.cu uses for the outer radix of the split x-transform
+    (mlsim_slab_geometry is compared with it at run time on the GPU; this is the same check without one)."""
+    import os
+    import re
+    from ml_accelerated_simulation_b200 import slab
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "ml_accelerated_simulation_b200", "csrc", "plan.cu")).read()
+    n2 = int(re.search(r"#define MLSIM_SPLIT_N2 (\d+)", src).group(1))
+    assert "cfg->nx > 2048 ? cfg->nx / MLSIM_SPLIT_N2 : 1" in src
+    assert (slab.SPLIT_N2, slab.MAX_COL_FFT) == (n2, 2048)
+    for nx, want in ((256, 1), (2048, 1), (4096, 4096 // n2), (8192, 8192 // n2)):
+        assert slab.SlabGeometry(nx=nx, ny=64, batch=1, rank=0, world=1).r0 == want

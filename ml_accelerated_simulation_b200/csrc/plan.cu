@@ -384,7 +384,8 @@ int run_steps(mlsim_plan* pl, float* u, float* v, float* p_or_null, int nsteps, 
   // overlap where one big launch runs its CTAs in lockstep.  Joined before the correction network.
   // Measured at config 2 (bench.py, 200 steps): solver only 0.307 / 0.287 / 0.284 ms with 1 / 2 / 4 blocks; with the
   // correction network behind every step 1.823 (1) / 1.785 (2) / 1.805 ms (4): each join before the CNN costs a little,
-  // so rollouts with the network use 2 blocks and bare solver rollouts (data generation) 4.
+  // so rollouts with the network use 2 blocks and bare solver rollouts (data generation) 4 -- where a block keeps
+  // >= 2M cells; below that four blocks make the launching thread the limit (solver_blocks above).
   int ns = allow_split ? solver_blocks(pl, apply_cnn, c.nb) : 1;
   for (int s = 0; s < nsteps; ++s) {
     float* pp = (s == nsteps - 1) ? p_or_null : nullptr;

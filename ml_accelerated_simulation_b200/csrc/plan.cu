@@ -435,6 +435,9 @@ void release_graph(mlsim_plan::StepGraph& g) {
   g = mlsim_plan::StepGraph();
 }
 void drop_graphs(mlsim_plan* pl) {
+  bool any = false;
+  for (auto& g : pl->sgraph) any = any || g.one || g.many;
+  if (any) cudaDeviceSynchronize();     // a replay may still be in flight on the caller's stream
   for (auto& g : pl->sgraph) release_graph(g);
 }
 
@@ -481,6 +484,7 @@ int run_steps_graphed(mlsim_plan* pl, float* u, float* v, float* p, int nsteps, 
   if (!g) {
     g = &pl->sgraph[pl->sgraph_next];
     pl->sgraph_next = (pl->sgraph_next + 1) % mlsim_plan::MAX_STEP_GRAPHS;
+    if (g->one || g->many) cudaDeviceSynchronize();       // evicting an entry whose replay may still be in flight
     release_graph(*g);
     g->u = u; g->v = v; g->p = p; g->apply_cnn = apply_cnn; g->scale = scale;
   }
@@ -489,6 +493,8 @@ int run_steps_graphed(mlsim_plan* pl, float* u, float* v, float* p, int nsteps, 
   if (!g->one && capture_steps(pl, u, v, p, 1, apply_cnn, scale, &g->one)) g->failed = true;
   if (!g->failed && nsteps >= UN && !g->many && capture_steps(pl, u, v, p, UN, apply_cnn, scale, &g->many)) g->failed = true;
   if (g->failed) return run_steps(pl, u, v, p, nsteps, apply_cnn, scale, st, all);
+  // (with a pressure output every replayed graph writes p in its last step where the eager loop writes it once, in the
+  // last step of the call: the final content is the same)
   int left = nsteps;
   for (; left >= UN && g->many; left -= UN, ++pl->graph_launches) MLSIM_CUDA_CHECK(cudaGraphLaunch(g->many, st));
   for (; left > 0; --left, ++pl->graph_launches) MLSIM_CUDA_CHECK(cudaGraphLaunch(g->one, st));
